@@ -1,0 +1,156 @@
+// ctx.h -- internal state of libcdmft_b200 (not part of the ABI).
+// The reference keeps the active sector in module globals (ED_HAMILTONIAN_COMMON.f90:11-20,
+// ED_VARS_GLOBAL.f90:142-146,286-306); this is the same thing as one C++ singleton.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cdmft_b200.h"
+
+namespace cb {
+
+struct Term {  // h(a,b) c^+_a c_b, a != b, 0-based bit positions inside one spin's string
+  int32_t a, b;
+  double re, im;
+};
+
+// Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).
+struct SpinOp {
+  int32_t npart = 0;        // Nup or Ndw
+  int64_t n = 0;            // DimUp or DimDw
+  int32_t *map = nullptr;   // [n] ascending Ns-bit integers with popcount npart (device)
+  int32_t *lin_lo = nullptr, *lin_hi = nullptr;  // Lin tables: rank(s) = lin_hi[s>>L] + lin_lo[s & (2^L-1)]
+  double *f = nullptr;      // [n] spin-local part of the diagonal (device)
+  // one-body hop terms (device copy) -- used by the CSR builder and the matrix-free kernels
+  Term *terms = nullptr;
+  int32_t nterms = 0;
+  bool real_h = true;
+  // canonical CSR (mode SPARSE): rows ascending, cols ascending 0-based
+  int64_t nnz = 0;
+  int32_t *rowptr = nullptr;  // [n+1]
+  int32_t *col = nullptr;     // [nnz]
+  double2 *val = nullptr;     // [nnz]
+  // ELL copy, column-major (k*n + i), row lengths in rowlen: coalesced for row-per-thread kernels
+  int32_t ell_w = 0;
+  int32_t *ell_col = nullptr;
+  double2 *ell_val = nullptr;
+  int32_t *rowlen = nullptr;
+};
+
+struct Split {  // first (n mod P) ranks get one more (ED_HAMILTONIAN.f90:92-105)
+  int64_t q, off;
+};
+inline Split split_of(int64_t n, int P, int r) {
+  int64_t q = n / P, rem = n % P;
+  if (r < rem) return {q + 1, (int64_t)r * (q + 1)};
+  return {q, (int64_t)r * q + rem};
+}
+
+// one rank's share of the active sector (SPMD: exactly one; sim: all P)
+struct RankState {
+  int rank = 0;
+  Split dw{};  // owned columns of v(DimUp, DimDw)      (mpiQdw, offset)
+  Split up{};  // owned rows in the transposed layout   (mpiQup, offset)
+  int64_t nloc = 0;
+  double2 *vt = nullptr, *hvt = nullptr;  // transposed work vectors [DimDw * up.q]
+  double2 *sendbuf = nullptr, *recvbuf = nullptr;  // NCCL staging (SPMD only)
+};
+
+struct Options {
+  int64_t colpass_variant = 0;  // 0 = auto
+  int64_t rowpass_variant = 0;
+  int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
+  int64_t col_batch = 4;
+  int64_t row_slab = 256;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = 0;
+  int nranks = 1, rank = 0;
+  bool spmd = false, sim = false;
+  void *nccl_comm = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int64_t launches = 0;
+  int sm_count = 148;
+  Options opt;
+
+  // model (host copies)
+  bool have_model = false;
+  cdmft_b200_model m{};
+  std::vector<double> imphloc, hbath, vbath;
+  int32_t ns = 0, nimp = 0, nlso = 0;
+  bool jhflag = false;
+  std::vector<Term> terms_up, terms_dw;
+  bool real_h = true;
+  // diagonal coefficients (host)
+  std::vector<double> e_up, e_dw;   // [Ns]
+  std::vector<double> spair;        // [Nimp*Nimp] same-spin pair interaction (a<b)
+  std::vector<double> wcross;       // [Nimp*Nimp] up-dw density-density
+  double const0 = 0;
+  double *cross_tab = nullptr;      // device [Nimp * 2^Nimp]: T[b][mu] = sum_a W[a][b] n_a(mu)
+
+  // active sector
+  bool hstatus = false;
+  int32_t hsector = 0, mode = CDMFT_B200_SPARSE;
+  int64_t dim = 0, dimup = 0, dimdw = 0;
+  int p_eff = 1;  // min(P, DimDw)
+  SpinOp up, dw;
+  std::vector<RankState> rk;
+  // staging for host-pointer calls
+  double2 *stage_v = nullptr, *stage_hv = nullptr;
+  int64_t stage_n = 0;
+  // Krylov work vectors (allocated lazily)
+  double2 *kv[3] = {nullptr, nullptr, nullptr};
+  int64_t kv_n = 0;
+  double *red = nullptr;       // device reduction scratch
+  double *red_host = nullptr;  // pinned
+};
+
+Ctx &ctx();
+int fail(const char *fmt, ...);
+void set_error(const std::string &s);
+
+#define CB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return cb::fail("CUDA error %s at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define CB_CHECK(expr)        \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+#define CB_REQUIRE_INIT() \
+  if (!cb::ctx().inited) return cb::fail("cdmft_b200: not initialised (call cdmft_b200_init first)")
+
+// ---- internal entry points shared between translation units ----
+int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
+                  double const_add, bool want_csr);
+void free_spin_op(SpinOp &op);
+int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
+int nccl_allreduce_sum(double *dev_buf, int n);
+int nccl_all_to_all(const double2 *send, double2 *recv, const int64_t *counts_send, const int64_t *offs_send,
+                    const int64_t *counts_recv, const int64_t *offs_recv);
+int nccl_load();
+int ensure_stage(int64_t n);
+bool is_device_ptr(const void *p);
+
+template <typename T>
+inline int dev_alloc(T **p, int64_t n) {
+  *p = nullptr;
+  if (n <= 0) n = 1;
+  cudaError_t e = cudaMalloc((void **)p, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) return fail("cudaMalloc of %lld bytes failed: %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
+  return 0;
+}
+template <typename T>
+inline void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+}  // namespace cb

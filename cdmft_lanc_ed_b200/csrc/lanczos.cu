@@ -1,0 +1,447 @@
+// lanczos.cu -- device-resident Krylov drivers around hxv_device and the Green's-function helpers.
+//
+// Restates the SciFortran SF_SP_LINALG routines the reference wraps around spHtimesV_p
+// (un-vendored dependency, no version pin -- SURVEY.md App. B):
+//   lanczos_iteration / sp_lanc_tridiag   caller ED_GF_NORMAL.f90:215 (and 7 more blocks)
+//   sp_lanc_eigh                          caller ED_DIAG.f90:176-184
+// and from the reference itself
+//   vvinit = c^+_is|gs>, c_is|gs>, mixed channels       ED_GF_NORMAL.f90:180-199,244-266,590-620
+//   add_to_lanczos_gf_normal                              ED_GF_NORMAL.f90:915-975
+// The vectors never leave HBM between iterations; each iteration moves 2 scalars to the host.
+// Dot products use a fixed two-stage reduction tree -> bitwise reproducible run to run.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "ctx.h"
+
+namespace cb {
+
+static const int kRedBlocks = 1024;  // stage-1 partials (fixed => deterministic)
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  return x;
+}
+// block reduction of two doubles; result valid in thread 0
+__device__ __forceinline__ void block_sum2(double &a, double &b) {
+  __shared__ double sa[32], sb[32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = lane < nw ? sa[lane] : 0.0;
+    b = lane < nw ? sb[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// partial[blk] = sum conj(a)*b over the block's grid-stride share
+__global__ void __launch_bounds__(256) k_dot(int64_t n, const double2 *__restrict__ a, const double2 *__restrict__ b,
+                                             double2 *__restrict__ partial) {
+  double re = 0, im = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 x = a[i], y = b[i];
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, im);
+}
+// vout += tmp ; partial <vin, vout>
+__global__ void __launch_bounds__(256) k_add_dot(int64_t n, double2 *__restrict__ vout, const double2 *__restrict__ tmp,
+                                                 const double2 *__restrict__ vin, double2 *__restrict__ partial) {
+  double re = 0, im = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 y = vout[i], t = tmp[i], x = vin[i];
+    y.x += t.x; y.y += t.y;
+    vout[i] = y;
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, im);
+}
+// vout -= alfa*vin ; partial <vout, vout>
+__global__ void __launch_bounds__(256) k_axpy_norm(int64_t n, double2 *__restrict__ vout, const double2 *__restrict__ vin,
+                                                   double alfa, double2 *__restrict__ partial) {
+  double re = 0, im = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 y = vout[i], x = vin[i];
+    y.x -= alfa * x.x; y.y -= alfa * x.y;
+    vout[i] = y;
+    re += y.x * y.x + y.y * y.y;
+  }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
+}
+__global__ void k_reduce_final(int nparts, const double2 *__restrict__ partial, double *__restrict__ out) {
+  double re = 0, im = 0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) { re += partial[i].x; im += partial[i].y; }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) { out[0] = re; out[1] = im; }
+}
+__global__ void __launch_bounds__(256) k_scale(int64_t n, double2 *__restrict__ v, double s) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 x = v[i];
+    v[i] = make_double2(x.x * s, x.y * s);
+  }
+}
+__global__ void __launch_bounds__(256) k_fill(int64_t n, double2 *__restrict__ v, double re) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = make_double2(re, 0.0);
+}
+// tmp=vin; vin=vout/beta; vout=-beta*tmp   (lanczos_iteration, iter>1)
+__global__ void __launch_bounds__(256) k_swap_scale(int64_t n, double2 *__restrict__ vin, double2 *__restrict__ vout,
+                                                    double beta) {
+  const double ib = 1.0 / beta;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 t = vin[i], y = vout[i];
+    vin[i] = make_double2(y.x / beta, y.y / beta);
+    vout[i] = make_double2(-beta * t.x, -beta * t.y);
+  }
+  (void)ib;
+}
+// acc += z * v
+__global__ void __launch_bounds__(256) k_axpy_real(int64_t n, double2 *__restrict__ acc, const double2 *__restrict__ v,
+                                                   double z) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 a = acc[i], x = v[i];
+    acc[i] = make_double2(fma(z, x.x, a.x), fma(z, x.y, a.y));
+  }
+}
+
+static unsigned vec_grid(int64_t n) {
+  Ctx &c = ctx();
+  int64_t nb = (n + 255) / 256;
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)c.sm_count * 8));
+}
+
+// finish a reduction whose stage-1 partials sit in c.red (as double2[kRedBlocks]); all-reduce over
+// ranks in SPMD mode; returns the complex sum on the host.
+static int finish_reduce(std::complex<double> *out) {
+  Ctx &c = ctx();
+  double2 *partial = (double2 *)c.red;
+  double *res = c.red + 2 * kRedBlocks;
+  k_reduce_final<<<1, 256, 0, c.stream>>>(kRedBlocks, partial, res);
+  c.launches++;
+  CB_CHECK(nccl_allreduce_sum(res, 2));
+  CB_CUDA(cudaMemcpyAsync(c.red_host, res, 16, cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  *out = std::complex<double>(c.red_host[0], c.red_host[1]);
+  return 0;
+}
+static int zero_partials() {
+  Ctx &c = ctx();
+  CB_CUDA(cudaMemsetAsync(c.red, 0, 2 * kRedBlocks * sizeof(double), c.stream));
+  return 0;
+}
+static int dot(int64_t n, const double2 *a, const double2 *b, std::complex<double> *out) {
+  Ctx &c = ctx();
+  CB_CHECK(zero_partials());
+  if (n > 0) {
+    k_dot<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, a, b, (double2 *)c.red);
+    c.launches++;
+  }
+  return finish_reduce(out);
+}
+
+static int ensure_kv(int64_t n, int count) {
+  Ctx &c = ctx();
+  if (c.kv_n < n) {
+    for (auto &k : c.kv) dev_free(k);
+    c.kv_n = n;
+  }
+  for (int i = 0; i < count; i++)
+    if (!c.kv[i]) CB_CHECK(dev_alloc(&c.kv[i], c.kv_n));
+  return 0;
+}
+
+static int64_t local_n() {
+  int64_t n = 0;
+  for (auto &r : ctx().rk) n += r.nloc;
+  return n;
+}
+
+// one step of the 3-term recurrence (SciFortran lanczos_iteration)
+static int lanczos_iteration(int64_t n, int iter, double2 *vin, double2 *vout, double2 *tmp, double *alfa, double *beta) {
+  Ctx &c = ctx();
+  std::complex<double> z;
+  if (iter == 1) {
+    CB_CHECK(dot(n, vin, vin, &z));
+    double norm = std::sqrt(z.real());
+    if (norm == 0.0) return fail("LANCZOS_ITERATION: norm(vin)=0");
+    if (n > 0) { k_scale<<<vec_grid(n), 256, 0, c.stream>>>(n, vin, 1.0 / norm); c.launches++; }
+  } else {
+    if (n > 0) { k_swap_scale<<<vec_grid(n), 256, 0, c.stream>>>(n, vin, vout, *beta); c.launches++; }
+  }
+  CB_CHECK(hxv_device(vin, tmp));
+  CB_CHECK(zero_partials());
+  if (n > 0) {
+    k_add_dot<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, vout, tmp, vin, (double2 *)c.red);
+    c.launches++;
+  }
+  CB_CHECK(finish_reduce(&z));
+  *alfa = z.real();
+  CB_CHECK(zero_partials());
+  if (n > 0) {
+    k_axpy_norm<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, vout, vin, *alfa, (double2 *)c.red);
+    c.launches++;
+  }
+  CB_CHECK(finish_reduce(&z));
+  *beta = std::sqrt(z.real());
+  return 0;
+}
+
+// symmetric tridiagonal eigenproblem, implicit-shift QL (what SF_LINALG eigh(diag,subdiag,Ev) gets
+// from LAPACK).  d[n] diagonal, e[n] with e[i] coupling i-1,i (e[0] unused); Z row-major n x n.
+static int tridiag_eigh(int n, std::vector<double> &d, const std::vector<double> &e_in, std::vector<double> *Z) {
+  std::vector<double> e(n + 1, 0.0);
+  for (int i = 1; i < n; i++) e[i - 1] = e_in[i];
+  if (Z) { Z->assign((size_t)n * n, 0.0); for (int i = 0; i < n; i++) (*Z)[(size_t)i * n + i] = 1.0; }
+  auto z = [&](int r, int col) -> double & { return (*Z)[(size_t)r * n + col]; };
+  for (int l = 0; l < n; l++) {
+    for (int iter = 0;; iter++) {
+      int m = l;
+      for (; m < n - 1; m++) {
+        double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+        if (std::fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+      }
+      if (m == l) break;
+      if (iter == 300) return fail("tridiag_eigh: no convergence");
+      double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+      double r = std::hypot(g, 1.0);
+      g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
+      double s = 1.0, cs = 1.0, p = 0.0;
+      int i = m - 1;
+      bool underflow = false;
+      for (; i >= l; i--) {
+        double f = s * e[i], b = cs * e[i];
+        r = std::hypot(f, g);
+        e[i + 1] = r;
+        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; underflow = true; break; }
+        s = f / r; cs = g / r;
+        g = d[i + 1] - p;
+        r = (d[i] - g) * s + 2.0 * cs * b;
+        p = s * r;
+        d[i + 1] = g + p;
+        g = cs * r - b;
+        if (Z)
+          for (int k = 0; k < n; k++) {
+            double t = z(k, i + 1);
+            z(k, i + 1) = s * z(k, i) + cs * t;
+            z(k, i) = cs * z(k, i) - s * t;
+          }
+      }
+      if (underflow) continue;
+      d[l] -= p; e[l] = g; e[m] = 0.0;
+    }
+  }
+  // ascending order
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; i++) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return d[a] < d[b]; });
+  std::vector<double> d2(n);
+  for (int i = 0; i < n; i++) d2[i] = d[idx[i]];
+  if (Z) {
+    std::vector<double> Z2((size_t)n * n);
+    for (int k = 0; k < n; k++)
+      for (int i = 0; i < n; i++) Z2[(size_t)k * n + i] = (*Z)[(size_t)k * n + idx[i]];
+    Z->swap(Z2);
+  }
+  d.swap(d2);
+  return 0;
+}
+
+// c^+_pos / c_pos applied to one spin index of every basis state (ED_GF_NORMAL.f90:180-194)
+__global__ void __launch_bounds__(256) k_apply_op(int64_t idim, int64_t idimup, int64_t jdimup, int ispin, int iop, int pos0,
+                                                  const int32_t *__restrict__ imap, const int32_t *__restrict__ jlo,
+                                                  const int32_t *__restrict__ jhi, int lbits, double2 coef,
+                                                  const double2 *__restrict__ state, double2 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= idim) return;
+  const int64_t iu = i % idimup, id = i / idimup;
+  const uint32_t s = (uint32_t)__ldg(imap + (ispin == 1 ? iu : id));
+  const uint32_t bit = 1u << pos0;
+  const bool occ = (s & bit) != 0;
+  if (iop > 0 ? occ : !occ) return;
+  const double sg = (__popc(s & (bit - 1u)) & 1) ? -1.0 : 1.0;  // c / cdg sign rule, ED_SETUP.f90:807-833
+  const uint32_t r = iop > 0 ? (s | bit) : (s & ~bit);
+  const int64_t jr = __ldg(jhi + (r >> lbits)) + __ldg(jlo + (r & ((1u << lbits) - 1u)));
+  const int64_t j = ispin == 1 ? jr + id * jdimup : iu + jr * jdimup;
+  const double2 x = state[i];
+  double2 o = out[j];
+  o.x += sg * (coef.x * x.x - coef.y * x.y);
+  o.y += sg * (coef.x * x.y + coef.y * x.x);
+  out[j] = o;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, double threshold, double *alanc,
+                               double *blanc, int32_t *ndone) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("lanczos_tridiag: Hsector NOT set");
+  if (nloc != local_n()) return fail("lanczos_tridiag: nloc mismatch");
+  if (threshold <= 0) threshold = 1e-12;
+  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
+  double2 *vin = c.kv[0], *vout = c.kv[1], *tmp = c.kv[2];
+  if (nloc > 0) {
+    CB_CUDA(cudaMemcpyAsync(vin, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
+  }
+  for (int i = 0; i < nitermax; i++) { alanc[i] = 0; blanc[i] = 0; }
+  double a = 0, b = 0;
+  int done = 0;
+  for (int iter = 1; iter <= nitermax; iter++) {
+    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
+    alanc[iter - 1] = a;
+    done = iter;
+    if (std::fabs(b) < threshold) break;
+    if (iter < nitermax) blanc[iter] = b;
+  }
+  if (ndone) *ndone = done;
+  return 0;
+}
+
+int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double threshold, int32_t ncheck, double *egs,
+                          int32_t *niter, double *alanc_out, double *blanc_out) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("lanczos_gs: Hsector NOT set");
+  if (nloc != local_n()) return fail("lanczos_gs: nloc mismatch");
+  if ((int64_t)nitermax > c.dim) nitermax = (int32_t)c.dim;
+  if (ncheck <= 0) ncheck = 10;
+  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
+  const bool dev = is_device_ptr(vect);
+  double2 *vin = c.kv[0], *vout = c.kv[1], *tmp = c.kv[2];
+  double2 *gs = nullptr;  // start vector, later the accumulated eigenvector
+  if (dev) gs = (double2 *)vect;
+  else {
+    CB_CHECK(ensure_stage(std::max<int64_t>(nloc, 1)));
+    gs = c.stage_v;
+    if (nloc > 0) CB_CUDA(cudaMemcpyAsync(gs, vect, (size_t)nloc * 16, cudaMemcpyHostToDevice, c.stream));
+  }
+  std::complex<double> z;
+  CB_CHECK(dot(nloc, gs, gs, &z));
+  if (z.real() == 0.0) {  // SciFortran start vector is unpinned; constant 1/sqrt(Dim)
+    if (nloc > 0) { k_fill<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt((double)c.dim)); c.launches++; }
+  }
+  if (nloc > 0) {
+    CB_CUDA(cudaMemcpyAsync(vin, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
+    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
+  }
+  std::vector<double> al, bl;  // bl[i] couples i-1,i ; bl[0]=0
+  std::vector<double> d, Z;
+  double a = 0, b = 0, esave = 0, e0 = 0;
+  for (int iter = 1; iter <= nitermax; iter++) {
+    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
+    al.push_back(a);
+    if ((int)bl.size() < (int)al.size()) bl.push_back(0.0);
+    if (std::fabs(b) < threshold) break;  // invariant subspace
+    if (iter < nitermax) bl.push_back(b);
+    d = al;
+    std::vector<double> e(bl.begin(), bl.begin() + al.size());
+    CB_CHECK(tridiag_eigh((int)al.size(), d, e, nullptr));
+    e0 = d[0];
+    if ((int)al.size() >= ncheck && std::fabs(e0 - esave) <= threshold) break;
+    esave = e0;
+  }
+  const int nlanc = (int)al.size();
+  d = al;
+  {
+    std::vector<double> e(bl.begin(), bl.begin() + nlanc);
+    CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
+  }
+  e0 = d[0];
+  // second pass: vect = sum_iter vin_iter * Z(iter,1)
+  if (nloc > 0) {
+    CB_CUDA(cudaMemcpyAsync(vin, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
+    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
+    CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * 16, c.stream));
+  }
+  for (int iter = 1; iter <= nlanc; iter++) {
+    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
+    if (nloc > 0) { k_axpy_real<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, vin, Z[(size_t)(iter - 1) * nlanc + 0]); c.launches++; }
+  }
+  CB_CHECK(dot(nloc, gs, gs, &z));
+  if (nloc > 0) { k_scale<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt(z.real())); c.launches++; }
+  if (!dev && nloc > 0) CB_CUDA(cudaMemcpyAsync(vect, gs, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  *egs = e0;
+  if (niter) *niter = nlanc;
+  if (alanc_out) std::copy(al.begin(), al.end(), alanc_out);
+  if (blanc_out) std::copy(bl.begin(), bl.begin() + nlanc, blanc_out);
+  return 0;
+}
+
+int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nops, const int32_t *pos, const double *coef,
+                        const void *state, void *out, int32_t *jsector) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.have_model) return fail("apply_op: no model set");
+  if (c.spmd) return fail("apply_op: single-rank only (gather the state first, ED_EIGENSPACE.f90:499-569)");
+  if (ispin != 1 && ispin != 2) return fail("apply_op: ispin must be 1 or 2");
+  const int ns = c.ns;
+  int nup = (isector - 1) / (ns + 1), ndw = (isector - 1) % (ns + 1);
+  int jnup = nup + (ispin == 1 ? (iop > 0 ? 1 : -1) : 0), jndw = ndw + (ispin == 2 ? (iop > 0 ? 1 : -1) : 0);
+  if (jnup < 0 || jnup > ns || jndw < 0 || jndw > ns) { if (jsector) *jsector = 0; return 0; }  // getCsector = 0
+  if (jsector) *jsector = 1 + jnup * (ns + 1) + jndw;
+  int64_t idimup, idimdw, idim, jdimup, jdimdw, jdim;
+  CB_CHECK(cdmft_b200_get_sector_dims(isector, &idimup, &idimdw, &idim));
+  CB_CHECK(cdmft_b200_get_sector_dims(1 + jnup * (ns + 1) + jndw, &jdimup, &jdimdw, &jdim));
+  SpinOp src, dst;
+  std::vector<Term> none;
+  std::vector<double> e0(ns, 0.0);
+  CB_CHECK(build_spin_op(src, ispin == 1 ? nup : ndw, none, e0, 0.0, false));
+  CB_CHECK(build_spin_op(dst, ispin == 1 ? jnup : jndw, none, e0, 0.0, false));
+  const bool ds = is_device_ptr(state), dd = is_device_ptr(out);
+  double2 *d_state = (double2 *)state, *d_out = (double2 *)out;
+  if (!ds) { CB_CHECK(dev_alloc(&d_state, idim)); CB_CUDA(cudaMemcpyAsync(d_state, state, idim * 16, cudaMemcpyHostToDevice, c.stream)); }
+  if (!dd) CB_CHECK(dev_alloc(&d_out, jdim));
+  CB_CUDA(cudaMemsetAsync(d_out, 0, jdim * 16, c.stream));
+  for (int k = 0; k < nops; k++) {
+    if (pos[k] < 1 || pos[k] > ns) return fail("apply_op: pos out of range");
+    k_apply_op<<<(unsigned)((idim + 255) / 256), 256, 0, c.stream>>>(idim, idimup, jdimup, ispin, iop, pos[k] - 1, src.map,
+                                                                      dst.lin_lo, dst.lin_hi, ns / 2,
+                                                                      make_double2(coef[2 * k], coef[2 * k + 1]), d_state, d_out);
+    c.launches++;
+  }
+  if (!dd) CB_CUDA(cudaMemcpyAsync(out, d_out, jdim * 16, cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  if (!ds) cudaFree(d_state);
+  if (!dd) cudaFree(d_out);
+  free_spin_op(src);
+  free_spin_op(dst);
+  return 0;
+}
+
+int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlanc, const double *alanc, const double *blanc,
+                                 int32_t isign, double zeta, int32_t lmats, const double *wm, double *g, double *poles,
+                                 double *weights) {
+  std::vector<double> d(alanc, alanc + nlanc), e(blanc, blanc + nlanc), Z;
+  CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
+  const std::complex<double> pesoBZ = std::complex<double>(vnorm2[0], vnorm2[1]) / zeta;  // T=0 branch
+  std::complex<double> *gc = (std::complex<double> *)g;
+  for (int j = 0; j < nlanc; j++) {
+    double de = d[j] - ei;
+    std::complex<double> peso = pesoBZ * Z[j] * Z[j];  // Z(1,j): first row
+    if (poles) poles[j] = isign * de;
+    if (weights) { weights[2 * j] = peso.real(); weights[2 * j + 1] = peso.imag(); }
+    for (int i = 0; i < lmats; i++) gc[i] += peso / (std::complex<double>(0.0, wm[i]) - (double)isign * de);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,435 @@
+// sector.cu -- sector Fock maps, per-spin CSR (ED_SPARSE_MATRIX), ED_SPARSE_MAP and the
+// build_Hv_sector / delete_Hv_sector lifecycle as sm_100a kernels.
+//
+// Reference semantics reproduced bit-exactly for the integer objects:
+//   Hs(s)%map   = ascending Ns-bit integers with popcount N      ED_SETUP.f90:749-769
+//   spH0ups/dws = row-wise lists, columns ascending (insertion order of the jup-outermost
+//                 loop of sparse/H_up.f90:1-89 with sp_insert_element, ED_SPARSE_MATRIX.f90:254-284)
+//   sparse_map  = per impurity configuration the bath configurations and sector indices in
+//                 ascending-state order                          ED_SETUP.f90:757-759
+// The scan over 2^Ns integers + recursive binary_search (ED_SETUP.f90:1044-1061) of the
+// reference is replaced by ranking with two Lin tables: rank(s) = hi[s >> L] + lo[s & (2^L-1)].
+#include <algorithm>
+#include <vector>
+
+#include "ctx.h"
+
+namespace cb {
+
+__device__ __forceinline__ int32_t lin_rank(const int32_t *__restrict__ lin_lo, const int32_t *__restrict__ lin_hi,
+                                            int lbits, uint32_t s) {
+  return __ldg(lin_hi + (s >> lbits)) + __ldg(lin_lo + (s & ((1u << lbits) - 1u)));
+}
+
+// one thread per Ns-bit integer: the members of the sector write themselves at their rank
+__global__ void k_sector_map(int ns, int npart, const int32_t *__restrict__ lin_lo, const int32_t *__restrict__ lin_hi,
+                             int lbits, int32_t *__restrict__ map) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (1u << ns)) return;
+  if (__popc(s) != npart) return;
+  map[lin_rank(lin_lo, lin_hi, lbits, s)] = (int32_t)s;
+}
+
+// spin-local diagonal: f(i) = const + sum_p e[p] n_p + sum_{a<b} S[a][b] n_a n_b   (sparse/H_local.f90)
+__global__ void k_spin_diag(int64_t n, const int32_t *__restrict__ map, int ns, int nimp, const double *__restrict__ e,
+                            const double *__restrict__ spair, double const_add, double *__restrict__ f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = (uint32_t)map[i];
+  double acc = const_add;
+  for (int p = 0; p < ns; p++)
+    if ((s >> p) & 1u) acc += e[p];
+  for (int a = 0; a < nimp; a++)
+    if ((s >> a) & 1u)
+      for (int b = a + 1; b < nimp; b++)
+        if ((s >> b) & 1u) acc += spair[a * nimp + b];
+  f[i] = acc;
+}
+
+// fermionic sign of c^+_a c_b on a state: (-1)^(#occupied orbitals strictly between a and b)
+// == sg1*sg2 of c(b,m,k1,sg1); cdg(a,k1,k2,sg2)  (ED_SETUP.f90:807-833)
+__device__ __forceinline__ double hop_sign(uint32_t s, int a, int b) {
+  int lo = min(a, b), hi = max(a, b);
+  uint32_t between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+  return (__popc(s & between) & 1) ? -1.0 : 1.0;
+}
+
+// row lengths: entry (row k2, col m) exists for term (a,b) iff k2 has a occupied and b empty
+__global__ void k_csr_count(int64_t n, const int32_t *__restrict__ map, const Term *__restrict__ terms, int nterms,
+                            int32_t *__restrict__ rowlen) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = (uint32_t)map[i];
+  int cnt = 0;
+  for (int t = 0; t < nterms; t++) {
+    int a = terms[t].a, b = terms[t].b;
+    cnt += (int)(((s >> a) & 1u) & (~(s >> b) & 1u));
+  }
+  rowlen[i] = cnt;
+}
+
+// exclusive scan of row lengths, single block (n <= ~1e6 rows; runs once per sector)
+__global__ void k_exclusive_scan(int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ out) {
+  __shared__ int64_t carry;
+  __shared__ int32_t buf[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    int32_t x = i < n ? in[i] : 0;
+    buf[threadIdx.x] = x;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      int32_t y = threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += y;
+      __syncthreads();
+    }
+    if (i < n) out[i] = (int32_t)(carry + buf[threadIdx.x] - x);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = (int32_t)carry;
+}
+
+// fill rows, then sort each row by column (rows are short: <= nterms entries)
+__global__ void k_csr_fill(int64_t n, const int32_t *__restrict__ map, const int32_t *__restrict__ lin_lo,
+                           const int32_t *__restrict__ lin_hi, int lbits, const Term *__restrict__ terms, int nterms,
+                           const int32_t *__restrict__ rowptr, int32_t *__restrict__ col, double2 *__restrict__ val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = (uint32_t)map[i];
+  int32_t p0 = rowptr[i], p = p0;
+  for (int t = 0; t < nterms; t++) {
+    int a = terms[t].a, b = terms[t].b;
+    if (((s >> a) & 1u) && !((s >> b) & 1u)) {
+      uint32_t m = (s & ~(1u << a)) | (1u << b);  // source state: k2 = c^+_a c_b m
+      double sg = hop_sign(s, a, b);
+      int32_t j = lin_rank(lin_lo, lin_hi, lbits, m);
+      double2 h = make_double2(terms[t].re * sg, terms[t].im * sg);
+      int32_t q = p;  // insertion sort by column
+      while (q > p0 && col[q - 1] > j) {
+        col[q] = col[q - 1];
+        val[q] = val[q - 1];
+        q--;
+      }
+      col[q] = j;
+      val[q] = h;
+      p++;
+    }
+  }
+}
+
+__global__ void k_csr_to_ell(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                             const double2 *__restrict__ val, int ell_w, int32_t *__restrict__ ell_col,
+                             double2 *__restrict__ ell_val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t p0 = rowptr[i], len = rowptr[i + 1] - p0;
+  for (int k = 0; k < ell_w; k++) {
+    bool in = k < len;
+    ell_col[(int64_t)k * n + i] = in ? col[p0 + k] : (int32_t)i;
+    ell_val[(int64_t)k * n + i] = in ? val[p0 + k] : make_double2(0.0, 0.0);
+  }
+}
+
+// ED_SPARSE_MAP (ED_SPARSE_MAP.f90:101-121 via ED_SETUP.f90:757-759): counting pass + ordered fill.
+// States of one impurity configuration appear in ascending sector index, so the position inside
+// the row is the number of earlier sector states with the same impurity bits.
+__global__ void k_spmap_count(int64_t n, const int32_t *__restrict__ map, int nimp, unsigned long long *__restrict__ cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = (uint32_t)map[i];
+  atomicAdd(&cnt[s & ((1u << nimp) - 1u)], 1ull);
+}
+__global__ void k_spmap_fill(int64_t n, const int32_t *__restrict__ map, int ns, int nimp, int npart,
+                             const int64_t *__restrict__ rowptr, const int32_t *__restrict__ binom /*[31*31]*/,
+                             int32_t *__restrict__ bath_state, int32_t *__restrict__ sector_indx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = (uint32_t)map[i];
+  uint32_t iimp = s & ((1u << nimp) - 1u), ibath = s >> nimp;
+  // position = rank of ibath among (Ns-Nimp)-bit strings with the same popcount (ascending)
+  int k = 0, r = 0;
+  for (int p = 0; p < ns - nimp; p++)
+    if ((ibath >> p) & 1u) { k++; r += binom[p * 31 + k]; }
+  (void)npart;
+  int64_t q = rowptr[iimp] + r;
+  bath_state[q] = (int32_t)ibath;
+  sector_indx[q] = (int32_t)(i + 1);
+}
+
+// ------------------------------------------------------------------------------------
+static int64_t binom64(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  int64_t r = 1;
+  for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+  return r;
+}
+
+#define LAUNCH_1D(kernel, n, ...)                                                  \
+  do {                                                                             \
+    int64_t nb__ = ((n) + 255) / 256;                                              \
+    if (nb__ > 0) {                                                                \
+      kernel<<<(unsigned)nb__, 256, 0, c.stream>>>(__VA_ARGS__);                   \
+      c.launches++;                                                                \
+    }                                                                              \
+  } while (0)
+
+int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
+                  double const_add, bool want_csr) {
+  Ctx &c = ctx();
+  const int ns = c.ns;
+  op.npart = npart;
+  op.n = binom64(ns, npart);
+  op.real_h = c.real_h;
+  const int lbits = ns / 2, hbits = ns - lbits;
+  // Lin tables (host, tiny)
+  std::vector<int32_t> lo((size_t)1 << lbits), hi((size_t)1 << hbits);
+  {
+    std::vector<int32_t> cnt(lbits + 1, 0);
+    for (uint32_t x = 0; x < (1u << lbits); x++) lo[x] = cnt[__builtin_popcount(x)]++;
+    int64_t off = 0;
+    for (uint32_t h = 0; h < (1u << hbits); h++) {
+      hi[h] = (int32_t)off;
+      int need = npart - __builtin_popcount(h);
+      if (need >= 0 && need <= lbits) off += binom64(lbits, need);
+    }
+    if (off != op.n) return fail("internal: Lin table size mismatch");
+  }
+  CB_CHECK(dev_alloc(&op.lin_lo, (int64_t)lo.size()));
+  CB_CHECK(dev_alloc(&op.lin_hi, (int64_t)hi.size()));
+  CB_CUDA(cudaMemcpyAsync(op.lin_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(op.lin_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CHECK(dev_alloc(&op.map, op.n));
+  LAUNCH_1D(k_sector_map, (int64_t)1 << ns, ns, npart, op.lin_lo, op.lin_hi, lbits, op.map);
+  // terms + diagonal coefficients
+  op.nterms = (int32_t)terms.size();
+  CB_CHECK(dev_alloc(&op.terms, (int64_t)terms.size()));
+  if (!terms.empty())
+    CB_CUDA(cudaMemcpyAsync(op.terms, terms.data(), terms.size() * sizeof(Term), cudaMemcpyHostToDevice, c.stream));
+  double *d_e = nullptr, *d_sp = nullptr;
+  CB_CHECK(dev_alloc(&d_e, ns));
+  CB_CHECK(dev_alloc(&d_sp, (int64_t)c.nimp * c.nimp));
+  CB_CUDA(cudaMemcpyAsync(d_e, e.data(), ns * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(d_sp, c.spair.data(), c.spair.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  CB_CHECK(dev_alloc(&op.f, op.n));
+  LAUNCH_1D(k_spin_diag, op.n, op.n, op.map, ns, c.nimp, d_e, d_sp, const_add, op.f);
+  // row lengths are needed by both modes (ELL width / statistics)
+  CB_CHECK(dev_alloc(&op.rowlen, op.n));
+  LAUNCH_1D(k_csr_count, op.n, op.n, op.map, op.terms, op.nterms, op.rowlen);
+  if (want_csr) {
+    CB_CHECK(dev_alloc(&op.rowptr, op.n + 1));
+    k_exclusive_scan<<<1, 1024, 0, c.stream>>>(op.n, op.rowlen, op.rowptr);
+    c.launches++;
+    int32_t nnz32 = 0;
+    CB_CUDA(cudaMemcpyAsync(&nnz32, op.rowptr + op.n, 4, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    op.nnz = nnz32;
+    CB_CHECK(dev_alloc(&op.col, op.nnz));
+    CB_CHECK(dev_alloc(&op.val, op.nnz));
+    LAUNCH_1D(k_csr_fill, op.n, op.n, op.map, op.lin_lo, op.lin_hi, lbits, op.terms, op.nterms, op.rowptr, op.col, op.val);
+    // ELL width = longest row
+    std::vector<int32_t> rl(op.n);
+    CB_CUDA(cudaMemcpyAsync(rl.data(), op.rowlen, op.n * 4, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    op.ell_w = 0;
+    for (auto x : rl) op.ell_w = std::max(op.ell_w, x);
+    CB_CHECK(dev_alloc(&op.ell_col, (int64_t)op.ell_w * op.n));
+    CB_CHECK(dev_alloc(&op.ell_val, (int64_t)op.ell_w * op.n));
+    LAUNCH_1D(k_csr_to_ell, op.n, op.n, op.rowptr, op.col, op.val, op.ell_w, op.ell_col, op.ell_val);
+  }
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  cudaFree(d_e);
+  cudaFree(d_sp);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void free_spin_op(SpinOp &op) {
+  dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
+  dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
+  dev_free(op.rowlen);
+  op = SpinOp();
+}
+
+int ensure_stage(int64_t n) {
+  Ctx &c = ctx();
+  if (c.stage_n >= n) return 0;
+  dev_free(c.stage_v); dev_free(c.stage_hv);
+  CB_CHECK(dev_alloc(&c.stage_v, n));
+  CB_CHECK(dev_alloc(&c.stage_hv, n));
+  c.stage_n = n;
+  return 0;
+}
+
+static int sector_np(int32_t isector, int32_t *nup, int32_t *ndw) {
+  Ctx &c = ctx();
+  if (!c.have_model) return fail("no model set (call cdmft_b200_set_model)");
+  int nsec = (c.ns + 1) * (c.ns + 1);
+  if (isector < 1 || isector > nsec) return fail("isector %d out of range [1,%d]", isector, nsec);
+  *ndw = (isector - 1) % (c.ns + 1);  // get_Ndw / get_Nup, ED_SETUP.f90:476-500
+  *nup = (isector - 1) / (c.ns + 1);
+  return 0;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cdmft_b200_get_sector_dims(int32_t isector, int64_t *dimup, int64_t *dimdw, int64_t *dim) {
+  int32_t nup, ndw;
+  CB_CHECK(sector_np(isector, &nup, &ndw));
+  int64_t du = binom64(ctx().ns, nup), dd = binom64(ctx().ns, ndw);
+  if (dimup) *dimup = du;
+  if (dimdw) *dimdw = dd;
+  if (dim) *dim = du * dd;
+  return 0;
+}
+
+int cdmft_b200_vecdim_hv_sector(int32_t isector, int64_t *vecdim) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  int64_t du, dd, d;
+  CB_CHECK(cdmft_b200_get_sector_dims(isector, &du, &dd, &d));
+  if (!c.spmd) { *vecdim = d; return 0; }
+  int p_eff = (int)std::min<int64_t>(c.nranks, dd);
+  // ranks outside the shrunk communicator hold nothing (ED_HAMILTONIAN.f90:62-90)
+  *vecdim = c.rank < p_eff ? du * split_of(dd, p_eff, c.rank).q : 0;
+  return 0;
+}
+
+int cdmft_b200_build_hv_sector(int32_t isector, int32_t mode, int64_t *nloc) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (c.hstatus) return fail("build_hv_sector: sector %d is still active (sp_init_matrix: already allocated)", c.hsector);
+  if (mode != CDMFT_B200_SPARSE && mode != CDMFT_B200_DIRECT) return fail("build_hv_sector: bad mode %d", mode);
+  int32_t nup, ndw;
+  CB_CHECK(sector_np(isector, &nup, &ndw));
+  CB_CUDA(cudaSetDevice(c.device));
+  c.hsector = isector;
+  c.mode = mode;
+  CB_CHECK(build_spin_op(c.up, nup, c.terms_up, c.e_up, c.const0, mode == CDMFT_B200_SPARSE));
+  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE));
+  c.dimup = c.up.n; c.dimdw = c.dw.n; c.dim = c.dimup * c.dimdw;
+  c.p_eff = (int)std::min<int64_t>(c.nranks, c.dimdw);
+  c.rk.clear();
+  const bool sharded = c.spmd || c.sim || c.opt.force_sharded;
+  if (c.spmd) {
+    if (c.rank < c.p_eff) { RankState r; r.rank = c.rank; c.rk.push_back(r); }
+  } else {
+    for (int r = 0; r < c.p_eff; r++) { RankState s; s.rank = r; c.rk.push_back(s); }
+  }
+  int64_t total = 0;
+  for (auto &r : c.rk) {
+    r.dw = split_of(c.dimdw, c.p_eff, r.rank);
+    r.up = split_of(c.dimup, c.p_eff, r.rank);
+    r.nloc = c.dimup * r.dw.q;
+    total += r.nloc;
+    if (sharded) {
+      CB_CHECK(dev_alloc(&r.vt, c.dimdw * r.up.q));
+      CB_CHECK(dev_alloc(&r.hvt, c.dimdw * r.up.q));
+      if (c.spmd && c.p_eff > 1) {
+        CB_CHECK(dev_alloc(&r.sendbuf, std::max(r.nloc, c.dimdw * r.up.q)));
+        CB_CHECK(dev_alloc(&r.recvbuf, std::max(r.nloc, c.dimdw * r.up.q)));
+      }
+    }
+  }
+  c.hstatus = true;
+  if (nloc) *nloc = total;
+  return 0;
+}
+
+int cdmft_b200_delete_hv_sector(void) {
+  Ctx &c = ctx();
+  if (!c.inited) return 0;
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  free_spin_op(c.up);
+  free_spin_op(c.dw);
+  for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }
+  c.rk.clear();
+  dev_free(c.stage_v); dev_free(c.stage_hv); c.stage_n = 0;
+  for (auto &k : c.kv) dev_free(k);
+  c.kv_n = 0;
+  c.hsector = 0; c.hstatus = false;
+  c.dim = c.dimup = c.dimdw = 0;
+  return 0;
+}
+
+int cdmft_b200_active_ranks(int32_t *p) {
+  if (!ctx().hstatus) return fail("active_ranks: no active sector");
+  *p = ctx().p_eff;
+  return 0;
+}
+
+int cdmft_b200_get_sector_map(int32_t which, int32_t *map) {
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("get_sector_map: no active sector");
+  SpinOp &op = which == 1 ? c.up : c.dw;
+  CB_CUDA(cudaMemcpy(map, op.map, op.n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cdmft_b200_get_csr_nnz(int32_t which, int64_t *nnz) {
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("get_csr_nnz: no active sector");
+  if (c.mode != CDMFT_B200_SPARSE) return fail("get_csr_nnz: sector was built in DIRECT mode (no stored matrix)");
+  *nnz = (which == 1 ? c.up : c.dw).nnz;
+  return 0;
+}
+
+int cdmft_b200_get_csr(int32_t which, int64_t *rowptr, int32_t *col, double *val) {
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("get_csr: no active sector");
+  if (c.mode != CDMFT_B200_SPARSE) return fail("get_csr: sector was built in DIRECT mode (no stored matrix)");
+  SpinOp &op = which == 1 ? c.up : c.dw;
+  std::vector<int32_t> rp(op.n + 1);
+  CB_CUDA(cudaMemcpy(rp.data(), op.rowptr, (op.n + 1) * 4, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i <= op.n; i++) rowptr[i] = rp[i];
+  CB_CUDA(cudaMemcpy(col, op.col, op.nnz * 4, cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < op.nnz; k++) col[k] += 1;  // 1-based like the reference
+  CB_CUDA(cudaMemcpy(val, op.val, op.nnz * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cdmft_b200_get_sparse_map(int32_t which, int64_t *rowptr, int32_t *bath_state, int32_t *sector_indx) {
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("get_sparse_map: no active sector");
+  SpinOp &op = which == 1 ? c.up : c.dw;
+  const int64_t nst = (int64_t)1 << c.nimp;
+  unsigned long long *d_cnt = nullptr;
+  CB_CHECK(dev_alloc(&d_cnt, nst));
+  CB_CUDA(cudaMemsetAsync(d_cnt, 0, nst * 8, c.stream));
+  LAUNCH_1D(k_spmap_count, op.n, op.n, op.map, c.nimp, d_cnt);
+  std::vector<unsigned long long> cnt(nst);
+  CB_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, nst * 8, cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<int64_t> rp(nst + 1, 0);
+  for (int64_t k = 0; k < nst; k++) rp[k + 1] = rp[k] + (int64_t)cnt[k];
+  for (int64_t k = 0; k <= nst; k++) rowptr[k] = rp[k];
+  if (bath_state && sector_indx) {
+    std::vector<int32_t> binom(31 * 31, 0);
+    for (int n = 0; n < 31; n++)
+      for (int k = 0; k < 31; k++) binom[n * 31 + k] = (int32_t)std::min<int64_t>(binom64(n, k), INT32_MAX);
+    int64_t *d_rp = nullptr;
+    int32_t *d_bn = nullptr, *d_bs = nullptr, *d_si = nullptr;
+    CB_CHECK(dev_alloc(&d_rp, nst + 1));
+    CB_CHECK(dev_alloc(&d_bn, 31 * 31));
+    CB_CHECK(dev_alloc(&d_bs, op.n));
+    CB_CHECK(dev_alloc(&d_si, op.n));
+    CB_CUDA(cudaMemcpyAsync(d_rp, rp.data(), (nst + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    CB_CUDA(cudaMemcpyAsync(d_bn, binom.data(), binom.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    LAUNCH_1D(k_spmap_fill, op.n, op.n, op.map, c.ns, c.nimp, op.npart, d_rp, d_bn, d_bs, d_si);
+    CB_CUDA(cudaMemcpyAsync(bath_state, d_bs, op.n * 4, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaMemcpyAsync(sector_indx, d_si, op.n * 4, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(d_rp); cudaFree(d_bn); cudaFree(d_bs); cudaFree(d_si);
+  }
+  cudaFree(d_cnt);
+  return 0;
+}
+
+}  // extern "C"

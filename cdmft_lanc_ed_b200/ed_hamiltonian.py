@@ -1,0 +1,341 @@
+"""Host-side mirror of the reference's ED_HAMILTONIAN interface on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the Fortran module (the reference's
+toolchain -- gfortran + MPI + SciFortran -- is absent from this image, so the host layer
+above ``include/cdmft_b200.h`` is Python/ctypes here; the Fortran ISO_C_BINDING shim a
+maintainer would compile instead is ``fortran/ED_HAMILTONIAN_B200.f90``):
+
+    build_Hv_sector(isector)        ED_HAMILTONIAN.f90:39-143
+    delete_Hv_sector()              ED_HAMILTONIAN.f90:149-190
+    vecDim_Hv_sector(isector)       ED_HAMILTONIAN.f90:197-221
+    spHtimesV_p(Nloc, v, Hv)        ED_VARS_GLOBAL.f90:72-78,146   (procedure pointer; None when unset)
+    sp_lanc_eigh / sp_lanc_tridiag  SciFortran drivers called at ED_DIAG.f90:176, ED_GF_NORMAL.f90:215
+
+The product path is CUDA only: importing works without a GPU (so CPU-side tests can check
+symbols), every compute call raises ``EdB200Error`` when no device / library is available.
+Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcdmft_b200.so")
+
+SPARSE, DIRECT = 1, 0  # ed_sparse_H = T / F (ED_INPUT_VARS.f90:145)
+
+
+class EdB200Error(RuntimeError):
+    """Raised where the reference executes `stop "message"`."""
+
+
+class _CModel(C.Structure):
+    _fields_ = [("nlat", C.c_int32), ("norb", C.c_int32), ("nspin", C.c_int32), ("nbath", C.c_int32),
+                ("uloc", C.c_double * 5), ("ust", C.c_double), ("jh", C.c_double), ("jx", C.c_double),
+                ("jp", C.c_double), ("xmu", C.c_double), ("hfmode", C.c_int32),
+                ("quirk_direct_bathdiag", C.c_int32),
+                ("imphloc", C.c_void_p), ("hbath", C.c_void_p), ("vbath", C.c_void_p)]
+
+
+_lib = None
+
+# every symbol include/cdmft_b200.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = [
+    "cdmft_b200_last_error", "cdmft_b200_init", "cdmft_b200_nccl_unique_id", "cdmft_b200_init_rank",
+    "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_launch_count",
+    "cdmft_b200_set_option", "cdmft_b200_set_model", "cdmft_b200_get_ns", "cdmft_b200_get_sector_dims",
+    "cdmft_b200_vecdim_hv_sector", "cdmft_b200_build_hv_sector", "cdmft_b200_delete_hv_sector",
+    "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
+    "cdmft_b200_get_csr_nnz", "cdmft_b200_get_csr", "cdmft_b200_get_diag", "cdmft_b200_get_sparse_map",
+    "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
+    "cdmft_b200_add_to_lanczos_gf",
+]
+
+
+def load_library():
+    """dlopen libcdmft_b200.so (built in-tree by __graft_entry__.build()). No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EdB200Error(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.cdmft_b200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise EdB200Error(load_library().cdmft_b200_last_error().decode())
+
+
+def _ptr(a):
+    """numpy array, torch tensor (CPU or CUDA) or raw int address -> void*"""
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+# --------------------------------------------------------------------------------------
+# runtime (ed_set_MpiComm, ED_VARS_GLOBAL.f90:365-380)
+# --------------------------------------------------------------------------------------
+_state = {"inited": False, "nranks": 1, "rank": 0, "mode": None}
+spHtimesV_p = None  # the procedure pointer: bound by build_Hv_sector, None after delete_Hv_sector
+
+
+def ed_init(device: int = 0):
+    """Serial solver (MpiStatus = .false.)."""
+    _chk(load_library().cdmft_b200_init(C.c_int32(device)))
+    _state.update(inited=True, nranks=1, rank=0, mode="single")
+
+
+def ed_init_sim(nranks: int, device: int = 0):
+    """P simulated MPI ranks on one GPU (exercises the Ndw-sharded code path)."""
+    _chk(load_library().cdmft_b200_init_sim(C.c_int32(device), C.c_int32(nranks)))
+    _state.update(inited=True, nranks=nranks, rank=0, mode="sim")
+
+
+def ed_set_MpiComm(device: int | None = None):
+    """SPMD: one process per GPU, ranks from torch.distributed (the communicator the reference
+    receives from its driver, drivers/cdn_hm_2dsquare.f90:39).  The NCCL unique id is created on
+    rank 0 and broadcast through the already-initialised process group (any backend)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise EdB200Error("ed_set_MpiComm: torch.distributed is not initialised")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    L = load_library()
+    uid = (C.c_ubyte * 128)()
+    if rank == 0:
+        _chk(L.cdmft_b200_nccl_unique_id(uid))
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    uid = (C.c_ubyte * 128)(*t.cpu().tolist())
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    _chk(L.cdmft_b200_init_rank(C.c_int32(device), C.c_int32(world), C.c_int32(rank), uid))
+    _state.update(inited=True, nranks=world, rank=rank, mode="spmd")
+
+
+def ed_finalize():
+    global spHtimesV_p
+    if _lib is not None:
+        _chk(_lib.cdmft_b200_finalize())
+    _state.update(inited=False, nranks=1, rank=0, mode=None)
+    spHtimesV_p = None
+
+
+def set_stream(cuda_stream: int):
+    _chk(load_library().cdmft_b200_set_stream(C.c_void_p(cuda_stream)))
+
+
+def set_option(key: str, value: int):
+    _chk(load_library().cdmft_b200_set_option(key.encode(), C.c_int64(value)))
+
+
+def launch_count() -> int:
+    n = C.c_int64()
+    _chk(load_library().cdmft_b200_launch_count(C.byref(n)))
+    return n.value
+
+
+# --------------------------------------------------------------------------------------
+# model = what ED_HAMILTONIAN reads from globals (set_Himpurity + set_dmft_bath, ED_MAIN.f90:248-254)
+# --------------------------------------------------------------------------------------
+_model_keep = None
+
+
+def ed_set_model(model, quirk_direct_bathdiag: bool = False):
+    global _model_keep
+    a = np.asfortranarray(model.imphloc, dtype=np.complex128)
+    b = np.asfortranarray(model.hbath, dtype=np.complex128)
+    v = np.asfortranarray(model.vbath, dtype=np.float64)
+    _model_keep = (a, b, v)
+    m = _CModel(model.nlat, model.norb, model.nspin, model.nbath, (C.c_double * 5)(*model.uloc), model.ust,
+                model.jh, model.jx, model.jp, model.xmu, int(model.hfmode), int(quirk_direct_bathdiag),
+                a.ctypes.data, b.ctypes.data, v.ctypes.data)
+    _chk(load_library().cdmft_b200_set_model(C.byref(m)))
+
+
+def get_Ns() -> int:
+    n = C.c_int32()
+    _chk(load_library().cdmft_b200_get_ns(C.byref(n)))
+    return n.value
+
+
+def get_Sector(nup: int, ndw: int, ns: int | None = None) -> int:
+    """ED_SETUP.f90:446-457"""
+    ns = get_Ns() if ns is None else ns
+    return 1 + nup * (ns + 1) + ndw
+
+
+def getDim(isector: int):
+    """(Dim, DimUp, DimDw) -- ED_SETUP.f90:316-322, int64 (the reference overflows at Ns=18)."""
+    du, dd, d = C.c_int64(), C.c_int64(), C.c_int64()
+    _chk(load_library().cdmft_b200_get_sector_dims(C.c_int32(isector), C.byref(du), C.byref(dd), C.byref(d)))
+    return d.value, du.value, dd.value
+
+
+# --------------------------------------------------------------------------------------
+# the three module procedures + the pointer
+# --------------------------------------------------------------------------------------
+_sector = {"isector": 0, "nloc": 0}
+
+
+def _hxv(Nloc, v, Hv):
+    """cc_sparse_HxV contract: Hv = H_sector * v on the local shard; host or device buffers."""
+    _chk(load_library().cdmft_b200_hxv64(C.c_int64(Nloc), _ptr(v), _ptr(Hv)))
+
+
+def build_Hv_sector(isector: int, ed_sparse_H: bool = True) -> int:
+    """Returns the local vector length (what vecDim_Hv_sector reports)."""
+    global spHtimesV_p
+    nloc = C.c_int64()
+    _chk(load_library().cdmft_b200_build_hv_sector(C.c_int32(isector), C.c_int32(SPARSE if ed_sparse_H else DIRECT),
+                                                   C.byref(nloc)))
+    _sector.update(isector=isector, nloc=nloc.value)
+    spHtimesV_p = _hxv
+    return nloc.value
+
+
+def delete_Hv_sector():
+    global spHtimesV_p
+    _chk(load_library().cdmft_b200_delete_hv_sector())
+    _sector.update(isector=0, nloc=0)
+    spHtimesV_p = None
+
+
+def vecDim_Hv_sector(isector: int) -> int:
+    n = C.c_int64()
+    _chk(load_library().cdmft_b200_vecdim_hv_sector(C.c_int32(isector), C.byref(n)))
+    return n.value
+
+
+def active_ranks() -> int:
+    p = C.c_int32()
+    _chk(load_library().cdmft_b200_active_ranks(C.byref(p)))
+    return p.value
+
+
+def hxv(v: np.ndarray) -> np.ndarray:
+    """Convenience: allocate Hv and call the pointer (host arrays)."""
+    if spHtimesV_p is None:
+        raise EdB200Error("spHtimesV_p is not associated (call build_Hv_sector)")
+    v = np.ascontiguousarray(v, dtype=np.complex128)
+    out = np.empty_like(v)
+    spHtimesV_p(v.size, v, out)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# inspection
+# --------------------------------------------------------------------------------------
+def get_sector_map(which: int) -> np.ndarray:
+    _, du, dd = getDim(_sector["isector"])
+    m = np.empty(du if which == 1 else dd, dtype=np.int32)
+    _chk(load_library().cdmft_b200_get_sector_map(C.c_int32(which), _ptr(m)))
+    return m
+
+
+def get_csr(which: int):
+    nnz = C.c_int64()
+    _chk(load_library().cdmft_b200_get_csr_nnz(C.c_int32(which), C.byref(nnz)))
+    _, du, dd = getDim(_sector["isector"])
+    n = du if which == 1 else dd
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    col = np.zeros(nnz.value, dtype=np.int32)
+    val = np.zeros(nnz.value, dtype=np.complex128)
+    _chk(load_library().cdmft_b200_get_csr(C.c_int32(which), _ptr(rowptr), _ptr(col), _ptr(val)))
+    return rowptr, col, val
+
+
+def get_diag() -> np.ndarray:
+    d = np.zeros(_sector["nloc"], dtype=np.float64)
+    _chk(load_library().cdmft_b200_get_diag(C.c_int64(d.size), _ptr(d)))
+    return d
+
+
+def get_sparse_map(which: int, nimp: int):
+    _, du, dd = getDim(_sector["isector"])
+    n = du if which == 1 else dd
+    rowptr = np.zeros((1 << nimp) + 1, dtype=np.int64)
+    bath = np.zeros(n, dtype=np.int32)
+    indx = np.zeros(n, dtype=np.int32)
+    _chk(load_library().cdmft_b200_get_sparse_map(C.c_int32(which), _ptr(rowptr), _ptr(bath), _ptr(indx)))
+    return rowptr, bath, indx
+
+
+# --------------------------------------------------------------------------------------
+# Krylov drivers (SciFortran call sites)
+# --------------------------------------------------------------------------------------
+def sp_lanc_tridiag(vin, nitermax: int, threshold: float = 1e-12):
+    """sp_lanc_tridiag(spHtimesV_p, vin, alanc, blanc): returns (ndone, alanc, blanc)."""
+    n = vin.numel() if hasattr(vin, "numel") else vin.size
+    a = np.zeros(nitermax)
+    b = np.zeros(nitermax)
+    nd = C.c_int32()
+    _chk(load_library().cdmft_b200_lanczos_tridiag(C.c_int64(n), _ptr(vin), C.c_int32(nitermax), C.c_double(threshold),
+                                                   _ptr(a), _ptr(b), C.byref(nd)))
+    return nd.value, a, b
+
+
+def sp_lanc_eigh(vect, nitermax: int = 512, threshold: float = 1e-18, ncheck: int = 10):
+    """sp_lanc_eigh(spHtimesV_p, egs, vect, Nitermax, threshold): vect (numpy complex128 or CUDA
+    tensor) is the start vector on entry (all zero -> constant) and the eigenvector on exit.
+    Returns (egs, niter, alanc, blanc)."""
+    n = vect.numel() if hasattr(vect, "numel") else vect.size
+    e = C.c_double()
+    nit = C.c_int32()
+    a = np.zeros(nitermax)
+    b = np.zeros(nitermax)
+    _chk(load_library().cdmft_b200_lanczos_gs(C.c_int64(n), _ptr(vect), C.c_int32(nitermax), C.c_double(threshold),
+                                              C.c_int32(ncheck), C.byref(e), C.byref(nit), _ptr(a), _ptr(b)))
+    return e.value, nit.value, a[: nit.value], b[: nit.value]
+
+
+# --------------------------------------------------------------------------------------
+# Green's function helpers (ED_GF_NORMAL.f90)
+# --------------------------------------------------------------------------------------
+def apply_op(isector: int, iop: int, ispin: int, pos, coef, state: np.ndarray):
+    """(sum_k coef[k] op_{pos[k]}) |state>; returns (jsector, vector) or (0, None)."""
+    ns = get_Ns()
+    nup, ndw = (isector - 1) // (ns + 1), (isector - 1) % (ns + 1)
+    jn = [nup, ndw]
+    jn[ispin - 1] += 1 if iop > 0 else -1
+    if min(jn) < 0 or max(jn) > ns:
+        return 0, None
+    jsec = get_Sector(jn[0], jn[1], ns)
+    jdim = getDim(jsec)[0]
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    coef = np.ascontiguousarray(coef, dtype=np.complex128)
+    state = np.ascontiguousarray(state, dtype=np.complex128)
+    out = np.zeros(jdim, dtype=np.complex128)
+    js = C.c_int32()
+    _chk(load_library().cdmft_b200_apply_op(C.c_int32(isector), C.c_int32(iop), C.c_int32(ispin), C.c_int32(pos.size),
+                                            _ptr(pos), _ptr(coef), _ptr(state), _ptr(out), C.byref(js)))
+    return js.value, out
+
+
+def add_to_lanczos_gf_normal(vnorm2, Ei, alanc, blanc, isign, zeta, wm, g):
+    """Accumulates into g (complex128[Lmats]) in place; returns (poles, weights)."""
+    n = len(alanc)
+    a = np.ascontiguousarray(alanc, dtype=np.float64)
+    b = np.ascontiguousarray(blanc, dtype=np.float64)
+    wm = np.ascontiguousarray(wm, dtype=np.float64)
+    vn = (C.c_double * 2)(complex(vnorm2).real, complex(vnorm2).imag)
+    poles = np.zeros(n)
+    weights = np.zeros(n, dtype=np.complex128)
+    _chk(load_library().cdmft_b200_add_to_lanczos_gf(vn, C.c_double(Ei), C.c_int32(n), _ptr(a), _ptr(b), C.c_int32(isign),
+                                                     C.c_double(zeta), C.c_int32(wm.size), _ptr(wm), _ptr(g), _ptr(poles),
+                                                     _ptr(weights)))
+    return poles, weights

@@ -1,0 +1,146 @@
+/*
+ * cdmft_b200.h -- C ABI of libcdmft_b200.so (hand-written sm_100a CUDA behind it).
+ *
+ * Drop-in boundary for the Hamiltonian-times-vector hot path of QcmPlab/CDMFT-LANC-ED:
+ * the three module procedures + one procedure pointer of the reference
+ *
+ *   build_Hv_sector(isector[,Hmat])   ED_HAMILTONIAN.f90:39-143
+ *   delete_Hv_sector()                ED_HAMILTONIAN.f90:149-190
+ *   vecDim_Hv_sector(isector)         ED_HAMILTONIAN.f90:197-221
+ *   spHtimesV_p(Nloc,v,Hv)            ED_VARS_GLOBAL.f90:72-78,146  (abstract interface cc_sparse_HxV)
+ *
+ * plus the SciFortran Krylov drivers the callers wrap around the pointer
+ * (sp_lanc_eigh ED_DIAG.f90:176-184, sp_lanc_tridiag ED_GF_NORMAL.f90:215) as fused
+ * device-resident entry points, the start-vector construction of ED_GF_NORMAL.f90:180-199
+ * and the pole/weight accumulation of ED_GF_NORMAL.f90:915-975.
+ *
+ * All functions return 0 on success, non-zero on error (message via
+ * cdmft_b200_last_error(); the Fortran shim turns it into `stop`, the reference's only
+ * error mechanism).  Plain pointers and sizes only; complex(8) = interleaved (re,im) doubles.
+ * One global context, one active sector at a time (the reference keeps the sector in module
+ * globals, ED_HAMILTONIAN_COMMON.f90:11-20); calls must be serialised by the caller.
+ * There is NO CPU fallback: every entry point fails loudly without a CUDA device.
+ */
+#ifndef CDMFT_B200_H
+#define CDMFT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* What ED_HAMILTONIAN reads from module globals, packed by the caller:
+ *   impHloc                       ED_VARS_GLOBAL.f90:119      complex [Nlat,Nlat,Nspin,Nspin,Norb,Norb]
+ *   Hbath_build(lambda(:,ib))     ED_BATH/hbath_setup.f90:240-250   same shape x Nbath
+ *   dmft_bath%item(ib)%v(:)       ED_HAMILTONIAN_SPARSE_HxV.f90:63-75    real [Nlat*Nspin*Norb, Nbath]
+ *   Uloc,Ust,Jh,Jx,Jp,xmu,hfmode  ED_INPUT_VARS.f90:19-32,129-135,164
+ * Arrays are Fortran (column-major) order. */
+typedef struct cdmft_b200_model {
+  int32_t nlat, norb, nspin, nbath;
+  double uloc[5];
+  double ust, jh, jx, jp, xmu;
+  int32_t hfmode;
+  /* reproduce the direct-path bath-diagonal loop bound (ilat=1..Norb) of
+   * ED_HAMILTONIAN/direct/HxV_local.f90:83-84 instead of the sparse path's 1..Nlat
+   * (sparse/H_local.f90:85); default 0 = sparse (correct) semantics */
+  int32_t quirk_direct_bathdiag;
+  const double *imphloc;
+  const double *hbath;
+  const double *vbath;
+} cdmft_b200_model;
+
+/* ed_sparse_H switch (ED_INPUT_VARS.f90:145, ED_HAMILTONIAN.f90:129-141) */
+enum {
+  CDMFT_B200_SPARSE = 1, /* stored per-spin CSR (spMatVec_main / spMatVec_MPI_main)            */
+  CDMFT_B200_DIRECT = 0  /* matrix-free bit hopping (directMatVec_main / directMatVec_MPI_main) */
+};
+
+/* ---- runtime ------------------------------------------------------------------------ */
+const char *cdmft_b200_last_error(void);
+/* single rank on CUDA device `device` (MpiStatus=.false. in the reference) */
+int cdmft_b200_init(int32_t device);
+/* SPMD: one process per GPU (ed_set_MpiComm, ED_VARS_GLOBAL.f90:365-380).  `uid` is the
+ * 128-byte NCCL unique id produced on rank 0 by cdmft_b200_nccl_unique_id and broadcast by
+ * the host program (MPI_Bcast in Fortran, torch.distributed here). */
+int cdmft_b200_nccl_unique_id(void *uid128);
+int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const void *uid128);
+/* P simulated ranks on ONE device: the sharded code path (Ndw split + distributed transpose)
+ * with device-local exchange; hxv then takes the gathered vector (shards = contiguous blocks
+ * in rank order, the layout of gather_vector_MPI, ED_SETUP.f90:633-668). Test/debug aid. */
+int cdmft_b200_init_sim(int32_t device, int32_t nranks);
+int cdmft_b200_finalize(void);
+/* launch on this cudaStream_t instead of the library's own stream (0 = back to own stream) */
+int cdmft_b200_set_stream(void *cuda_stream);
+/* number of kernels this library has launched so far */
+int cdmft_b200_launch_count(int64_t *n);
+/* kernel variant selection for experiments/benchmarks: key/value, see DESIGN.md */
+int cdmft_b200_set_option(const char *key, int64_t value);
+
+/* ---- model -------------------------------------------------------------------------- */
+int cdmft_b200_set_model(const cdmft_b200_model *m);
+int cdmft_b200_get_ns(int32_t *ns); /* ed_setup_dimensions, ED_SETUP.f90:111-120 */
+
+/* ---- sector lifecycle ----------------------------------------------------------------- */
+/* isector = 1 + Nup*(Ns+1) + Ndw  (get_Sector, ED_SETUP.f90:446-457) */
+int cdmft_b200_get_sector_dims(int32_t isector, int64_t *dimup, int64_t *dimdw, int64_t *dim);
+/* vecDim_Hv_sector: DimUp*(DimDw/P + [rank < mod(DimDw,P)]); Dim for sim/single rank */
+int cdmft_b200_vecdim_hv_sector(int32_t isector, int64_t *vecdim);
+/* build_Hv_sector: Fock maps, Ndw shard (mpiQdw, mpiIstart, ...), H terms, per-spin CSR
+ * (mode SPARSE) and the device work buffers.  *nloc receives the local vector length.
+ * Building on an active sector is an error (reference: "alreay allocate can not init",
+ * ED_SPARSE_MATRIX.f90:134). */
+int cdmft_b200_build_hv_sector(int32_t isector, int32_t mode, int64_t *nloc);
+int cdmft_b200_delete_hv_sector(void);
+/* ranks that hold data for the active sector = min(P, DimDw) (ED_HAMILTONIAN.f90:62-90) */
+int cdmft_b200_active_ranks(int32_t *p);
+
+/* ---- the mat-vec: spHtimesV_p(Nloc,v,Hv) ---------------------------------------------- */
+/* v, hv: complex(8)[nloc], host OR device pointers (detected); hv is fully overwritten and
+ * must not alias v.  Synchronous on return for host pointers; stream-ordered for device
+ * pointers.  nloc must equal the value build_hv_sector returned. */
+int cdmft_b200_hxv(int32_t nloc, const void *v, void *hv);
+int cdmft_b200_hxv64(int64_t nloc, const void *v, void *hv); /* Ns=18: Dim > 2^31 */
+
+/* ---- inspection (parity tests: integer objects are bit-exact with the reference) ------ */
+/* which: 1 = up (Hs(1)%map / spH0ups(1)), 2 = dw (Hs(2)%map / spH0dws(1)) */
+int cdmft_b200_get_sector_map(int32_t which, int32_t *map);
+int cdmft_b200_get_csr_nnz(int32_t which, int64_t *nnz);
+/* canonical CSR: rowptr[n+1] 0-based offsets, col 1-based ascending (= the reference's
+ * insertion order), val complex interleaved */
+int cdmft_b200_get_csr(int32_t which, int64_t *rowptr, int32_t *col, double *val);
+/* spH0d values of the local rows (sparse/H_local.f90) */
+int cdmft_b200_get_diag(int64_t nloc, double *d);
+/* ED_SPARSE_MAP of build_sector(...,itrace=.true.) (ED_SETUP.f90:757-759,
+ * ED_SPARSE_MAP.f90:101-121): for imp state k in [0,2^Nimp) entries rowptr[k]..rowptr[k+1]-1 */
+int cdmft_b200_get_sparse_map(int32_t which, int64_t *rowptr, int32_t *bath_state, int32_t *sector_indx);
+
+/* ---- fused device-resident Krylov drivers (SciFortran SF_SP_LINALG semantics) --------- */
+/* sp_lanc_tridiag(MatVec,vin,alanc,blanc): v0 = local shard of the start vector (host or
+ * device; not modified), alanc/blanc host arrays of size nitermax (blanc[0] = 0);
+ * *ndone = iterations performed (stops early when |beta| < threshold, default 1e-12). */
+int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, double threshold,
+                               double *alanc, double *blanc, int32_t *ndone);
+/* sp_lanc_eigh(MatVec,egs,vect,Nitermax,threshold,ncheck): vect in = start vector (all zero
+ * -> constant 1/sqrt(Dim)), out = normalised ground-state shard; alanc/blanc may be NULL. */
+int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double threshold,
+                          int32_t ncheck, double *egs, int32_t *niter, double *alanc, double *blanc);
+
+/* ---- Green's function helpers (ED_GF_NORMAL.f90) --------------------------------------- */
+/* out = sum_k coef[k] * op(pos[k]) |state>  with op = c^+ (iop=+1) or c (iop=-1) acting on spin
+ * ispin (1 = up, 2 = dw) of a vector living in sector `isector`; the result lives in
+ * getCDGsector/getCsector(isector) (ED_SETUP.f90:377-418; loops ED_GF_NORMAL.f90:180-194,
+ * 244-258, 590-620).  Single-rank only: state[dim(isector)], out[dim(jsector)] host or device.
+ * pos is the 1-based orbital position imp_state_index(ilat,iorb); coef complex interleaved. */
+int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nops, const int32_t *pos,
+                        const double *coef, const void *state, void *out, int32_t *jsector);
+/* add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:915-975), T=0: poles/weights from the Lanczos
+ * tridiagonal matrix, g[i] += peso/(i*wm[i] - isign*(E_j - ei)), peso = vnorm2*Z(1,j)^2/zeta.
+ * g complex interleaved [lmats] on the host; poles/weights (size nlanc) may be NULL. */
+int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlanc, const double *alanc,
+                                 const double *blanc, int32_t isign, double zeta, int32_t lmats,
+                                 const double *wm, double *g, double *poles, double *weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

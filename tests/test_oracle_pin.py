@@ -1,0 +1,152 @@
+"""CPU tests that PIN the oracle (the reference ships no golden vectors):
+independent Jordan-Wigner ED, dense == sparse == direct == simulated MPI(P), scipy eigsh,
+exact Green's function, and the committed golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cdmft_lanc_ed_b200 import models
+from oracle import jw_ed
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SMALL = [
+    lambda: models.random_model(2, 1, 1, seed=1),
+    lambda: models.random_model(1, 2, 1, seed=2, kanamori=True),
+    lambda: models.random_model(2, 1, 1, nspin=2, seed=3),
+    lambda: models.random_model(1, 2, 1, seed=4, kanamori=True, complex_h=False),
+    lambda: models.random_model(1, 1, 3, seed=5, hfmode=False),
+]
+
+
+@pytest.mark.parametrize("k", range(len(SMALL)))
+def test_dense_hmat_equals_jordan_wigner_all_sectors(oracle_lib, k):
+    mdl = SMALL[k]()
+    H = jw_ed.full_hamiltonian(mdl)
+    assert np.abs(H - H.conj().T).max() < 1e-14
+    orc = oracle_lib.Oracle(mdl)
+    ns = mdl.ns
+    for nup in range(ns + 1):
+        for ndw in range(ns + 1):
+            isec = models.get_sector(ns, nup, ndw)
+            Hd = orc.dense_hmat(isec)
+            assert np.abs(jw_ed.sector_hamiltonian(mdl, nup, ndw, H) - Hd).max() < 1e-13
+            v = np.random.default_rng(isec).normal(size=Hd.shape[0]) + 1j * np.random.default_rng(isec + 1).normal(size=Hd.shape[0])
+            ref = Hd @ v
+            for kind, P in [(0, 1), (1, 1), (1, 2), (1, 3), (2, 1), (3, 1), (3, 2), (3, 5)]:
+                orc.build_hv_sector(isec, kind, P, 0)
+                assert np.abs(orc.hxv(v) - ref).max() < 1e-12
+                orc.delete_hv_sector()
+
+
+def test_maps_operators_and_index_helpers(oracle_lib):
+    e = oracle_lib
+    m = e.sector_map(8, 4)
+    assert m.size == 70 and np.all(np.diff(m) > 0) and all(bin(x).count("1") == 4 for x in m)
+    assert e.binomial(16, 8) == 12870 and e.binomial(18, 9) == 48620 and e.binomial(5, -1) == 0
+    # c / cdg sign rule and error stops (ED_SETUP.f90:807-833)
+    rc, out, sg = e.c_op(3, 0b0111)
+    assert (rc, out, sg) == (0, 0b0011, 1.0)
+    rc, out, sg = e.c_op(2, 0b0111)
+    assert (rc, out, sg) == (0, 0b0101, -1.0)
+    assert e.c_op(4, 0b0111)[0] != 0 and e.cdg_op(1, 0b0001)[0] != 0
+    rc, out, sg = e.cdg_op(4, 0b0111)
+    assert (rc, out, sg) == (0, 0b1111, -1.0)
+    for i, s in enumerate(m):
+        assert e.binary_search(m, int(s)) == i + 1
+    assert e.binary_search(m, 1) == 0
+    # sharding arithmetic (ED_HAMILTONIAN.f90:92-105, 197-221)
+    tot = 0
+    for r in range(8):
+        s = e.shard_of(12870, 12870, 8, r)
+        assert s["qdw"] == (1609 if r < 6 else 1608) and s["istart"] == tot + 1
+        assert e.vecdim(12870, 12870, 8, r) == s["q"] == 12870 * s["qdw"]
+        tot += s["q"]
+    assert tot == 12870 ** 2
+
+
+def test_transpose_sim_matches_numpy(oracle_lib):
+    rng = np.random.default_rng(0)
+    for P, nrow, ncol in [(1, 5, 7), (2, 5, 7), (3, 10, 4), (4, 6, 6), (5, 7, 5)]:
+        A = rng.normal(size=(nrow, ncol)) + 1j * rng.normal(size=(nrow, ncol))  # A[i,j]
+        a = np.asfortranarray(A).ravel(order="F")  # column blocks concatenated == plain column-major
+        b = oracle_lib.vector_transpose_sim(P, nrow, ncol, a)
+        assert np.array_equal(b, np.asfortranarray(A.T).ravel(order="F"))
+
+
+def test_tridiag_eigh_and_lanczos_vs_dense(oracle_lib):
+    rng = np.random.default_rng(3)
+    n = 40
+    d, e = rng.normal(size=n), np.r_[0.0, rng.normal(size=n - 1)]
+    w, z = oracle_lib.tridiag_eigh(d, e)
+    T = np.diag(d) + np.diag(e[1:], 1) + np.diag(e[1:], -1)
+    assert np.abs(w - np.linalg.eigvalsh(T)).max() < 1e-12
+    assert np.abs(T @ z - z * w).max() < 1e-12
+    mdl = models.hm2x2(1)
+    orc = oracle_lib.Oracle(mdl)
+    isec = models.get_sector(8, 4, 4)
+    w = np.linalg.eigvalsh(orc.dense_hmat(isec))
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+    e0, vec, nit, a, b = orc.lanc_eigh(512, 1e-14)
+    assert abs(e0 - w[0]) < 1e-11
+    assert np.linalg.norm(orc.hxv(vec) - e0 * vec) < 1e-6
+    orc.delete_hv_sector()
+
+
+def test_e0_vs_scipy_eigsh_K2(oracle_lib):
+    """Ns=12 sector (6,6), Dim 853 776: sparse assembly from the oracle CSR + ARPACK."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import eigsh
+    mdl = models.hm2x2(2)
+    orc = oracle_lib.Oracle(mdl)
+    isec = models.get_sector(12, 6, 6)
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+    n = orc.dimup
+    rp, col, val = orc.get_csr(1)
+    Hup = sp.csr_matrix((val.real, col - 1, rp), shape=(n, n))
+    rp, col, val = orc.get_csr(2)
+    Hdw = sp.csr_matrix((val.real, col - 1, rp), shape=(n, n))
+    H = sp.diags(orc.get_diag()) + sp.kron(sp.identity(n), Hup) + sp.kron(Hdw, sp.identity(n))
+    w = eigsh(H.tocsr(), k=1, which="SA", tol=1e-12)[0][0]
+    e0, vec, nit, a, b = orc.lanc_eigh(300, 1e-13)
+    assert abs(e0 - w) < 1e-9 * abs(w)
+    orc.delete_hv_sector()
+
+
+def test_gimp_vs_exact_full_fock(oracle_lib):
+    """4-channel off-diagonal trick + pole/weight accumulation reproduce the exact Lehmann G (Ns=4)."""
+    from tests.gf_pipeline import gimp_element
+    mdl = models.random_model(2, 1, 1, seed=24)
+    H = jw_ed.full_hamiltonian(mdl)
+    w = np.linalg.eigvalsh(H)
+    assert w[1] - w[0] > 1e-6, "need a non-degenerate ground state"
+    Hs = jw_ed.sector_hamiltonian(mdl, 2, 2, H)
+    assert abs(np.linalg.eigvalsh(Hs)[0] - w[0]) < 1e-12, "ground state must live in the (Ns/2,Ns/2) sector"
+    wm = np.pi / 20.0 * (2 * np.arange(1, 33) - 1)
+    G = jw_ed.gimp_exact(mdl, H, wm)
+    for ia, ib in [(1, 1), (2, 2), (1, 2), (2, 1)]:
+        g = gimp_element("oracle", mdl, ia, ib, wm, edo=oracle_lib)
+        assert np.abs(g - G[ia - 1, ib - 1]).max() < 2e-9  # limited by the Lanczos GS vector, not by conventions
+
+
+def test_golden_fixtures(oracle_lib):
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py (oracle outputs, checked against
+    jw_ed at generation time); they guard the oracle against drift and feed the GPU tests."""
+    path = os.path.join(HERE, "golden", "golden_small.npz")
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    for case in meta["cases"]:
+        mdl = getattr(models, case["builder"])(*case["args"])
+        orc = oracle_lib.Oracle(mdl)
+        isec = case["isector"]
+        key = case["key"]
+        orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+        assert np.array_equal(oracle_lib.sector_map(mdl.ns, case["nup"]), g[key + "_map_up"])
+        rp, col, val = orc.get_csr(1)
+        assert np.array_equal(rp, g[key + "_up_rowptr"]) and np.array_equal(col, g[key + "_up_col"])
+        assert np.abs(val - g[key + "_up_val"]).max() < 1e-15
+        v = g[key + "_v"]
+        assert np.abs(orc.hxv(v) - g[key + "_hv"]).max() < 1e-13
+        orc.delete_hv_sector()

@@ -1,0 +1,56 @@
+"""Developer timing sweep (not the bench contract): H x v variants on one GPU with CUDA events."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cdmft_lanc_ed_b200 import models  # noqa: E402
+from cdmft_lanc_ed_b200 import ed_hamiltonian as E  # noqa: E402
+
+
+def time_hxv(n, iters=10, warm=3):
+    v = torch.randn(n, dtype=torch.complex128, device="cuda")
+    v /= v.norm()
+    hv = torch.empty_like(v)
+    for _ in range(warm):
+        E.spHtimesV_p(n, v, hv)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        E.spHtimesV_p(n, v, hv)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "K3"
+    mdl, sec = {"K2": (models.hm2x2(2), (6, 6)), "K3": (models.hm2x2(3), (8, 8)), "K4": (models.bhz2(3), (8, 8))}[which]
+    E.ed_init(0)
+    E.set_stream(torch.cuda.current_stream().cuda_stream)
+    E.ed_set_model(mdl)
+    isec = models.get_sector(mdl.ns, *sec)
+    for sparse in (True, False):
+        for opts in [dict(col_batch=1), dict(col_batch=2), dict(col_batch=4), dict(col_batch=8), dict(col_batch=4, force_sharded=1)]:
+            for k, v in dict(col_batch=4, force_sharded=0).items():
+                E.set_option(k, v)
+            for k, v in opts.items():
+                E.set_option(k, v)
+            t0 = time.time()
+            n = E.build_Hv_sector(isec, sparse)
+            tb = time.time() - t0
+            ms = time_hxv(n)
+            E.delete_Hv_sector()
+            print(json.dumps(dict(cfg=which, sparse=sparse, **opts, n=n, build_s=round(tb, 3), ms=round(ms, 4),
+                                  gbs_alg=round(32 * n / ms / 1e6, 1))), flush=True)
+    E.ed_finalize()
+
+
+if __name__ == "__main__":
+    main()
