@@ -408,10 +408,15 @@ int cdmft_b200_hxv64(int64_t nloc, const void *v, void *hv) {
   if (nloc == 0) return 0;
   const bool dv = is_device_ptr(v), dh = is_device_ptr(hv);
   if (dv != dh) return fail("hxv: v and hv must both be host or both be device pointers");
-  if (dv) return hxv_device((const double2 *)v, (double2 *)hv);
+  if (dv) {
+    CB_CHECK(hxv_device((const double2 *)v, (double2 *)hv));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+  }
   CB_CHECK(ensure_stage(nloc));
   CB_CUDA(cudaMemcpyAsync(c.stage_v, v, (size_t)nloc * 16, cudaMemcpyHostToDevice, c.stream));
   CB_CHECK(hxv_device(c.stage_v, c.stage_hv));
+  CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(hv, c.stage_hv, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
   CB_CUDA(cudaStreamSynchronize(c.stream));
   return 0;

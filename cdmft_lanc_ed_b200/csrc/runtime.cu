@@ -203,8 +203,13 @@ int cdmft_b200_finalize(void) {
 
 int cdmft_b200_set_stream(void *s) {
   CB_REQUIRE_INIT();
-  Ctx &c = ctx();
-  c.stream = s ? (cudaStream_t)s : c.own_stream;
+  ctx().stream = (cudaStream_t)s;  // NULL = the legacy default stream, as in CUDA
+  return 0;
+}
+
+int cdmft_b200_reset_stream(void) {
+  CB_REQUIRE_INIT();
+  ctx().stream = ctx().own_stream;
   return 0;
 }
 

@@ -45,7 +45,7 @@ _lib = None
 # every symbol include/cdmft_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "cdmft_b200_last_error", "cdmft_b200_init", "cdmft_b200_nccl_unique_id", "cdmft_b200_init_rank",
-    "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_launch_count",
+    "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_reset_stream", "cdmft_b200_launch_count",
     "cdmft_b200_set_option", "cdmft_b200_set_model", "cdmft_b200_get_ns", "cdmft_b200_get_sector_dims",
     "cdmft_b200_vecdim_hv_sector", "cdmft_b200_build_hv_sector", "cdmft_b200_delete_hv_sector",
     "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
@@ -136,7 +136,12 @@ def ed_finalize():
 
 
 def set_stream(cuda_stream: int):
+    """Launch on this cudaStream_t handle (0 = CUDA's legacy default stream, torch's default)."""
     _chk(load_library().cdmft_b200_set_stream(C.c_void_p(cuda_stream)))
+
+
+def reset_stream():
+    _chk(load_library().cdmft_b200_reset_stream())
 
 
 def set_option(key: str, value: int):

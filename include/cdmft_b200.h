@@ -69,8 +69,10 @@ int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const voi
  * in rank order, the layout of gather_vector_MPI, ED_SETUP.f90:633-668). Test/debug aid. */
 int cdmft_b200_init_sim(int32_t device, int32_t nranks);
 int cdmft_b200_finalize(void);
-/* launch on this cudaStream_t instead of the library's own stream (0 = back to own stream) */
+/* launch on this cudaStream_t (NULL = CUDA's legacy default stream) instead of the library's own
+ * non-blocking stream; reset_stream goes back to the library's stream */
 int cdmft_b200_set_stream(void *cuda_stream);
+int cdmft_b200_reset_stream(void);
 /* number of kernels this library has launched so far */
 int cdmft_b200_launch_count(int64_t *n);
 /* kernel variant selection for experiments/benchmarks: key/value, see DESIGN.md */
