@@ -37,6 +37,18 @@ struct SpinOp {
   int32_t *ell_col = nullptr;
   double2 *ell_val = nullptr;
   int32_t *rowlen = nullptr;
+  // row blocks = runs of states sharing the top `tbits` bits (contiguous in rank order); hops that
+  // leave those bits alone stay inside a block, so a block x 8 columns is a closed shared-memory tile
+  int32_t tbits = 0, nblocks = 0, max_block = 0;
+  int2 *blocks = nullptr;  // device [nblocks] (start, size)
+  // packed tile CSR for the shared-memory kernels: per row two lists -- sources inside the row block
+  // (word = slot<<11 | coef_id<<4, slot = rel<<3 | swizzle) and outside it (word = row<<11 | coef_id<<4)
+  // -- each padded to rounds of 8 words; *_ptr are row pointers in rounds
+  uint32_t *pk_in = nullptr, *pk_off = nullptr;
+  int32_t *pk_in_ptr = nullptr, *pk_off_ptr = nullptr;  // [n+1]
+  double2 *coef = nullptr;       // [ncoef] distinct signed coefficients, coef[0] = 0
+  int32_t ncoef = 0;
+  bool pk_swizzled = false;      // built for the column pass (slot swizzled with rel&7)
 };
 
 struct Split {  // first (n mod P) ranks get one more (ED_HAMILTONIAN.f90:92-105)
@@ -64,6 +76,7 @@ struct Options {
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
   int64_t row_slab = 256;
+  int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
 };
 
 struct Ctx {
@@ -129,7 +142,7 @@ void set_error(const std::string &s);
 
 // ---- internal entry points shared between translation units ----
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
-                  double const_add, bool want_csr);
+                  double const_add, bool want_csr, bool pack_swizzled = true);
 void free_spin_op(SpinOp &op);
 int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
 int nccl_allreduce_sum(double *dev_buf, int n);

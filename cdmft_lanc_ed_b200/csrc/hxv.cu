@@ -134,6 +134,213 @@ __global__ void __launch_bounds__(256) k_colpass(int64_t n, int64_t ncols, const
 }
 
 // ------------------------------------------------------------------------------------
+// Column pass, shared-memory tile variant.  One CTA owns (row block) x (8 columns): the block is a
+// run of Fock states sharing their top bits, so every hop that leaves those bits alone lands
+// inside the tile.  The tile is staged once with cp.async (16 B, coalesced along the rows) into
+// tile[row][8 slots], slot = column ^ (row & 7); in the compute phase 8 consecutive lanes own the
+// 8 columns of ONE output row, so each gather reads one full 128-byte line of shared memory:
+// conflict-free by construction.  The CSR row is fetched cooperatively (lane c loads entry
+// base+c) and broadcast inside the 8-lane group with shuffles.  Hops that change the top bits
+// (a minority) gather from global memory / L2.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <bool REALH, bool DIRECT>
+__global__ void __launch_bounds__(1024, 1) k_colpass_tile(int64_t n, int64_t ncols, const double2 *__restrict__ v,
+                                                           double2 *__restrict__ out, const int2 *__restrict__ blocks,
+                                                           int nblocks, const int32_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ col,
+                                                           const double2 *__restrict__ val, OpArgs op, DiagArgs dg) {
+  extern __shared__ double2 tile[];
+  const int blk = blockIdx.x % nblocks;
+  const int64_t c0 = (int64_t)(blockIdx.x / nblocks) * 8;
+  const int2 b = blocks[blk];
+  const int g0 = b.x, ng = b.y;
+  const int nb = (int)min((int64_t)8, ncols - c0);
+  // ---- stage the tile: thread -> (row g, column cc), rows fastest => 512 B coalesced per warp
+  for (int idx = threadIdx.x; idx < ng * 8; idx += blockDim.x) {
+    const int cc = idx / ng, g = idx - cc * ng;
+    if (cc < nb) cp_async16(&tile[g * 8 + (cc ^ (g & 7))], v + (g0 + g) + (c0 + cc) * n);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // ---- compute: 8 lanes = 8 columns of one row
+  const int c = threadIdx.x & 7;
+  const int rsub = threadIdx.x >> 3, rstep = blockDim.x >> 3;
+  const int64_t colg = c0 + min(c, nb - 1);  // ragged last group: clamp loads, skip the store
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  for (int g = rsub; g < ng; g += rstep) {
+    const int64_t i = g0 + g;
+    double2 acc = make_double2(0.0, 0.0);
+    if (dg.enabled) {
+      uint32_t mu_imp = (uint32_t)__ldg(dg.map_row + i) & ((1u << dg.nimp) - 1u);
+      double d = diag_value(dg, i, mu_imp, colg);
+      double2 x = tile[g * 8 + (c ^ (g & 7))];
+      acc = make_double2(d * x.x, d * x.y);
+    }
+    if (!DIRECT) {
+      const int32_t p0 = __ldg(rowptr + i), p1 = __ldg(rowptr + i + 1);
+      for (int32_t base = p0; base < p1; base += 8) {
+        const int32_t my = base + c;
+        int32_t jc = 0;
+        double2 hv = make_double2(0.0, 0.0);
+        if (my < p1) { jc = __ldg(col + my); hv = ldg2(val + my); }
+        const int cnt = min(8, p1 - base);
+        for (int kk = 0; kk < cnt; kk++) {
+          const int32_t j = __shfl_sync(gmask, jc, kk, 8);
+          const double hx = __shfl_sync(gmask, hv.x, kk, 8);
+          double hy = 0.0;
+          if (!REALH) hy = __shfl_sync(gmask, hv.y, kk, 8);
+          const unsigned rel = (unsigned)(j - g0);
+          double2 x;
+          if (rel < (unsigned)ng) x = tile[rel * 8 + (c ^ (rel & 7))];
+          else x = ldg2(v + j + colg * n);
+          if (REALH) rfma(acc, hx, x); else cfma(acc, make_double2(hx, hy), x);
+        }
+      }
+    } else {
+      const uint32_t s = (uint32_t)__ldg(op.map + i);
+      for (int t = 0; t < op.nterms; t++) {
+        const Term tm = op.terms[t];
+        if (((s >> tm.a) & 1u) && !((s >> tm.b) & 1u)) {
+          const uint32_t m = (s & ~(1u << tm.a)) | (1u << tm.b);
+          const int32_t j = lin_rank_d(op.lin_lo, op.lin_hi, op.lbits, m);
+          const double sg = hop_sign_d(s, tm.a, tm.b);
+          const unsigned rel = (unsigned)(j - g0);
+          double2 x;
+          if (rel < (unsigned)ng) x = tile[rel * 8 + (c ^ (rel & 7))];
+          else x = ldg2(v + j + colg * n);
+          if (REALH) rfma(acc, tm.re * sg, x); else cfma(acc, make_double2(tm.re * sg, tm.im * sg), x);
+        }
+      }
+    }
+    if (c < nb) out[i + colg * n] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Packed shared-memory tile kernel (SPARSE mode, the fast path for both passes).
+// Same tiling as k_colpass_tile / k_rowpass_tile, but the operator rows come from the packed tile
+// CSR (see ctx.h): per row one list of sources inside the row block (shared memory) and one of
+// sources outside it (global memory / L2), 32-bit words in rounds of 8.  Lane c of an 8-lane group
+// loads word c of the round, the group broadcasts the words with SHFL; an in-block entry then costs
+// one shift, one LOP3 (slot ^ lane, mask), one AND (coefficient offset), LDS.128 + LDS.64, 2 DFMA.
+//   COLMODE = true : column pass. tile[row][slot], slot = column ^ (row&7); element (g, cc) of the
+//                    tile lives at v[(g0+g) + (c0+cc)*ld]; off-block source j at v[j + (c0+cc)*ld]
+//   COLMODE = false: row pass. tile[dwstate][iup 0..7]; element (g, bb) at v[(i0+bb) + (g0+g)*ld];
+//                    off-block source j at v[(i0+bb) + j*ld]; out is accumulated (+=)
+// Control flow is warp-uniform (the 4 row groups of a warp run the same number of rounds; short
+// rows run null rounds with coefficient id 0) so the shuffles are plain full-mask SHFL.IDX.
+// ------------------------------------------------------------------------------------
+template <bool REALH, bool COLMODE>
+__global__ void __launch_bounds__(1024, 1) k_tile_pk(int64_t ld, int64_t nbatch, const double2 *__restrict__ v,
+                                                      double2 *__restrict__ out, const int2 *__restrict__ blocks,
+                                                      int nblocks, const int32_t *__restrict__ in_ptr,
+                                                      const uint32_t *__restrict__ pk_in,
+                                                      const int32_t *__restrict__ off_ptr,
+                                                      const uint32_t *__restrict__ pk_off,
+                                                      const double2 *__restrict__ coef_g, DiagArgs dg) {
+  extern __shared__ double2 smem[];
+  double2 *coef = smem;        // [128]
+  double2 *tile = smem + 128;  // [ng*8]
+  const int blk = blockIdx.x % nblocks;
+  const int64_t b0 = (int64_t)(blockIdx.x / nblocks) * 8;
+  const int2 b = blocks[blk];
+  const int g0 = b.x, ng = b.y;
+  const int nb = (int)min((int64_t)8, nbatch - b0);
+  if (threadIdx.x < 128) coef[threadIdx.x] = coef_g[threadIdx.x];
+  if (COLMODE) {
+    for (int idx = threadIdx.x; idx < ng * 8; idx += blockDim.x) {
+      const int cc = idx / ng, g = idx - cc * ng;
+      if (cc < nb) cp_async16(&tile[g * 8 + (cc ^ (g & 7))], v + (g0 + g) + (b0 + cc) * ld);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < ng * 8; idx += blockDim.x) {
+      const int bb = idx & 7, g = idx >> 3;
+      if (bb < nb) cp_async16(&tile[idx], v + (b0 + bb) + (int64_t)(g0 + g) * ld);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int c = threadIdx.x & 7;
+  const unsigned c16 = (unsigned)c << 4;
+  const int rsub = threadIdx.x >> 3, rstep = blockDim.x >> 3;
+  const int64_t bg = b0 + min(c, nb - 1);  // my batch entry (clamped on the ragged last group)
+  // off-block gathers: COLMODE v[j + bg*ld], row mode v[bg + j*ld]
+  const double2 *vbase = COLMODE ? v + bg * ld : v + bg;
+  const int64_t gstride = COLMODE ? 1 : ld;
+  const char *tile_b = (const char *)tile;
+  const char *coef_b = (const char *)coef;
+  const int niter = (ng + rstep - 1) / rstep;
+  for (int it = 0; it < niter; it++) {
+    const int g_raw = rsub + it * rstep;
+    const bool valid = g_raw < ng;
+    const int g = valid ? g_raw : ng - 1;
+    const int64_t i = g0 + g;
+    double2 acc = make_double2(0.0, 0.0);
+    if (COLMODE && dg.enabled) {
+      uint32_t mu_imp = (uint32_t)__ldg(dg.map_row + i) & ((1u << dg.nimp) - 1u);
+      double d = diag_value(dg, i, mu_imp, bg);
+      double2 x = tile[(g << 3) | ((c ^ g) & 7)];
+      acc = make_double2(d * x.x, d * x.y);
+    }
+    // ---- sources outside the row block (long latency) first
+    {
+      const int32_t o0 = __ldg(off_ptr + i);
+      const int no = valid ? __ldg(off_ptr + i + 1) - o0 : 0;
+      int nomax = max(no, __shfl_xor_sync(0xffffffffu, no, 8));
+      nomax = max(nomax, __shfl_xor_sync(0xffffffffu, nomax, 16));
+      for (int rr = 0; rr < nomax; rr++) {
+        uint32_t mine = 0u;
+        if (rr < no) mine = __ldg(pk_off + (int64_t)(o0 + rr) * 8 + c);
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          const uint32_t w = __shfl_sync(0xffffffffu, mine, kk, 8);
+          const uint32_t idb = w & 0x7F0u;
+          if (idb) {
+            const double2 x = ldg2(vbase + (int64_t)(w >> 11) * gstride);
+            if (REALH) rfma(acc, *(const double *)(coef_b + idb), x);
+            else cfma(acc, *(const double2 *)(coef_b + idb), x);
+          }
+        }
+      }
+    }
+    // ---- sources inside the row block: shared memory
+    {
+      const int32_t r0 = __ldg(in_ptr + i);
+      const int nr = valid ? __ldg(in_ptr + i + 1) - r0 : 0;
+      int nrmax = max(nr, __shfl_xor_sync(0xffffffffu, nr, 8));
+      nrmax = max(nrmax, __shfl_xor_sync(0xffffffffu, nrmax, 16));
+      const uint32_t nullw = (((uint32_t)g << 3) | (COLMODE ? ((uint32_t)g & 7u) : 0u)) << 11;  // coef id 0 = 0.0
+      uint32_t mine = nullw;
+      if (0 < nr) mine = __ldg(pk_in + (int64_t)r0 * 8 + c);
+      for (int rr = 0; rr < nrmax; rr++) {
+        uint32_t next = nullw;  // prefetch the next round's word
+        if (rr + 1 < nr) next = __ldg(pk_in + (int64_t)(r0 + rr + 1) * 8 + c);
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          const uint32_t w = __shfl_sync(0xffffffffu, mine, kk, 8);
+          const uint32_t addr = ((w >> 7) ^ c16) & 0xFFFFFFF0u;
+          const double2 x = *(const double2 *)(tile_b + addr);
+          if (REALH) rfma(acc, *(const double *)(coef_b + (w & 0x7F0u)), x);
+          else cfma(acc, *(const double2 *)(coef_b + (w & 0x7F0u)), x);
+        }
+        mine = next;
+      }
+    }
+    if (valid && c < nb) {
+      double2 *o = COLMODE ? out + i + bg * ld : out + bg + i * ld;
+      if (!COLMODE) { double2 y = *o; acc.x += y.x; acc.y += y.y; }
+      *o = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Row pass (one rank, no transpose): out(i,c) += sum_k Hd(c,j_k) v(i,j_k).
 // Threads run along i (contiguous), the operator row of column c is warp-uniform (broadcast
 // loads).  Grid x = columns (fastest) inside one slab of rows, so a slab (rows x all columns)
@@ -182,6 +389,84 @@ __global__ void __launch_bounds__(256) k_rowpass(int64_t n /*rows=DimUp*/, int64
   o.x += acc.x;
   o.y += acc.y;
   out[i + c * n] = o;
+}
+
+// ------------------------------------------------------------------------------------
+// Row pass, shared-memory tile variant: one CTA owns (block of dw states) x (8 consecutive iup).
+// Same structure as k_colpass_tile with the roles swapped: the 8 batch entries of one dw state
+// are 128 contiguous bytes in global memory, so staging, the gathers (tile[j][0..7]), the
+// off-block gathers from L2 and the read-modify-write of out are all full 128-byte lines.
+//   out(i, c) += sum_k Hd(c, j_k) v(i, j_k)
+// ------------------------------------------------------------------------------------
+template <bool REALH, bool DIRECT>
+__global__ void __launch_bounds__(1024, 1) k_rowpass_tile(int64_t n /*rows = DimUp*/, const double2 *__restrict__ v,
+                                                           double2 *__restrict__ out, const int2 *__restrict__ blocks,
+                                                           int nblocks, const int32_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ col,
+                                                           const double2 *__restrict__ val, OpArgs op) {
+  extern __shared__ double2 tile[];
+  const int blk = blockIdx.x % nblocks;
+  const int64_t i0 = (int64_t)(blockIdx.x / nblocks) * 8;
+  const int2 b = blocks[blk];
+  const int g0 = b.x, ng = b.y;
+  const int nb = (int)min((int64_t)8, n - i0);
+  for (int idx = threadIdx.x; idx < ng * 8; idx += blockDim.x) {
+    const int bb = idx & 7, g = idx >> 3;
+    if (bb < nb) cp_async16(&tile[idx], v + (i0 + bb) + (int64_t)(g0 + g) * n);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int c = threadIdx.x & 7;
+  const int rsub = threadIdx.x >> 3, rstep = blockDim.x >> 3;
+  const int64_t ig = i0 + min(c, nb - 1);
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  for (int g = rsub; g < ng; g += rstep) {
+    const int64_t cdw = g0 + g;  // dw state = global column
+    double2 acc = make_double2(0.0, 0.0);
+    if (!DIRECT) {
+      const int32_t p0 = __ldg(rowptr + cdw), p1 = __ldg(rowptr + cdw + 1);
+      for (int32_t base = p0; base < p1; base += 8) {
+        const int32_t my = base + c;
+        int32_t jc = 0;
+        double2 hv = make_double2(0.0, 0.0);
+        if (my < p1) { jc = __ldg(col + my); hv = ldg2(val + my); }
+        const int cnt = min(8, p1 - base);
+        for (int kk = 0; kk < cnt; kk++) {
+          const int32_t j = __shfl_sync(gmask, jc, kk, 8);
+          const double hx = __shfl_sync(gmask, hv.x, kk, 8);
+          double hy = 0.0;
+          if (!REALH) hy = __shfl_sync(gmask, hv.y, kk, 8);
+          const unsigned rel = (unsigned)(j - g0);
+          double2 x;
+          if (rel < (unsigned)ng) x = tile[rel * 8 + c];
+          else x = ldg2(v + ig + (int64_t)j * n);
+          if (REALH) rfma(acc, hx, x); else cfma(acc, make_double2(hx, hy), x);
+        }
+      }
+    } else {
+      const uint32_t s = (uint32_t)__ldg(op.map + cdw);
+      for (int t = 0; t < op.nterms; t++) {
+        const Term tm = op.terms[t];
+        if (((s >> tm.a) & 1u) && !((s >> tm.b) & 1u)) {
+          const uint32_t m = (s & ~(1u << tm.a)) | (1u << tm.b);
+          const int32_t j = lin_rank_d(op.lin_lo, op.lin_hi, op.lbits, m);
+          const double sg = hop_sign_d(s, tm.a, tm.b);
+          const unsigned rel = (unsigned)(j - g0);
+          double2 x;
+          if (rel < (unsigned)ng) x = tile[rel * 8 + c];
+          else x = ldg2(v + ig + (int64_t)j * n);
+          if (REALH) rfma(acc, tm.re * sg, x); else cfma(acc, make_double2(tm.re * sg, tm.im * sg), x);
+        }
+      }
+    }
+    if (c < nb) {
+      double2 *o = out + ig + cdw * n;
+      double2 y = *o;
+      y.x += acc.x;
+      y.y += acc.y;
+      *o = y;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -257,7 +542,62 @@ static int launch_colpass(const SpinOp &s, int64_t ncols, const double2 *v, doub
   return 0;
 }
 
+// packed tile kernel: ld = leading dimension of v, nbatch = number of batch entries (columns for the
+// column pass, iup rows for the row pass)
+template <bool REALH, bool COLMODE>
+static int launch_tile_pk(const SpinOp &s, int64_t ld, int64_t nbatch, const double2 *v, double2 *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const size_t smem = ((size_t)s.max_block * 8 + 128) * sizeof(double2);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CB_CUDA(cudaFuncSetAttribute(k_tile_pk<REALH, COLMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t nct = ((nbatch + 7) / 8) * s.nblocks;
+  if (nct > 0x7fffffffLL) return fail("tile_pk: grid too large");
+  int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(256, ((int64_t)s.max_block * 8 + 255) / 256 * 256));
+  k_tile_pk<REALH, COLMODE><<<(unsigned)nct, threads, smem, c.stream>>>(ld, nbatch, v, out, s.blocks, s.nblocks, s.pk_in_ptr, s.pk_in, s.pk_off_ptr, s.pk_off,
+                                                                          s.coef, dg);
+  c.launches++;
+  return 0;
+}
+
+template <bool REALH, bool DIRECT>
+static int launch_colpass_tile_t(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const size_t smem = (size_t)s.max_block * 8 * sizeof(double2);
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    CB_CUDA(cudaFuncSetAttribute(k_colpass_tile<REALH, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t ngroups = (ncols + 7) / 8;
+  const int64_t nct = ngroups * s.nblocks;
+  if (nct > 0x7fffffffLL) return fail("colpass_tile: grid too large");
+  // enough threads to cover the biggest block once, in multiples of 256 (8 lanes per row)
+  int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(256, ((int64_t)s.max_block * 8 + 255) / 256 * 256));
+  k_colpass_tile<REALH, DIRECT><<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.rowptr,
+                                                                             s.col, s.val, op_args(s), dg);
+  c.launches++;
+  return 0;
+}
+
+static int launch_colpass_tile(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  if (c.real_h) return direct ? launch_colpass_tile_t<true, true>(s, ncols, v, out, dg) : launch_colpass_tile_t<true, false>(s, ncols, v, out, dg);
+  return direct ? launch_colpass_tile_t<false, true>(s, ncols, v, out, dg) : launch_colpass_tile_t<false, false>(s, ncols, v, out, dg);
+}
+
 static int colpass(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
+  if (ncols <= 0 || s.n <= 0) return 0;
+  // variant 0/2 = shared-memory tiles (default), 1 = generic global-gather kernel
+  const int64_t var = ctx().opt.colpass_variant;
+  if (var != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+    if (var != 2 && ctx().mode == CDMFT_B200_SPARSE && s.pk_in && s.pk_swizzled)
+      return ctx().real_h ? launch_tile_pk<true, true>(s, s.n, ncols, v, out, dg) : launch_tile_pk<false, true>(s, s.n, ncols, v, out, dg);
+    return launch_colpass_tile(s, ncols, v, out, dg);
+  }
   switch (ctx().opt.col_batch) {
     case 1: return launch_colpass<1>(s, ncols, v, out, dg);
     case 2: return launch_colpass<2>(s, ncols, v, out, dg);
@@ -266,9 +606,36 @@ static int colpass(const SpinOp &s, int64_t ncols, const double2 *v, double2 *ou
   }
 }
 
+template <bool REALH, bool DIRECT>
+static int launch_rowpass_tile_t(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
+  Ctx &c = ctx();
+  const size_t smem = (size_t)s.max_block * 8 * sizeof(double2);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CB_CUDA(cudaFuncSetAttribute(k_rowpass_tile<REALH, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int64_t nct = ((nrows + 7) / 8) * s.nblocks;
+  if (nct > 0x7fffffffLL) return fail("rowpass_tile: grid too large");
+  int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(256, ((int64_t)s.max_block * 8 + 255) / 256 * 256));
+  k_rowpass_tile<REALH, DIRECT><<<(unsigned)nct, threads, smem, c.stream>>>(nrows, v, out, s.blocks, s.nblocks, s.rowptr, s.col,
+                                                                             s.val, op_args(s));
+  c.launches++;
+  return 0;
+}
+
 static int rowpass(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
   Ctx &c = ctx();
   if (s.n <= 0 || nrows <= 0) return 0;
+  if (c.opt.rowpass_variant != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+    const bool direct = c.mode == CDMFT_B200_DIRECT;
+    if (c.opt.rowpass_variant != 2 && !direct && s.pk_in && !s.pk_swizzled) {
+      DiagArgs nodiag{};
+      return c.real_h ? launch_tile_pk<true, false>(s, nrows, nrows, v, out, nodiag) : launch_tile_pk<false, false>(s, nrows, nrows, v, out, nodiag);
+    }
+    if (c.real_h) return direct ? launch_rowpass_tile_t<true, true>(s, nrows, v, out) : launch_rowpass_tile_t<true, false>(s, nrows, v, out);
+    return direct ? launch_rowpass_tile_t<false, true>(s, nrows, v, out) : launch_rowpass_tile_t<false, false>(s, nrows, v, out);
+  }
   dim3 grid((unsigned)s.n, (unsigned)((nrows + 255) / 256));
   if (grid.y > 65535) return fail("rowpass: too many row chunks");
   OpArgs op = op_args(s);

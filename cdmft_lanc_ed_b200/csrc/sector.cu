@@ -134,6 +134,50 @@ __global__ void k_csr_to_ell(int64_t n, const int32_t *__restrict__ rowptr, cons
   }
 }
 
+// packed tile CSR (see ctx.h): per row two lists (sources inside / outside the row block), each
+// padded to rounds of 8 words; word = (slot_or_row << 11) | (coef_id << 4)
+__device__ __forceinline__ int find_block(const int2 *__restrict__ blocks, int nblocks, int64_t i) {
+  int lo = 0, hi = nblocks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (blocks[mid].x <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void k_pk_rounds(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                            const int2 *__restrict__ blocks, int nblocks, int32_t *__restrict__ rounds_in,
+                            int32_t *__restrict__ rounds_off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 b = blocks[find_block(blocks, nblocks, i)];
+  int nin = 0, noff = 0;
+  for (int32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+    if ((uint32_t)(col[p] - b.x) < (uint32_t)b.y) nin++; else noff++;
+  }
+  rounds_in[i] = (nin + 7) >> 3;
+  rounds_off[i] = (noff + 7) >> 3;
+}
+__global__ void k_pk_fill(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                          const uint8_t *__restrict__ coefidx, const int2 *__restrict__ blocks, int nblocks,
+                          const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ off_ptr, int swz,
+                          uint32_t *__restrict__ pk_in, uint32_t *__restrict__ pk_off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 b = blocks[find_block(blocks, nblocks, i)];
+  const int g0 = b.x, ng = b.y;
+  int64_t qi = (int64_t)in_ptr[i] * 8, qo = (int64_t)off_ptr[i] * 8;
+  const int64_t ei = (int64_t)in_ptr[i + 1] * 8, eo = (int64_t)off_ptr[i + 1] * 8;
+  for (int32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+    const int32_t j = col[p];
+    const uint32_t rel = (uint32_t)(j - g0), id = coefidx[p];
+    if (rel < (uint32_t)ng) pk_in[qi++] = ((((rel << 3) | (swz ? (rel & 7u) : 0u))) << 11) | (id << 4);
+    else pk_off[qo++] = ((uint32_t)j << 11) | (id << 4);
+  }
+  const uint32_t rel = (uint32_t)(i - g0);  // padding: coefficient id 0 (= 0.0) on a valid slot / row
+  while (qi < ei) pk_in[qi++] = (((rel << 3) | (swz ? (rel & 7u) : 0u))) << 11;
+  while (qo < eo) pk_off[qo++] = (uint32_t)i << 11;
+}
+
 // ED_SPARSE_MAP (ED_SPARSE_MAP.f90:101-121 via ED_SETUP.f90:757-759): counting pass + ordered fill.
 // States of one impurity configuration appear in ascending sector index, so the position inside
 // the row is the number of earlier sector states with the same impurity bits.
@@ -178,7 +222,7 @@ static int64_t binom64(int n, int k) {
   } while (0)
 
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
-                  double const_add, bool want_csr) {
+                  double const_add, bool want_csr, bool pack_swizzled) {
   Ctx &c = ctx();
   const int ns = c.ns;
   op.npart = npart;
@@ -240,6 +284,84 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
     CB_CHECK(dev_alloc(&op.ell_val, (int64_t)op.ell_w * op.n));
     LAUNCH_1D(k_csr_to_ell, op.n, op.n, op.rowptr, op.col, op.val, op.ell_w, op.ell_col, op.ell_val);
   }
+  // row blocks by the top tbits bits: smallest tbits with every block <= tile_rows
+  {
+    const int64_t cap = std::max<int64_t>(8, c.opt.tile_rows);
+    int t = 0;
+    for (; t <= ns; t++) {
+      int64_t mx = 0;
+      for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, npart - k));
+      if (mx <= cap) break;
+    }
+    op.tbits = t;
+    std::vector<int2> blk;
+    int64_t start = 0, mx = 0;
+    for (uint32_t P = 0; P < (1u << t); P++) {
+      int64_t sz = binom64(ns - t, npart - __builtin_popcount(P));
+      if (sz <= 0) continue;
+      blk.push_back(make_int2((int)start, (int)sz));
+      start += sz;
+      mx = std::max(mx, sz);
+    }
+    if (start != op.n) return fail("internal: row blocks do not cover the sector");
+    op.nblocks = (int32_t)blk.size();
+    op.max_block = (int32_t)mx;
+    CB_CHECK(dev_alloc(&op.blocks, (int64_t)blk.size()));
+    CB_CUDA(cudaMemcpyAsync(op.blocks, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+  }
+  // packed tile CSR: distinct signed coefficients -> 7-bit ids (host; the matrices are small)
+  if (want_csr && op.nnz > 0 && op.n < (1 << 21) && (int64_t)op.max_block < (1 << 18)) {
+    std::vector<double2> hval(op.nnz);
+    CB_CUDA(cudaMemcpyAsync(hval.data(), op.val, op.nnz * sizeof(double2), cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    std::vector<double2> table;
+    table.push_back(make_double2(0.0, 0.0));
+    std::vector<uint8_t> ids(op.nnz);
+    bool ok = true;
+    for (int64_t k = 0; k < op.nnz && ok; k++) {
+      int found = -1;
+      for (size_t t = 1; t < table.size(); t++)
+        if (table[t].x == hval[k].x && table[t].y == hval[k].y) { found = (int)t; break; }
+      if (found < 0) {
+        if (table.size() >= 128) { ok = false; break; }
+        table.push_back(hval[k]);
+        found = (int)table.size() - 1;
+      }
+      ids[k] = (uint8_t)found;
+    }
+    if (ok) {
+      uint8_t *d_ids = nullptr;
+      int32_t *d_rounds = nullptr;
+      CB_CHECK(dev_alloc(&d_ids, op.nnz));
+      CB_CHECK(dev_alloc(&d_rounds, op.n));
+      CB_CUDA(cudaMemcpyAsync(d_ids, ids.data(), op.nnz, cudaMemcpyHostToDevice, c.stream));
+      int32_t *d_rounds2 = nullptr;
+      CB_CHECK(dev_alloc(&d_rounds2, op.n));
+      CB_CHECK(dev_alloc(&op.pk_in_ptr, op.n + 1));
+      CB_CHECK(dev_alloc(&op.pk_off_ptr, op.n + 1));
+      LAUNCH_1D(k_pk_rounds, op.n, op.n, op.rowptr, op.col, op.blocks, op.nblocks, d_rounds, d_rounds2);
+      k_exclusive_scan<<<1, 1024, 0, c.stream>>>(op.n, d_rounds, op.pk_in_ptr);
+      k_exclusive_scan<<<1, 1024, 0, c.stream>>>(op.n, d_rounds2, op.pk_off_ptr);
+      c.launches += 2;
+      int32_t tot_in = 0, tot_off = 0;
+      CB_CUDA(cudaMemcpyAsync(&tot_in, op.pk_in_ptr + op.n, 4, cudaMemcpyDeviceToHost, c.stream));
+      CB_CUDA(cudaMemcpyAsync(&tot_off, op.pk_off_ptr + op.n, 4, cudaMemcpyDeviceToHost, c.stream));
+      CB_CUDA(cudaStreamSynchronize(c.stream));
+      CB_CHECK(dev_alloc(&op.pk_in, (int64_t)tot_in * 8));
+      CB_CHECK(dev_alloc(&op.pk_off, (int64_t)tot_off * 8));
+      LAUNCH_1D(k_pk_fill, op.n, op.n, op.rowptr, op.col, d_ids, op.blocks, op.nblocks, op.pk_in_ptr, op.pk_off_ptr,
+                pack_swizzled ? 1 : 0, op.pk_in, op.pk_off);
+      cudaFree(d_rounds2);
+      op.ncoef = (int32_t)table.size();
+      CB_CHECK(dev_alloc(&op.coef, 128));
+      table.resize(128, make_double2(0.0, 0.0));
+      CB_CUDA(cudaMemcpyAsync(op.coef, table.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice, c.stream));
+      op.pk_swizzled = pack_swizzled;
+      CB_CUDA(cudaStreamSynchronize(c.stream));
+      cudaFree(d_ids);
+      cudaFree(d_rounds);
+    }
+  }
   CB_CUDA(cudaStreamSynchronize(c.stream));
   cudaFree(d_e);
   cudaFree(d_sp);
@@ -250,7 +372,7 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
 void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
-  dev_free(op.rowlen);
+  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
   op = SpinOp();
 }
 
@@ -313,7 +435,10 @@ int cdmft_b200_build_hv_sector(int32_t isector, int32_t mode, int64_t *nloc) {
   c.hsector = isector;
   c.mode = mode;
   CB_CHECK(build_spin_op(c.up, nup, c.terms_up, c.e_up, c.const0, mode == CDMFT_B200_SPARSE));
-  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE));
+  // Hdw acts on the contiguous index of the transposed vector when sharded (column pass, swizzled
+  // tile) and on the strided index of v otherwise (row pass, natural tile)
+  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE,
+                         c.spmd || c.sim || c.opt.force_sharded));
   c.dimup = c.up.n; c.dimdw = c.dw.n; c.dim = c.dimup * c.dimdw;
   c.p_eff = (int)std::min<int64_t>(c.nranks, c.dimdw);
   c.rk.clear();

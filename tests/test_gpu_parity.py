@@ -235,3 +235,39 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     g_prod = gimp_element("product", mdl, 1, 2, wm, ed=ed)
     g_orc = gimp_element("oracle", mdl, 1, 2, wm, edo=oracle_lib)
     assert _relerr(g_prod, g_orc) < 1e-6
+
+
+@pytest.mark.parametrize("opts", [
+    dict(colpass_variant=1, rowpass_variant=1, col_batch=1),   # generic global-gather kernels
+    dict(colpass_variant=1, rowpass_variant=1, col_batch=8),
+    dict(colpass_variant=0, rowpass_variant=0, tile_rows=1800),  # shared-memory tiles, one block
+    dict(colpass_variant=0, rowpass_variant=0, tile_rows=40),    # many row blocks: off-block gathers
+    dict(colpass_variant=0, rowpass_variant=0, tile_rows=9),
+    dict(colpass_variant=0, rowpass_variant=1, tile_rows=25, force_sharded=1),
+    dict(colpass_variant=2, rowpass_variant=2, tile_rows=40),    # unpacked tile kernels
+    dict(colpass_variant=2, rowpass_variant=0, tile_rows=30, force_sharded=1),
+])
+@pytest.mark.parametrize("name", ["hm2x2_nb2", "bhz2_nb1", "rand_c_L2O2B1_S2"])
+def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
+    """Every kernel variant (generic / shared-memory tiles with forced small row blocks / sharded path on
+    one rank) against the oracle, SPARSE and DIRECT."""
+    mdl = MODELS[name]()
+    orc = oracle_lib.Oracle(mdl)
+    ed.ed_set_model(mdl)
+    defaults = dict(colpass_variant=0, rowpass_variant=0, col_batch=4, tile_rows=1800, force_sharded=0)
+    try:
+        for k, v in {**defaults, **opts}.items():
+            ed.set_option(k, v)
+        ns = mdl.ns
+        for nup, ndw in [(ns // 2, ns // 2), (ns // 2 + 1, ns // 2 - 1), (1, ns - 2)]:
+            isec = models.get_sector(ns, nup, ndw)
+            for sparse in (True, False):
+                n = ed.build_Hv_sector(isec, sparse)
+                orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+                v = _rand_vec(n, seed=isec)
+                assert _relerr(ed.hxv(v), orc.hxv(v)) < RTOL, (opts, nup, ndw, sparse)
+                ed.delete_Hv_sector()
+                orc.delete_hv_sector()
+    finally:
+        for k, v in defaults.items():
+            ed.set_option(k, v)

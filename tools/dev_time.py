@@ -29,6 +29,11 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
+SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=0, rowpass_variant=1),
+         dict(colpass_variant=1, rowpass_variant=0), dict(), dict(colpass_variant=2, rowpass_variant=2),
+         dict(tile_rows=1000), dict(force_sharded=1)]
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "K3"
     mdl, sec = {"K2": (models.hm2x2(2), (6, 6)), "K3": (models.hm2x2(3), (8, 8)), "K4": (models.bhz2(3), (8, 8))}[which]
@@ -37,8 +42,8 @@ def main():
     E.ed_set_model(mdl)
     isec = models.get_sector(mdl.ns, *sec)
     for sparse in (True, False):
-        for opts in [dict(col_batch=1), dict(col_batch=2), dict(col_batch=4), dict(col_batch=8), dict(col_batch=4, force_sharded=1)]:
-            for k, v in dict(col_batch=4, force_sharded=0).items():
+        for opts in SWEEP:
+            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=0, rowpass_variant=0, tile_rows=1800).items():
                 E.set_option(k, v)
             for k, v in opts.items():
                 E.set_option(k, v)
