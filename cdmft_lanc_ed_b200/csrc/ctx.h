@@ -41,6 +41,8 @@ struct SpinOp {
   // leave those bits alone stay inside a block, so a block x 8 columns is a closed shared-memory tile
   int32_t tbits = 0, nblocks = 0, max_block = 0;
   int2 *blocks = nullptr;  // device [nblocks] (start, size)
+  int32_t nblocks_l1 = 0;   // finer blocks for the L1-blocked row pass
+  int2 *blocks_l1 = nullptr;
   // packed tile CSR for the shared-memory kernels: per row two lists -- sources inside the row block
   // (word = slot<<11 | coef_id<<4, slot = rel<<3 | swizzle) and outside it (word = row<<11 | coef_id<<4)
   // -- each padded to rounds of 8 words; *_ptr are row pointers in rounds
@@ -71,12 +73,15 @@ struct RankState {
 };
 
 struct Options {
-  int64_t colpass_variant = 0;  // 0 = auto
-  int64_t rowpass_variant = 0;
+  // kernel variants: 1 = generic global-gather kernels (default: fastest measured on B200, see
+  // DESIGN.md), 0 = packed shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass
+  int64_t colpass_variant = 1;
+  int64_t rowpass_variant = 1;
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
   int64_t row_slab = 256;
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
+  int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)
 };
 
 struct Ctx {

@@ -470,6 +470,56 @@ __global__ void __launch_bounds__(1024, 1) k_rowpass_tile(int64_t n /*rows = Dim
 }
 
 // ------------------------------------------------------------------------------------
+// Row pass, L1-blocked variant: one CTA (32 warps) owns 32 consecutive iup rows x one block of
+// dw states sharing their top bits.  Lanes run along iup, so every gather is one coalesced 512-byte
+// line set and the operator row is warp-uniform (broadcast loads, no shuffles).  All warps of the
+// CTA work on the same 32 rows, so the block's slice of v (block x 512 B, <= ~128 KB) stays in the
+// SM's L1 after the first touch: hops inside the block hit L1, only hops that change the top bits
+// go to L2.  No shared memory, no staging, no barriers.
+//   out(i, c) += sum_k Hd(c, j_k) v(i, j_k)
+// ------------------------------------------------------------------------------------
+template <bool REALH>
+__global__ void __launch_bounds__(1024, 1) k_rowpass_l1(int64_t n /*rows = DimUp*/, const double2 *__restrict__ v,
+                                                         double2 *__restrict__ out, const int2 *__restrict__ blocks,
+                                                         int nblocks, const int32_t *__restrict__ rowptr,
+                                                         const int32_t *__restrict__ col,
+                                                         const double2 *__restrict__ val) {
+  const int blk = blockIdx.x % nblocks;
+  const int64_t i = (int64_t)(blockIdx.x / nblocks) * 32 + (threadIdx.x & 31);
+  const int2 b = blocks[blk];
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool live = i < n;
+  const double2 *vi = v + (live ? i : n - 1);
+  for (int g = warp; g < b.y; g += nwarps) {
+    const int64_t c = b.x + g;
+    const int32_t p0 = __ldg(rowptr + c), p1 = __ldg(rowptr + c + 1);
+    double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+    int32_t p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      const double2 x0 = ldg2(vi + (int64_t)__ldg(col + p) * n);
+      const double2 x1 = ldg2(vi + (int64_t)__ldg(col + p + 1) * n);
+      const double2 x2 = ldg2(vi + (int64_t)__ldg(col + p + 2) * n);
+      const double2 x3 = ldg2(vi + (int64_t)__ldg(col + p + 3) * n);
+      const double2 h0 = ldg2(val + p), h1 = ldg2(val + p + 1), h2 = ldg2(val + p + 2), h3 = ldg2(val + p + 3);
+      if (REALH) { rfma(acc0, h0.x, x0); rfma(acc1, h1.x, x1); rfma(acc0, h2.x, x2); rfma(acc1, h3.x, x3); }
+      else { cfma(acc0, h0, x0); cfma(acc1, h1, x1); cfma(acc0, h2, x2); cfma(acc1, h3, x3); }
+    }
+    for (; p < p1; p++) {
+      const double2 x = ldg2(vi + (int64_t)__ldg(col + p) * n);
+      const double2 h = ldg2(val + p);
+      if (REALH) rfma(acc0, h.x, x); else cfma(acc0, h, x);
+    }
+    if (live) {
+      double2 *o = out + i + c * n;
+      double2 y = *o;
+      y.x += acc0.x + acc1.x;
+      y.y += acc0.y + acc1.y;
+      *o = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Tiled transpose of a sub-block: dst[(dcol_off + c) + r*ld_dst] (=|+=) src[(srow_off + r) + c*ld_src]
 // for r in [0,nr), c in [0,nc).  This is pack + exchange + unpack + local_transpose of
 // vector_transpose_MPI in one kernel when dst is the destination rank's buffer.
@@ -627,6 +677,20 @@ static int launch_rowpass_tile_t(const SpinOp &s, int64_t nrows, const double2 *
 static int rowpass(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
   Ctx &c = ctx();
   if (s.n <= 0 || nrows <= 0) return 0;
+  if (c.opt.rowpass_variant == 3 && c.mode == CDMFT_B200_SPARSE && s.nblocks_l1 > 0) {
+    static bool configured = false;
+    if (!configured) {  // all of the unified L1/shared array as L1
+      cudaFuncSetAttribute(k_rowpass_l1<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+      cudaFuncSetAttribute(k_rowpass_l1<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+      configured = true;
+    }
+    const int64_t nct = ((nrows + 31) / 32) * s.nblocks_l1;
+    if (nct > 0x7fffffffLL) return fail("rowpass_l1: grid too large");
+    if (c.real_h) k_rowpass_l1<true><<<(unsigned)nct, 1024, 0, c.stream>>>(nrows, v, out, s.blocks_l1, s.nblocks_l1, s.rowptr, s.col, s.val);
+    else k_rowpass_l1<false><<<(unsigned)nct, 1024, 0, c.stream>>>(nrows, v, out, s.blocks_l1, s.nblocks_l1, s.rowptr, s.col, s.val);
+    c.launches++;
+    return 0;
+  }
   if (c.opt.rowpass_variant != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
     const bool direct = c.mode == CDMFT_B200_DIRECT;
     if (c.opt.rowpass_variant != 2 && !direct && s.pk_in && !s.pk_swizzled) {

@@ -227,6 +227,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "col_batch") c.opt.col_batch = value;
   else if (k == "row_slab") c.opt.row_slab = value;
   else if (k == "tile_rows") c.opt.tile_rows = value;
+  else if (k == "l1_rows") c.opt.l1_rows = value;
   else return fail("set_option: unknown key %s", key);
   return 0;
 }

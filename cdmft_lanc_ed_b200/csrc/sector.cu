@@ -309,6 +309,27 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
     CB_CHECK(dev_alloc(&op.blocks, (int64_t)blk.size()));
     CB_CUDA(cudaMemcpyAsync(op.blocks, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
   }
+  // second, finer decomposition for the L1-blocked row pass (block x 32 rows x 16 B must stay in L1)
+  {
+    const int64_t cap = std::max<int64_t>(8, c.opt.l1_rows);
+    int t = 0;
+    for (; t <= ns; t++) {
+      int64_t mx = 0;
+      for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, npart - k));
+      if (mx <= cap) break;
+    }
+    std::vector<int2> blk;
+    int64_t start = 0;
+    for (uint32_t P = 0; P < (1u << t); P++) {
+      int64_t sz = binom64(ns - t, npart - __builtin_popcount(P));
+      if (sz <= 0) continue;
+      blk.push_back(make_int2((int)start, (int)sz));
+      start += sz;
+    }
+    op.nblocks_l1 = (int32_t)blk.size();
+    CB_CHECK(dev_alloc(&op.blocks_l1, (int64_t)blk.size()));
+    CB_CUDA(cudaMemcpyAsync(op.blocks_l1, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+  }
   // packed tile CSR: distinct signed coefficients -> 7-bit ids (host; the matrices are small)
   if (want_csr && op.nnz > 0 && op.n < (1 << 21) && (int64_t)op.max_block < (1 << 18)) {
     std::vector<double2> hval(op.nnz);
@@ -372,7 +393,7 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
 void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
-  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
+  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
   op = SpinOp();
 }
 

@@ -245,6 +245,8 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     dict(colpass_variant=0, rowpass_variant=0, tile_rows=9),
     dict(colpass_variant=0, rowpass_variant=1, tile_rows=25, force_sharded=1),
     dict(colpass_variant=2, rowpass_variant=2, tile_rows=40),    # unpacked tile kernels
+    dict(colpass_variant=1, rowpass_variant=3, l1_rows=256),     # L1-blocked row pass
+    dict(colpass_variant=0, rowpass_variant=3, l1_rows=12),
     dict(colpass_variant=2, rowpass_variant=0, tile_rows=30, force_sharded=1),
 ])
 @pytest.mark.parametrize("name", ["hm2x2_nb2", "bhz2_nb1", "rand_c_L2O2B1_S2"])
@@ -254,7 +256,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=0, rowpass_variant=0, col_batch=4, tile_rows=1800, force_sharded=0)
+    defaults = dict(colpass_variant=1, rowpass_variant=1, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)

@@ -29,9 +29,9 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=0, rowpass_variant=1),
-         dict(colpass_variant=1, rowpass_variant=0), dict(), dict(colpass_variant=2, rowpass_variant=2),
-         dict(tile_rows=1000), dict(force_sharded=1)]
+SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=1, rowpass_variant=3, l1_rows=128),
+         dict(colpass_variant=1, rowpass_variant=3, l1_rows=256), dict(colpass_variant=1, rowpass_variant=3, l1_rows=512),
+         dict(colpass_variant=0, rowpass_variant=3, l1_rows=256), dict()]
 
 
 def main():
@@ -41,9 +41,9 @@ def main():
     E.set_stream(torch.cuda.current_stream().cuda_stream)
     E.ed_set_model(mdl)
     isec = models.get_sector(mdl.ns, *sec)
-    for sparse in (True, False):
+    for sparse in (True,):
         for opts in SWEEP:
-            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=0, rowpass_variant=0, tile_rows=1800).items():
+            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=0, rowpass_variant=0, tile_rows=1800, l1_rows=256).items():
                 E.set_option(k, v)
             for k, v in opts.items():
                 E.set_option(k, v)
