@@ -123,11 +123,18 @@ struct Ctx {
   // Krylov work vectors (allocated lazily)
   double2 *kv[3] = {nullptr, nullptr, nullptr};
   int64_t kv_n = 0;
+  // per-kernel-kind CUDA-event timing (option "profile"): 0 column pass, 1 row pass, 2 transpose /
+  // pack / unpack, 3 NCCL all-to-all, 4 Krylov vector kernels
+  bool profile = false;
+  struct ProfRec { int kind; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
   double *red = nullptr;       // device reduction scratch
   double *red_host = nullptr;  // pinned
 };
 
 Ctx &ctx();
+void prof_begin(int kind);
+void prof_end();
 int fail(const char *fmt, ...);
 void set_error(const std::string &s);
 

@@ -639,7 +639,14 @@ static int launch_colpass_tile(const SpinOp &s, int64_t ncols, const double2 *v,
   return direct ? launch_colpass_tile_t<false, true>(s, ncols, v, out, dg) : launch_colpass_tile_t<false, false>(s, ncols, v, out, dg);
 }
 
+static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg);
 static int colpass(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
+  prof_begin(0);
+  int rc = colpass_impl(s, ncols, v, out, dg);
+  prof_end();
+  return rc;
+}
+static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
   if (ncols <= 0 || s.n <= 0) return 0;
   // variant 0/2 = shared-memory tiles (default), 1 = generic global-gather kernel
   const int64_t var = ctx().opt.colpass_variant;
@@ -674,7 +681,14 @@ static int launch_rowpass_tile_t(const SpinOp &s, int64_t nrows, const double2 *
   return 0;
 }
 
+static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out);
 static int rowpass(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
+  prof_begin(1);
+  int rc = rowpass_impl(s, nrows, v, out);
+  prof_end();
+  return rc;
+}
+static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
   Ctx &c = ctx();
   if (s.n <= 0 || nrows <= 0) return 0;
   if (c.opt.rowpass_variant == 3 && c.mode == CDMFT_B200_SPARSE && s.nblocks_l1 > 0) {
@@ -768,17 +782,21 @@ int hxv_device(const double2 *v, double2 *hv) {
   const int P = c.p_eff;
   if (!c.spmd || P == 1) {
     // device-local exchange: write straight into the destination rank's buffer
+    prof_begin(2);
     for (size_t a = 0; a < c.rk.size(); a++)
       for (size_t b = 0; b < c.rk.size(); b++) {
         RankState &src = c.rk[a], &dst = c.rk[b];
         transpose_block<false>(v + offs[a], c.dimup, dst.up.off, dst.up.q, src.dw.q, dst.vt, c.dimdw, src.dw.off);
       }
+    prof_end();
     for (auto &r : c.rk) CB_CHECK(colpass(c.dw, r.up.q, r.vt, r.hvt, nodiag));
+    prof_begin(2);
     for (size_t a = 0; a < c.rk.size(); a++)
       for (size_t b = 0; b < c.rk.size(); b++) {
         RankState &src = c.rk[a], &dst = c.rk[b];
         transpose_block<true>(src.hvt, c.dimdw, dst.dw.off, dst.dw.q, src.up.q, hv + offs[b], c.dimup, src.up.off);
       }
+    prof_end();
     return 0;
   }
   // SPMD over NCCL: pack (transposing) -> grouped send/recv -> unpack
@@ -786,30 +804,42 @@ int hxv_device(const double2 *v, double2 *hv) {
   RankState &me = c.rk[0];
   std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
   int64_t so = 0, ro = 0;
+  prof_begin(2);
   for (int p = 0; p < P; p++) {
     Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
     cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];   // my columns, p's rows
     cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];  // my rows, p's columns
     transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
   }
+  prof_end();
+  prof_begin(3);
   CB_CHECK(nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data()));
+  prof_end();
+  prof_begin(2);
   for (int p = 0; p < P; p++) {
     Split pd = split_of(c.dimdw, P, p);
     copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
   }
+  prof_end();
   CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
   so = ro = 0;
+  prof_begin(2);
   for (int p = 0; p < P; p++) {
     Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
     cs[p] = pd.q * me.up.q; os[p] = so; so += cs[p];   // my rows (up), p's columns (dw)
     cr[p] = me.dw.q * pu.q; orr[p] = ro; ro += cr[p];
     transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me.up.q, me.sendbuf + os[p], me.up.q, 0);
   }
+  prof_end();
+  prof_begin(3);
   CB_CHECK(nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data()));
+  prof_end();
+  prof_begin(2);
   for (int p = 0; p < P; p++) {
     Split pu = split_of(c.dimup, P, p);
     copy_block<true>(me.recvbuf + orr[p], me.dw.q, pu.q, hv, c.dimup, pu.off);
   }
+  prof_end();
   return 0;
 }
 

@@ -26,6 +26,22 @@ int fail(const char *fmt, ...) {
   return 1;
 }
 
+void prof_begin(int kind) {
+  Ctx &c = ctx();
+  if (!c.profile) return;
+  Ctx::ProfRec r;
+  r.kind = kind;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c.stream);
+  c.prof.push_back(r);
+}
+void prof_end() {
+  Ctx &c = ctx();
+  if (!c.profile || c.prof.empty()) return;
+  cudaEventRecord(c.prof.back().b, c.stream);
+}
+
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -213,6 +229,27 @@ int cdmft_b200_reset_stream(void) {
   return 0;
 }
 
+// sum of the CUDA-event durations recorded for one kernel kind since the last query (clears them)
+int cdmft_b200_profile_query(int32_t kind, double *ms_total, int64_t *count) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  double tot = 0;
+  int64_t n = 0;
+  std::vector<Ctx::ProfRec> keep;
+  for (auto &r : c.prof) {
+    if (r.kind != kind) { keep.push_back(r); continue; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; n++; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c.prof.swap(keep);
+  if (ms_total) *ms_total = tot;
+  if (count) *count = n;
+  return 0;
+}
+
 int cdmft_b200_launch_count(int64_t *n) {
   *n = ctx().launches;
   return 0;
@@ -228,6 +265,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "row_slab") c.opt.row_slab = value;
   else if (k == "tile_rows") c.opt.tile_rows = value;
   else if (k == "l1_rows") c.opt.l1_rows = value;
+  else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);
   return 0;
 }

@@ -45,7 +45,8 @@ _lib = None
 # every symbol include/cdmft_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "cdmft_b200_last_error", "cdmft_b200_init", "cdmft_b200_nccl_unique_id", "cdmft_b200_init_rank",
-    "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_reset_stream", "cdmft_b200_launch_count",
+    "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_reset_stream",
+    "cdmft_b200_profile_query", "cdmft_b200_launch_count",
     "cdmft_b200_set_option", "cdmft_b200_set_model", "cdmft_b200_get_ns", "cdmft_b200_get_sector_dims",
     "cdmft_b200_vecdim_hv_sector", "cdmft_b200_build_hv_sector", "cdmft_b200_delete_hv_sector",
     "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
@@ -146,6 +147,13 @@ def reset_stream():
 
 def set_option(key: str, value: int):
     _chk(load_library().cdmft_b200_set_option(key.encode(), C.c_int64(value)))
+
+
+def profile_query(kind: int):
+    """(total ms, launches) of kernel kind 0 column pass / 1 row pass / 2 transpose / 3 NCCL since last query."""
+    ms, n = C.c_double(), C.c_int64()
+    _chk(load_library().cdmft_b200_profile_query(C.c_int32(kind), C.byref(ms), C.byref(n)))
+    return ms.value, n.value
 
 
 def launch_count() -> int:

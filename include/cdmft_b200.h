@@ -73,6 +73,10 @@ int cdmft_b200_finalize(void);
  * non-blocking stream; reset_stream goes back to the library's stream */
 int cdmft_b200_set_stream(void *cuda_stream);
 int cdmft_b200_reset_stream(void);
+/* with set_option("profile",1) the library brackets its kernels with CUDA events on the launch
+ * stream; this returns the summed duration and count for one kind since the last query
+ * (0 column pass, 1 row pass, 2 transpose/pack/unpack, 3 NCCL all-to-all) and clears them */
+int cdmft_b200_profile_query(int32_t kind, double *ms_total, int64_t *count);
 /* number of kernels this library has launched so far */
 int cdmft_b200_launch_count(int64_t *n);
 /* kernel variant selection for experiments/benchmarks: key/value, see DESIGN.md */

@@ -42,7 +42,10 @@ typedef struct {
 typedef struct {
   /* per simulated MPI rank */
   edo_shard sh;
-  sp_mat h0d, h0nd; /* local rows (ED_HAMILTONIAN_SPARSE_HxV.f90:77-91) */
+  /* spH0d always holds exactly ONE entry per local row (value htmp at column i, even when 0:
+   * sparse/H_local.f90:95-100), so it is stored flat: d0[i-ishift-1] = htmp; column = global row. */
+  edo_c64 *d0;
+  sp_mat h0nd; /* local rows (ED_HAMILTONIAN_SPARSE_HxV.f90:77-91) */
 } rank_state;
 
 struct edo_ctx {
@@ -505,19 +508,22 @@ static int buildh(edo_ctx *c) {
   for (int r = 0; r < c->P; r++) {
     rank_state *rk = &c->rk[r];
     int64_t nloc = rk->sh.iend - rk->sh.istart + 1;
-    sp_init(&rk->h0d, nloc, c->dim);
+    rk->d0 = (edo_c64 *)malloc((size_t)(nloc > 0 ? nloc : 1) * sizeof(edo_c64));
     if (c->jhflag) sp_init(&rk->h0nd, nloc, c->dim);
     /* H_local.f90: do i=MpiIstart,MpiIend ... sp_insert_element(spH0d,htmp,i,i) */
+#pragma omp parallel for schedule(static)
     for (int64_t i = rk->sh.istart; i <= rk->sh.iend; i++) {
       int64_t iup = i % c->dimup; if (iup == 0) iup = c->dimup;
       int64_t idw = (i - 1) / c->dimup + 1;
-      edo_c64 h = local_element(c, c->map_up[iup - 1], c->map_dw[idw - 1], 0);
-      sp_insert(&rk->h0d, h, i - rk->sh.ishift, i);
-      if (c->jhflag) {
+      rk->d0[i - rk->sh.ishift - 1] = local_element(c, c->map_up[iup - 1], c->map_dw[idw - 1], 0);
+    }
+    if (c->jhflag)
+      for (int64_t i = rk->sh.istart; i <= rk->sh.iend; i++) {
+        int64_t iup = i % c->dimup; if (iup == 0) iup = c->dimup;
+        int64_t idw = (i - 1) / c->dimup + 1;
         nlins_ud ud = {&rk->h0nd, i - rk->sh.ishift};
         nonlocal_row(c, iup, idw, nlins_cb, &ud);
       }
-    }
   }
   /* H_up.f90: do jup=1,DimUp ... sp_insert_element(spH0ups(1),htmp,iup,jup) */
   for (int64_t jup = 1; jup <= c->dimup; jup++) {
@@ -559,7 +565,7 @@ int32_t edo_delete_hv_sector(edo_ctx *c) {
   if (!c->hstatus) return 0;
   free(c->map_up); free(c->map_dw);
   c->map_up = c->map_dw = NULL;
-  for (int r = 0; r < c->P; r++) { sp_delete(&c->rk[r].h0d); sp_delete(&c->rk[r].h0nd); }
+  for (int r = 0; r < c->P; r++) { free(c->rk[r].d0); c->rk[r].d0 = NULL; sp_delete(&c->rk[r].h0nd); }
   sp_delete(&c->h0up); sp_delete(&c->h0dw);
   free(c->rk); c->rk = NULL;
   c->hsector = 0; c->hstatus = 0;
@@ -602,8 +608,7 @@ static void spmatvec_serial(edo_ctx *c, const edo_c64 *v, edo_c64 *hv) {
   const int64_t DimUp = c->dimup, DimDw = c->dimdw, N = c->dim;
   rank_state *rk = &c->rk[0];
   for (int64_t i = 0; i < N; i++) hv[i] = 0;
-  for (int64_t i = 0; i < N; i++)
-    for (int32_t j = 0; j < rk->h0d.row[i].size; j++) hv[i] += rk->h0d.row[i].vals[j] * v[rk->h0d.row[i].cols[j] - 1];
+  for (int64_t i = 0; i < N; i++) hv[i] += rk->d0[i] * v[i]; /* Hv(i) += spH0d%row(i)%vals(1)*v(cols(1)), cols(1)=i */
   for (int64_t iup = 1; iup <= DimUp; iup++)
     for (int64_t idw = 1; idw <= DimDw; idw++) {
       int64_t i = iup + (idw - 1) * DimUp;
@@ -632,10 +637,7 @@ static void spmatvec_mpi(edo_ctx *c, const edo_c64 *v, edo_c64 *hv) {
     const edo_c64 *vl = v + rk->sh.ishift;
     edo_c64 *hl = hv + rk->sh.ishift;
     int64_t nloc = rk->sh.q;
-    for (int64_t i = 0; i < nloc; i++) {
-      hl[i] = 0;
-      for (int32_t j = 0; j < rk->h0d.row[i].size; j++) hl[i] += rk->h0d.row[i].vals[j] * vl[i];
-    }
+    for (int64_t i = 0; i < nloc; i++) hl[i] = rk->d0[i] * vl[i]; /* uses v(i), local index (:251-255) */
     for (int64_t idw = 1; idw <= rk->sh.qdw; idw++)
       for (int64_t iup = 1; iup <= DimUp; iup++) {
         int64_t i = iup + (idw - 1) * DimUp;
@@ -839,7 +841,7 @@ int32_t edo_dense_hmat(edo_ctx *c, int32_t isector, edo_c64 *hmat) {
   memset(hmat, 0, (size_t)N * N * sizeof(edo_c64));
   rank_state *rk = &c->rk[0];
   for (int64_t i = 0; i < N; i++) {
-    for (int32_t k = 0; k < rk->h0d.row[i].size; k++) hmat[i + (rk->h0d.row[i].cols[k] - 1) * N] += rk->h0d.row[i].vals[k];
+    hmat[i + i * N] += rk->d0[i];
     if (c->jhflag)
       for (int32_t k = 0; k < rk->h0nd.row[i].size; k++) hmat[i + (rk->h0nd.row[i].cols[k] - 1) * N] += rk->h0nd.row[i].vals[k];
   }
