@@ -229,12 +229,12 @@ def run_ours(args):
             flush.zero_()
         E.spHtimesV_p(nloc, v, hv)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     sampler = _clock_sampler_start(clk_path) if rank == 0 else (None, None)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     l0 = E.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
@@ -257,7 +257,6 @@ def run_ours(args):
         ms = ev[0].elapsed_time(ev[1])
     barrier()
     launches = E.launch_count() - l0
-    clocks = _clock_sampler_stop(*sampler, clk_path, gpu_index=local) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -277,6 +276,8 @@ def run_ours(args):
         if n:
             kern[nm] = {"ms_per_step": tot / nprof, "launches_per_step": n / nprof}
     E.set_option("profile", 0)
+    # clocks were sampled (nvidia-smi -lms 100) from the first warm-up step to the end of the profiled loop
+    clocks = _clock_sampler_stop(*sampler, clk_path, gpu_index=local) if rank == 0 else None
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
     e2e = None
@@ -323,11 +324,11 @@ def run_ours(args):
         # dominant kernel = column pass: algorithmic bytes per launch = read v + write Hv = 32 B/state of the shard
         nl = kern["column_pass"]["launches_per_step"]
         dur = kern["column_pass"]["ms_per_step"] / max(nl, 1)
-        bytes_launch = 32.0 * nloc * (1 if world == 1 else 0.5)  # sharded: two column passes (Hup on v, Hdw on vt) per step
+        bytes_launch = 32.0 * nloc  # one column pass reads its nloc-element operand once and writes nloc outputs
         ach = bytes_launch / (dur * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "column pass (k_colpass*)", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_source": peak_src,
-                    "traffic": (prof.get(args.workload, {}).get("column_pass", {}) or {}).get("dram_bytes_per_launch"),
+                    "traffic": (prof.get(args.workload, {}).get("column_pass", {}) or {}).get("dram_bytes_per_launch") if world == 1 else None,
                     "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur,
                     "step_frac_of_peak": value / world / peak}
 

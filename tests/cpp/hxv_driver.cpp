@@ -1,0 +1,55 @@
+// C++ driver over the header-only host mirror: 2x2 Hubbard plaquette, Nbath=1 (BASELINE config K1),
+// sector (4,4): one H x v on a deterministic vector, the Lanczos ground-state energy and 10 tridiagonal
+// coefficients are printed as JSON; tests/test_gpu_cpp_host.py compares them with the oracle.
+#include <cmath>
+#include <cstdio>
+
+#include "ed_hamiltonian_b200.hpp"
+
+using namespace ed_b200;
+
+int main() {
+  try {
+    Model m;
+    m.Nlat = 4; m.Norb = 1; m.Nspin = 1; m.Nbath = 1;
+    const double ts = 0.25;
+    m.impHloc.assign(16, cplx(0, 0));
+    m.Hbath.assign(16, cplx(0, 0));
+    const int bonds[4][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}};  // drivers/cdn_hm_2dsquare.f90:221-259
+    for (auto &b : bonds) {
+      m.impHloc[b[0] + 4 * b[1]] = m.impHloc[b[1] + 4 * b[0]] = -ts;
+      m.Hbath[b[0] + 4 * b[1]] = m.Hbath[b[1] + 4 * b[0]] = ts;  // lambda2 * abs(Hloc), onsite 0
+    }
+    m.Vbath.assign(4, 1.0);
+    ed_init(0);
+    ed_set_model(m);
+    const int isector = get_Sector(4, 4);
+    if (spHtimesV_p() != nullptr) return 2;
+    const int64_t n = build_Hv_sector(isector);
+    if (n != vecDim_Hv_sector(isector) || n != 4900) return 3;
+    std::vector<cplx> v(n), hv(n);
+    for (int64_t i = 0; i < n; i++) v[i] = cplx(std::sin(0.37 * (i + 1)), std::cos(0.11 * (i + 1)));
+    spHtimesV_p()((int)n, v.data(), hv.data());
+    std::vector<double> a(10), b;
+    sp_lanc_tridiag(v, a, b);
+    std::vector<cplx> gs(n, cplx(0, 0));
+    double e0 = 0;
+    int nit = sp_lanc_eigh(e0, gs, 512, 1e-14);
+    delete_Hv_sector();
+    bool threw = false;
+    try { b200_HxV((int)n, v.data(), hv.data()); } catch (const std::runtime_error &) { threw = true; }
+    ed_finalize();
+    std::printf("{\"n\": %lld, \"e0\": %.15e, \"niter\": %d, \"threw_after_delete\": %s, \"hv\": [", (long long)n, e0, nit,
+                threw ? "true" : "false");
+    for (int i = 0; i < 8; i++) std::printf("%s[%.17e, %.17e]", i ? ", " : "", hv[i * 601].real(), hv[i * 601].imag());
+    std::printf("], \"alanc\": [");
+    for (int i = 0; i < 10; i++) std::printf("%s%.17e", i ? ", " : "", a[i]);
+    std::printf("], \"blanc\": [");
+    for (int i = 0; i < 10; i++) std::printf("%s%.17e", i ? ", " : "", b[i]);
+    std::printf("]}\n");
+    return 0;
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+}
