@@ -34,6 +34,7 @@ WORKLOADS = {
     "K2": ("hm2x2", (2,), (6, 6)),
     "K3": ("hm2x2", (3,), (8, 8)),
     "K4": ("bhz2", (3,), (8, 8)),
+    "K5": ("hm_ns18", (), (9, 9)),  # Ns=18, Dim 2 363 904 400: needs >= 2 GPUs (int64 global index; the reference overflows)
 }
 
 
