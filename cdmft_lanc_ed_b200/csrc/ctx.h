@@ -117,6 +117,7 @@ struct Ctx {
   int p_eff = 1;  // min(P, DimDw)
   SpinOp up, dw;
   std::vector<RankState> rk;
+  double2 *vfull = nullptr;  // all-gathered vector for the non-local (Jx/Jp) term, SPMD only
   // staging for host-pointer calls
   double2 *stage_v = nullptr, *stage_hv = nullptr;
   int64_t stage_n = 0;

@@ -761,7 +761,103 @@ static DiagArgs diag_args(int64_t coloff) {
 
 // H x v on the local shard(s); v/hv device pointers laid out as the concatenation of the local
 // ranks' shards (exactly one shard in SPMD mode, all P in sim mode, the whole vector otherwise).
+// ------------------------------------------------------------------------------------
+// Non-local Kanamori terms (Jhflag: Norb>1 and Jx/=0 or Jp/=0): spin-exchange and pair-hopping,
+// ED_HAMILTONIAN/sparse/H_non_local.f90:4-100 == direct/HxV_non_local.f90:4-86.  One thread per
+// local row i=(iup,idw): conditions on the row state, column j = (c^+_is c_js)_up (c^+_js c_is)_dw |i>
+// (S-E) or (c^+_is c_js)_up (c^+_is c_js)_dw |i> (P-H), Hv(i) += J * sg1 sg2 sg3 sg4 * v(j).
+// v is the FULL vector (the reference all-gathers it, ED_HAMILTONIAN_SPARSE_HxV.f90:302-305).
+// ------------------------------------------------------------------------------------
+struct NonLocalArgs {
+  const int32_t *map_up, *map_dw;
+  const int32_t *up_lo, *up_hi, *dw_lo, *dw_hi;
+  int lbits, nlat, norb;
+  double jx, jp;
+  int64_t dimup;
+  int64_t row0;  // global index of the first local row
+};
+__device__ __forceinline__ double hop_sign2(uint32_t s, int a, int b) { return hop_sign_d(s, a, b); }
+
+__global__ void __launch_bounds__(256) k_nonlocal(int64_t nloc, const double2 *__restrict__ vfull, double2 *__restrict__ hv,
+                                                   NonLocalArgs a) {
+  const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (il >= nloc) return;
+  const int64_t ig = il + a.row0;
+  const int64_t iup = ig % a.dimup, idw = ig / a.dimup;
+  const uint32_t mup = (uint32_t)__ldg(a.map_up + iup), mdw = (uint32_t)__ldg(a.map_dw + idw);
+  double2 acc = make_double2(0.0, 0.0);
+  for (int ilat = 0; ilat < a.nlat; ilat++)
+    for (int io = 0; io < a.norb; io++)
+      for (int jo = 0; jo < a.norb; jo++) {
+        if (io == jo) continue;
+        const int is = io + ilat * a.norb, js = jo + ilat * a.norb;  // imp_state_index - 1
+        const uint32_t bi = 1u << is, bj = 1u << js;
+        const bool nup_i = mup & bi, nup_j = mup & bj, ndw_i = mdw & bi, ndw_j = mdw & bj;
+        // S-E: nup(j)=1, ndw(i)=1, ndw(j)=0, nup(i)=0 : dw c(is) cdg(js) ; up c(js) cdg(is)
+        if (a.jx != 0.0 && nup_j && ndw_i && !ndw_j && !nup_i) {
+          const uint32_t kdw = (mdw & ~bi) | bj, kup = (mup & ~bj) | bi;
+          const double sg = hop_sign2(mdw, js, is) * hop_sign2(mup, is, js);
+          const int64_t jdw = lin_rank_d(a.dw_lo, a.dw_hi, a.lbits, kdw), jup = lin_rank_d(a.up_lo, a.up_hi, a.lbits, kup);
+          const double2 x = ldg2(vfull + jup + jdw * a.dimup);
+          acc.x += a.jx * sg * x.x;
+          acc.y += a.jx * sg * x.y;
+        }
+        // P-H: nup(j)=1, ndw(j)=1, ndw(i)=0, nup(i)=0 : dw c(js) cdg(is) ; up c(js) cdg(is)
+        if (a.jp != 0.0 && nup_j && ndw_j && !ndw_i && !nup_i) {
+          const uint32_t kdw = (mdw & ~bj) | bi, kup = (mup & ~bj) | bi;
+          const double sg = hop_sign2(mdw, is, js) * hop_sign2(mup, is, js);
+          const int64_t jdw = lin_rank_d(a.dw_lo, a.dw_hi, a.lbits, kdw), jup = lin_rank_d(a.up_lo, a.up_hi, a.lbits, kup);
+          const double2 x = ldg2(vfull + jup + jdw * a.dimup);
+          acc.x += a.jp * sg * x.x;
+          acc.y += a.jp * sg * x.y;
+        }
+      }
+  double2 o = hv[il];
+  o.x += acc.x;
+  o.y += acc.y;
+  hv[il] = o;
+}
+
+static int hxv_local_terms(const double2 *v, double2 *hv);
+
 int hxv_device(const double2 *v, double2 *hv) {
+  Ctx &c = ctx();
+  CB_CHECK(hxv_local_terms(v, hv));
+  if (!c.jhflag) return 0;
+  NonLocalArgs a{};
+  a.map_up = c.up.map; a.map_dw = c.dw.map;
+  a.up_lo = c.up.lin_lo; a.up_hi = c.up.lin_hi; a.dw_lo = c.dw.lin_lo; a.dw_hi = c.dw.lin_hi;
+  a.lbits = c.ns / 2; a.nlat = c.m.nlat; a.norb = c.m.norb; a.jx = c.m.jx; a.jp = c.m.jp; a.dimup = c.dimup;
+  const double2 *vfull = v;
+  if (c.spmd && c.p_eff > 1) {
+    // allgather_vector_MPI (ED_SETUP.f90:672-708): every rank sends its shard to every rank
+    if (c.rk.empty()) return 0;
+    if (!c.vfull) CB_CHECK(dev_alloc(&c.vfull, c.dim));
+    std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
+    for (int p = 0; p < c.p_eff; p++) {
+      Split pd = split_of(c.dimdw, c.p_eff, p);
+      cs[p] = c.rk[0].nloc; os[p] = 0;
+      cr[p] = pd.q * c.dimup; orr[p] = pd.off * c.dimup;
+    }
+    prof_begin(3);
+    CB_CHECK(nccl_all_to_all(v, c.vfull, cs.data(), os.data(), cr.data(), orr.data()));
+    prof_end();
+    vfull = c.vfull;
+  }
+  int64_t off = 0;
+  for (auto &r : c.rk) {
+    if (r.nloc > 0) {
+      a.row0 = r.dw.off * c.dimup;
+      // single process (one rank or simulated ranks): v is already the gathered vector
+      k_nonlocal<<<(unsigned)((r.nloc + 255) / 256), 256, 0, c.stream>>>(r.nloc, vfull, hv + off, a);
+      c.launches++;
+    }
+    off += r.nloc;
+  }
+  return 0;
+}
+
+static int hxv_local_terms(const double2 *v, double2 *hv) {
   Ctx &c = ctx();
   const bool sharded = c.spmd || c.sim || c.opt.force_sharded;
   DiagArgs nodiag{};

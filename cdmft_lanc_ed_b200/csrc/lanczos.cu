@@ -169,33 +169,81 @@ static int64_t local_n() {
   return n;
 }
 
-// one step of the 3-term recurrence (SciFortran lanczos_iteration)
-static int lanczos_iteration(int64_t n, int iter, double2 *vin, double2 *vout, double2 *tmp, double *alfa, double *beta) {
+// ------------------------------------------------------------------------------------
+// The 3-term recurrence of SciFortran's lanczos_iteration, restated on UNNORMALISED
+// vectors u_j = beta_j v_j so that no separate normalise / swap sweeps are needed:
+//     t        = H u_j
+//     alfa_j   = Re<u_j, t> / beta_j^2
+//     u_{j+1}  = t/beta_j - (alfa_j/beta_j) u_j - (beta_j/beta_{j-1}) u_{j-1},   beta_{j+1} = |u_{j+1}|
+// (identical to vout = H vin - alfa vin - beta vin_prev with vin = u_j/beta_j).  Per iteration the
+// vector kernels move 96 B/state (one dot, one fused 3-term update + norm) instead of the textbook
+// 176 B/state (swap/scale, add+dot, axpy+norm).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lanczos_update(int64_t n, double2 *__restrict__ um, const double2 *__restrict__ u,
+                                                        const double2 *__restrict__ t, double ct, double cu, double cum,
+                                                        double2 *__restrict__ partial) {
+  double re = 0, im = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 a = um[i], b = u[i], x = t[i];
+    double2 y;
+    y.x = ct * x.x - cu * b.x - cum * a.x;
+    y.y = ct * x.y - cu * b.y - cum * a.y;
+    um[i] = y;
+    re += y.x * y.x + y.y * y.y;
+  }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
+}
+
+struct LanczosRun {
+  int64_t n = 0;
+  double2 *um = nullptr, *u = nullptr, *t = nullptr;  // u_{j-1}, u_j, H u_j
+  double beta_prev = 1.0, beta_cur = 1.0;
+};
+
+// u holds the start vector on entry; normalises it (iter == 1 branch of lanczos_iteration)
+static int lanczos_start(LanczosRun &L) {
   Ctx &c = ctx();
   std::complex<double> z;
-  if (iter == 1) {
-    CB_CHECK(dot(n, vin, vin, &z));
-    double norm = std::sqrt(z.real());
-    if (norm == 0.0) return fail("LANCZOS_ITERATION: norm(vin)=0");
-    if (n > 0) { k_scale<<<vec_grid(n), 256, 0, c.stream>>>(n, vin, 1.0 / norm); c.launches++; }
-  } else {
-    if (n > 0) { k_swap_scale<<<vec_grid(n), 256, 0, c.stream>>>(n, vin, vout, *beta); c.launches++; }
-  }
-  CB_CHECK(hxv_device(vin, tmp));
-  CB_CHECK(zero_partials());
-  if (n > 0) {
-    k_add_dot<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, vout, tmp, vin, (double2 *)c.red);
+  CB_CHECK(dot(L.n, L.u, L.u, &z));
+  const double norm = std::sqrt(z.real());
+  if (norm == 0.0) return fail("LANCZOS_ITERATION: norm(vin)=0");
+  if (L.n > 0) {
+    prof_begin(4);
+    k_scale<<<vec_grid(L.n), 256, 0, c.stream>>>(L.n, L.u, 1.0 / norm);
     c.launches++;
+    CB_CUDA(cudaMemsetAsync(L.um, 0, (size_t)L.n * 16, c.stream));
+    prof_end();
+  }
+  L.beta_prev = L.beta_cur = 1.0;
+  return 0;
+}
+
+// one Lanczos step; on return alfa = alfa_j, beta = beta_{j+1}; the normalised vector of this step is
+// v_j = L.um / L.beta_prev (buffers are rotated)
+static int lanczos_step(LanczosRun &L, double *alfa, double *beta) {
+  Ctx &c = ctx();
+  std::complex<double> z;
+  CB_CHECK(hxv_device(L.u, L.t));
+  prof_begin(4);
+  CB_CHECK(dot(L.n, L.u, L.t, &z));
+  prof_end();
+  const double a = z.real() / (L.beta_cur * L.beta_cur);
+  CB_CHECK(zero_partials());
+  if (L.n > 0) {
+    prof_begin(4);
+    k_lanczos_update<<<std::min<unsigned>(vec_grid(L.n), kRedBlocks), 256, 0, c.stream>>>(
+        L.n, L.um, L.u, L.t, 1.0 / L.beta_cur, a / L.beta_cur, L.beta_cur / L.beta_prev, (double2 *)c.red);
+    c.launches++;
+    prof_end();
   }
   CB_CHECK(finish_reduce(&z));
-  *alfa = z.real();
-  CB_CHECK(zero_partials());
-  if (n > 0) {
-    k_axpy_norm<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, vout, vin, *alfa, (double2 *)c.red);
-    c.launches++;
-  }
-  CB_CHECK(finish_reduce(&z));
-  *beta = std::sqrt(z.real());
+  const double bnext = std::sqrt(z.real());
+  std::swap(L.um, L.u);
+  L.beta_prev = L.beta_cur;
+  L.beta_cur = bnext;
+  *alfa = a;
+  *beta = bnext;
   return 0;
 }
 
@@ -296,16 +344,16 @@ int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, d
   if (nloc != local_n()) return fail("lanczos_tridiag: nloc mismatch");
   if (threshold <= 0) threshold = 1e-12;
   CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
-  double2 *vin = c.kv[0], *vout = c.kv[1], *tmp = c.kv[2];
-  if (nloc > 0) {
-    CB_CUDA(cudaMemcpyAsync(vin, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
-    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
-  }
+  LanczosRun L;
+  L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
+  if (nloc > 0)
+    CB_CUDA(cudaMemcpyAsync(L.u, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
   for (int i = 0; i < nitermax; i++) { alanc[i] = 0; blanc[i] = 0; }
+  CB_CHECK(lanczos_start(L));
   double a = 0, b = 0;
   int done = 0;
   for (int iter = 1; iter <= nitermax; iter++) {
-    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
+    CB_CHECK(lanczos_step(L, &a, &b));
     alanc[iter - 1] = a;
     done = iter;
     if (std::fabs(b) < threshold) break;
@@ -325,7 +373,8 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
   if (ncheck <= 0) ncheck = 10;
   CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
   const bool dev = is_device_ptr(vect);
-  double2 *vin = c.kv[0], *vout = c.kv[1], *tmp = c.kv[2];
+  LanczosRun L;
+  L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
   double2 *gs = nullptr;  // start vector, later the accumulated eigenvector
   if (dev) gs = (double2 *)vect;
   else {
@@ -338,15 +387,13 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
   if (z.real() == 0.0) {  // SciFortran start vector is unpinned; constant 1/sqrt(Dim)
     if (nloc > 0) { k_fill<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt((double)c.dim)); c.launches++; }
   }
-  if (nloc > 0) {
-    CB_CUDA(cudaMemcpyAsync(vin, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
-    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
-  }
+  if (nloc > 0) CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
+  CB_CHECK(lanczos_start(L));
   std::vector<double> al, bl;  // bl[i] couples i-1,i ; bl[0]=0
   std::vector<double> d, Z;
   double a = 0, b = 0, esave = 0, e0 = 0;
   for (int iter = 1; iter <= nitermax; iter++) {
-    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
+    CB_CHECK(lanczos_step(L, &a, &b));
     al.push_back(a);
     if ((int)bl.size() < (int)al.size()) bl.push_back(0.0);
     if (std::fabs(b) < threshold) break;  // invariant subspace
@@ -365,15 +412,20 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
     CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
   }
   e0 = d[0];
-  // second pass: vect = sum_iter vin_iter * Z(iter,1)
+  // second pass: vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter (same recurrence, same start)
   if (nloc > 0) {
-    CB_CUDA(cudaMemcpyAsync(vin, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
-    CB_CUDA(cudaMemsetAsync(vout, 0, (size_t)nloc * 16, c.stream));
+    CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
     CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * 16, c.stream));
   }
+  CB_CHECK(lanczos_start(L));
   for (int iter = 1; iter <= nlanc; iter++) {
-    CB_CHECK(lanczos_iteration(nloc, iter, vin, vout, tmp, &a, &b));
-    if (nloc > 0) { k_axpy_real<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, vin, Z[(size_t)(iter - 1) * nlanc + 0]); c.launches++; }
+    CB_CHECK(lanczos_step(L, &a, &b));
+    if (nloc > 0) {
+      prof_begin(4);
+      k_axpy_real<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, Z[(size_t)(iter - 1) * nlanc + 0] / L.beta_prev);
+      c.launches++;
+      prof_end();
+    }
   }
   CB_CHECK(dot(nloc, gs, gs, &z));
   if (nloc > 0) { k_scale<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt(z.real())); c.launches++; }

@@ -295,8 +295,6 @@ int cdmft_b200_set_model(const cdmft_b200_model *m) {
   c.vbath.assign(m->vbath, m->vbath + (int64_t)c.nlso * B);
   c.m.imphloc = c.imphloc.data(); c.m.hbath = c.hbath.data(); c.m.vbath = c.vbath.data();
   c.jhflag = (O > 1 && (m->jx != 0.0 || m->jp != 0.0));  // ED_SETUP.f90:200-201
-  if (c.jhflag)
-    return fail("set_model: Jx/Jp != 0 with Norb>1 (spin-exchange / pair-hopping, H_non_local.f90) is not implemented yet");
 
   auto hidx = [&](int il, int jl, int s, int iorb, int jorb) {
     return (int64_t)il + (int64_t)L * (jl + (int64_t)L * (s + (int64_t)S * (s + (int64_t)S * (iorb + (int64_t)O * jorb))));

@@ -498,6 +498,7 @@ int cdmft_b200_delete_hv_sector(void) {
   for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }
   c.rk.clear();
   dev_free(c.stage_v); dev_free(c.stage_hv); c.stage_n = 0;
+  dev_free(c.vfull);
   for (auto &k : c.kv) dev_free(k);
   c.kv_n = 0;
   c.hsector = 0; c.hstatus = false;

@@ -28,6 +28,10 @@ MODELS = {
     "rand_c_L2O2B1_S2": lambda: models.random_model(2, 2, 1, nspin=2, seed=12),
     "rand_r_L3O1B1": lambda: models.random_model(3, 1, 1, complex_h=False, seed=13),
     "rand_c_L1O3B1": lambda: models.random_model(1, 3, 1, seed=14),
+    # Jhflag: spin-exchange + pair-hopping (H_non_local.f90)
+    "bhz2_nb1_kanamori": lambda: models.bhz2(1, kanamori=True),
+    "rand_kanamori_L2O2B1": lambda: models.random_model(2, 2, 1, seed=15, kanamori=True),
+    "rand_kanamori_L1O3B1_S2": lambda: models.random_model(1, 3, 1, nspin=2, seed=16, kanamori=True),
 }
 
 
@@ -158,7 +162,7 @@ def test_empty_and_tiny_sectors(ed, oracle_lib):
 
 
 @pytest.mark.parametrize("P", [2, 3, 5, 8])
-@pytest.mark.parametrize("name", ["hm2x2_nb1", "bhz2_nb1", "rand_c_L2O2B1_S2"])
+@pytest.mark.parametrize("name", ["hm2x2_nb1", "bhz2_nb1", "rand_c_L2O2B1_S2", "rand_kanamori_L2O2B1"])
 def test_sharded_path_simulated_ranks(oracle_lib, name, P):
     """Ndw sharding + distributed transpose (ED_HAMILTONIAN.f90:92-105, ED_HAMILTONIAN_COMMON.f90:30-101)
     with P simulated ranks on one GPU, against the oracle's simulated MPI mat-vec; includes P not

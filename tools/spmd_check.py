@@ -22,7 +22,8 @@ def main():
     E.ed_set_MpiComm(local)
     ok = True
     cases = [(models.hm2x2(1), (4, 4)), (models.hm2x2(1), (1, 0)), (models.bhz2(1), (4, 3)), (models.hm2x2(2), (6, 6)),
-             (models.random_model(2, 2, 1, nspin=2, seed=12), (4, 4))]
+             (models.random_model(2, 2, 1, nspin=2, seed=12), (4, 4)),
+             (models.random_model(2, 2, 1, seed=15, kanamori=True), (4, 4)), (models.bhz2(1, kanamori=True), (5, 3))]
     for mdl, (nup, ndw) in cases:
         E.ed_set_model(mdl)
         ns = mdl.ns
