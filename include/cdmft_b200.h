@@ -102,8 +102,10 @@ int cdmft_b200_active_ranks(int32_t *p);
 
 /* ---- the mat-vec: spHtimesV_p(Nloc,v,Hv) ---------------------------------------------- */
 /* v, hv: complex(8)[nloc], host OR device pointers (detected); hv is fully overwritten and
- * must not alias v.  Synchronous on return for host pointers; stream-ordered for device
- * pointers.  nloc must equal the value build_hv_sector returned. */
+ * must not alias v.  Synchronous on return for host pointers.  For device pointers the kernels are
+ * only enqueued, on the library's own non-blocking stream unless cdmft_b200_set_stream was called:
+ * the caller orders its producers/consumers of v and hv against that stream (or passes its stream).
+ * nloc must equal the value build_hv_sector returned. */
 int cdmft_b200_hxv(int32_t nloc, const void *v, void *hv);
 int cdmft_b200_hxv64(int64_t nloc, const void *v, void *hv); /* Ns=18: Dim > 2^31 */
 

@@ -1,0 +1,111 @@
+"""-m gpu tests at BASELINE.json's full single-GPU sizes (K3: Ns=16 sector (8,8), Dim 165 636 900; K4: complex
+BHZ, same dims): the oracle on one full H x v, and size-independent properties -- hermiticity, linearity,
+SPARSE == DIRECT == sharded (simulated ranks) == every kernel variant."""
+import numpy as np
+import pytest
+import torch
+
+from cdmft_lanc_ed_b200 import models
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _vec(n, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    v = torch.view_as_complex(torch.randn(n, 2, dtype=torch.float64, device="cuda", generator=g))
+    return v / torch.linalg.vector_norm(v)
+
+
+def _hxv(E, n, v):
+    # the library launches on its own non-blocking stream unless told otherwise: order it after torch's work
+    torch.cuda.synchronize()
+    hv = torch.empty_like(v)
+    E.spHtimesV_p(n, v, hv)
+    torch.cuda.synchronize()
+    return hv
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize("wl", ["K3", "K4"])
+def test_fullsize_properties(ed, wl):
+    mdl = models.hm2x2(3) if wl == "K3" else models.bhz2(3)
+    ed.ed_set_model(mdl)
+    isec = models.get_sector(16, 8, 8)
+    n = ed.build_Hv_sector(isec, True)
+    assert n == 12870 ** 2
+    u, v = _vec(n, 1), _vec(n, 2)
+    hu, hv = _hxv(ed, n, u), _hxv(ed, n, v)
+    # hermiticity <u,Hv> = conj(<v,Hu>)
+    a, b = torch.vdot(u, hv), torch.vdot(v, hu).conj()
+    assert abs(a - b) <= 1e-12 * max(abs(a), 1e-3)
+    # linearity
+    c1, c2 = 0.3 - 1.1j, -0.7 + 0.2j
+    w = _hxv(ed, n, c1 * u + c2 * v)
+    assert _rel(w, c1 * hu + c2 * hv) < 1e-12
+    # every SPARSE kernel variant agrees with the default one
+    for opts in [dict(colpass_variant=0, rowpass_variant=0), dict(colpass_variant=2, rowpass_variant=2),
+                 dict(colpass_variant=1, rowpass_variant=3), dict(force_sharded=1)]:
+        ed.delete_Hv_sector()
+        for k, val in opts.items():
+            ed.set_option(k, val)
+        try:
+            ed.build_Hv_sector(isec, True)
+            assert _rel(_hxv(ed, n, v), hv) < RTOL, opts
+        finally:
+            for k in opts:
+                ed.set_option(k, {"colpass_variant": 1, "rowpass_variant": 1, "force_sharded": 0}[k])
+    # DIRECT (matrix-free) == SPARSE
+    ed.delete_Hv_sector()
+    ed.build_Hv_sector(isec, False)
+    assert _rel(_hxv(ed, n, v), hv) < RTOL
+    ed.delete_Hv_sector()
+
+
+def test_fullsize_sharded_sim_equals_single(oracle_lib):
+    """P=3 simulated ranks (12870 = 3*4290, and P=7 with a remainder) on the full K3 sector."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    mdl = models.hm2x2(3)
+    isec = models.get_sector(16, 8, 8)
+    E.ed_init(0)
+    E.ed_set_model(mdl)
+    n = E.build_Hv_sector(isec, True)
+    v = _vec(n, 5)
+    ref = _hxv(E, n, v).clone()
+    E.delete_Hv_sector()
+    E.ed_finalize()
+    for P in (3, 7):
+        E.ed_init_sim(P, 0)
+        try:
+            E.ed_set_model(mdl)
+            assert E.build_Hv_sector(isec, True) == n
+            assert _rel(_hxv(E, n, v), ref) < RTOL
+            E.delete_Hv_sector()
+        finally:
+            E.ed_finalize()
+
+
+def test_fullsize_K3_against_oracle(ed, oracle_lib):
+    """One full K3 H x v against the CPU oracle (spMatVec_mpi_main restatement on all host cores)."""
+    import os
+    mdl = models.hm2x2(3)
+    isec = models.get_sector(16, 8, 8)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(isec, True)
+    v = _vec(n, 11)
+    hv = _hxv(ed, n, v).cpu().numpy()
+    vh = v.cpu().numpy()
+    ed.delete_Hv_sector()
+    cores = os.cpu_count() or 1
+    oracle_lib.lib().edo_set_num_threads(cores)
+    orc = oracle_lib.Oracle(mdl)
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_MPI, cores)
+    ref = orc.hxv(vh)
+    orc.delete_hv_sector()
+    assert np.abs(hv - ref).max() / np.abs(ref).max() < RTOL
+    # checksum of checksums: column sums of |Hv|^2 agree as well
+    assert abs(np.vdot(hv, hv).real - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
