@@ -46,6 +46,8 @@ struct SpinOp {
   // packed tile CSR for the shared-memory kernels: per row two lists -- sources inside the row block
   // (word = slot<<11 | coef_id<<4, slot = rel<<3 | swizzle) and outside it (word = row<<11 | coef_id<<4)
   // -- each padded to rounds of 8 words; *_ptr are row pointers in rounds
+  uint32_t *pkell = nullptr;  // packed ELL [ell_w][n]: (col << 7) | coef_id, thread-per-row kernels
+  int2 *rowsplit = nullptr;   // [n]: entries [x,y) of a row have their source inside the row's block
   uint32_t *pk_in = nullptr, *pk_off = nullptr;
   int32_t *pk_in_ptr = nullptr, *pk_off_ptr = nullptr;  // [n+1]
   double2 *coef = nullptr;       // [ncoef] distinct signed coefficients, coef[0] = 0

@@ -341,6 +341,115 @@ __global__ void __launch_bounds__(1024, 1) k_tile_pk(int64_t ld, int64_t nbatch,
 }
 
 // ------------------------------------------------------------------------------------
+// Column pass, "rotating slot" shared-memory kernel (SPARSE mode).
+// One CTA owns (row block) x (8 columns), tile[row][8 slots] UNswizzled.  Each THREAD owns one output
+// row and all 8 columns of it (8 accumulators), so an operator entry is decoded once per 8 outputs
+// and no shuffles are needed.  Lane l reads, at step kk, slot (kk + l) & 7 of its source row: the 8
+// lanes of a quarter-warp then hit 8 different 16-byte bank groups WHATEVER rows they gather from ->
+// every LDS.128 is conflict-free (128 B per wavefront, the shared-memory peak).  acc[kk] therefore
+// holds column (kk + l) & 7; the permutation is undone in the address of the final store.
+// Rows are dealt to lanes as row = 4*(l&7) + (l>>3) inside each group of 32, so the four lanes that
+// touch the same column at a step own 4 consecutive rows: stores and off-block loads move 64-byte
+// runs (full sectors).  Hops that change the top bits gather from global memory / L2.
+// ------------------------------------------------------------------------------------
+template <bool REALH>
+__global__ void __launch_bounds__(576, 1) k_colpass_rot(int64_t n, int64_t ncols, const double2 *__restrict__ v,
+                                                         double2 *__restrict__ out, const int2 *__restrict__ blocks,
+                                                         int nblocks, const uint32_t *__restrict__ pkell,
+                                                         const int32_t *__restrict__ rowlen,
+                                                         const int2 *__restrict__ rowsplit,
+                                                         const double2 *__restrict__ coef_g, DiagArgs dg) {
+  extern __shared__ double2 smem[];
+  double2 *coef = smem;        // [128]
+  double2 *tile = smem + 128;  // [ng*8]
+  const int blk = blockIdx.x % nblocks;
+  const int64_t c0 = (int64_t)(blockIdx.x / nblocks) * 8;
+  const int2 b = blocks[blk];
+  const int g0 = b.x, ng = b.y;
+  const int nb = (int)min((int64_t)8, ncols - c0);
+  if (threadIdx.x < 128) coef[threadIdx.x] = coef_g[threadIdx.x];
+  // staging: 8 consecutive lanes = the 8 columns of one row -> conflict-free 128-byte smem lines
+  for (int idx = threadIdx.x; idx < ng * 8; idx += blockDim.x) {
+    const int cc = idx & 7, g = idx >> 3;
+    if (cc < nb) cp_async16(&tile[idx], v + (g0 + g) + (c0 + cc) * n);
+    else tile[idx] = make_double2(0.0, 0.0);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, L = lane & 7;
+  const int rowperm = (L << 2) | (lane >> 3);  // row inside the group of 32
+  const char *tile_b = (const char *)tile;
+  const char *coef_b = (const char *)coef;
+  unsigned slot16[8];    // byte offset of the slot this lane reads at step kk
+  const double2 *vcol[8];  // global column base of that slot (clamped on the ragged last group)
+#pragma unroll
+  for (int kk = 0; kk < 8; kk++) {
+    const int col = (kk + L) & 7;
+    slot16[kk] = (unsigned)col << 4;
+    vcol[kk] = v + (c0 + min(col, nb - 1)) * n;
+  }
+  for (int gbase = (threadIdx.x & ~31); gbase < ng; gbase += blockDim.x) {
+    const int g = gbase + rowperm;
+    if (g >= ng) continue;
+    const int64_t i = g0 + g;
+    double2 acc[8];
+    if (dg.enabled) {
+      const uint32_t mu_imp = (uint32_t)__ldg(dg.map_row + i) & ((1u << dg.nimp) - 1u);
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        const int col = (kk + L) & 7;
+        const double d = diag_value(dg, i, mu_imp, c0 + min(col, nb - 1));
+        const double2 x = *(const double2 *)(tile_b + ((unsigned)g << 7) + slot16[kk]);
+        acc[kk] = make_double2(d * x.x, d * x.y);
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) acc[kk] = make_double2(0.0, 0.0);
+    }
+    const int len = __ldg(rowlen + i);
+    const int2 sp = __ldg(rowsplit + i);  // entries [sp.x, sp.y) gather inside the tile
+    const uint32_t *pw = pkell + i;
+    // three homogeneous loops (columns are ascending: below the block, inside, above): no branch
+    // divergence between the lanes of a warp, only different trip counts
+    auto off_block = [&](int k0, int k1) {
+      for (int k = k0; k < k1; k++) {
+        const uint32_t w = __ldg(pw + (int64_t)k * n);
+        const uint32_t j = w >> 7;
+        const double2 h = *(const double2 *)(coef_b + ((w & 127u) << 4));
+        double2 x[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) x[kk] = ldg2(vcol[kk] + j);
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          if (REALH) rfma(acc[kk], h.x, x[kk]); else cfma(acc[kk], h, x[kk]);
+        }
+      }
+    };
+    off_block(0, sp.x);
+    off_block(sp.y, len);
+    {
+      uint32_t wnext = sp.x < sp.y ? __ldg(pw + (int64_t)sp.x * n) : 0u;
+      for (int k = sp.x; k < sp.y; k++) {
+        const uint32_t w = wnext;  // next operator word is prefetched
+        if (k + 1 < sp.y) wnext = __ldg(pw + (int64_t)(k + 1) * n);
+        const double2 h = *(const double2 *)(coef_b + ((w & 127u) << 4));
+        const char *src = tile_b + (((w >> 7) - (unsigned)g0) << 7);
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          const double2 x = *(const double2 *)(src + slot16[kk]);
+          if (REALH) rfma(acc[kk], h.x, x); else cfma(acc[kk], h, x);
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int col = (kk + L) & 7;
+      if (col < nb) out[i + (c0 + col) * n] = acc[kk];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Row pass (one rank, no transpose): out(i,c) += sum_k Hd(c,j_k) v(i,j_k).
 // Threads run along i (contiguous), the operator row of column c is warp-uniform (broadcast
 // loads).  Grid x = columns (fastest) inside one slab of rows, so a slab (rows x all columns)
@@ -650,7 +759,26 @@ static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double
   if (ncols <= 0 || s.n <= 0) return 0;
   // variant 0/2 = shared-memory tiles (default), 1 = generic global-gather kernel
   const int64_t var = ctx().opt.colpass_variant;
-  if (var != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+  if (var == 4 && ctx().mode == CDMFT_B200_SPARSE && s.pkell && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+    Ctx &c = ctx();
+    const size_t smem = ((size_t)s.max_block * 8 + 128) * sizeof(double2);
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[c.real_h ? 1 : 0]) {
+      if (c.real_h) CB_CUDA(cudaFuncSetAttribute(k_colpass_rot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else CB_CUDA(cudaFuncSetAttribute(k_colpass_rot<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[c.real_h ? 1 : 0] = smem;
+    }
+    const int64_t nct = ((ncols + 7) / 8) * s.nblocks;
+    if (nct > 0x7fffffffLL) return fail("colpass_rot: grid too large");
+    const int niter = (s.max_block + 575) / 576;
+    int threads = ((s.max_block + niter - 1) / niter + 31) / 32 * 32;
+    threads = std::max(64, std::min(576, threads));
+    if (c.real_h) k_colpass_rot<true><<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.pkell, s.rowlen, s.rowsplit, s.coef, dg);
+    else k_colpass_rot<false><<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.pkell, s.rowlen, s.rowsplit, s.coef, dg);
+    c.launches++;
+    return 0;
+  }
+  if (var != 1 && var != 4 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
     if (var != 2 && ctx().mode == CDMFT_B200_SPARSE && s.pk_in && s.pk_swizzled)
       return ctx().real_h ? launch_tile_pk<true, true>(s, s.n, ncols, v, out, dg) : launch_tile_pk<false, true>(s, s.n, ncols, v, out, dg);
     return launch_colpass_tile(s, ncols, v, out, dg);

@@ -178,6 +178,31 @@ __global__ void k_pk_fill(int64_t n, const int32_t *__restrict__ rowptr, const i
   while (qo < eo) pk_off[qo++] = (uint32_t)i << 11;
 }
 
+// packed ELL: word[k*n + i] = (col << 7) | coef_id for the k-th entry of row i (columns ascending)
+__global__ void k_pkell_fill(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                             const uint8_t *__restrict__ coefidx, int ell_w, uint32_t *__restrict__ pkell) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t p0 = rowptr[i], len = rowptr[i + 1] - p0;
+  for (int k = 0; k < ell_w; k++)
+    pkell[(int64_t)k * n + i] = k < len ? (((uint32_t)col[p0 + k] << 7) | coefidx[p0 + k]) : 0u;
+}
+
+// per row: [k0,k1) = entries (columns ascending) whose source lies inside the row's own block
+__global__ void k_rowsplit(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                           const int2 *__restrict__ blocks, int nblocks, int2 *__restrict__ split) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 b = blocks[find_block(blocks, nblocks, i)];
+  const int32_t p0 = rowptr[i], p1 = rowptr[i + 1];
+  int k0 = 0, k1 = 0;
+  for (int32_t p = p0; p < p1; p++) {
+    if (col[p] < b.x) k0++;
+    if (col[p] < b.x + b.y) k1++;
+  }
+  split[i] = make_int2(k0, k1);
+}
+
 // ED_SPARSE_MAP (ED_SPARSE_MAP.f90:101-121 via ED_SETUP.f90:757-759): counting pass + ordered fill.
 // States of one impurity configuration appear in ascending sector index, so the position inside
 // the row is the number of earlier sector states with the same impurity bits.
@@ -373,6 +398,10 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
       LAUNCH_1D(k_pk_fill, op.n, op.n, op.rowptr, op.col, d_ids, op.blocks, op.nblocks, op.pk_in_ptr, op.pk_off_ptr,
                 pack_swizzled ? 1 : 0, op.pk_in, op.pk_off);
       cudaFree(d_rounds2);
+      CB_CHECK(dev_alloc(&op.rowsplit, op.n));
+      LAUNCH_1D(k_rowsplit, op.n, op.n, op.rowptr, op.col, op.blocks, op.nblocks, op.rowsplit);
+      CB_CHECK(dev_alloc(&op.pkell, (int64_t)op.ell_w * op.n));
+      LAUNCH_1D(k_pkell_fill, op.n, op.n, op.rowptr, op.col, d_ids, op.ell_w, op.pkell);
       op.ncoef = (int32_t)table.size();
       CB_CHECK(dev_alloc(&op.coef, 128));
       table.resize(128, make_double2(0.0, 0.0));
@@ -393,7 +422,7 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
 void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
-  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
+  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
   op = SpinOp();
 }
 

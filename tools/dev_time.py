@@ -29,9 +29,9 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=1, rowpass_variant=3, l1_rows=128),
-         dict(colpass_variant=1, rowpass_variant=3, l1_rows=256), dict(colpass_variant=1, rowpass_variant=3, l1_rows=512),
-         dict(colpass_variant=0, rowpass_variant=3, l1_rows=256), dict()]
+SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=4, rowpass_variant=1),
+         dict(colpass_variant=4, rowpass_variant=1, tile_rows=1000), dict(colpass_variant=4, rowpass_variant=1, force_sharded=1),
+         dict(colpass_variant=1, rowpass_variant=1, force_sharded=1)]
 
 
 def main():
