@@ -83,6 +83,7 @@ struct Options {
   int64_t col_batch = 4;
   int64_t row_slab = 256;
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
+  int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
   int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)
 };
 
@@ -93,6 +94,8 @@ struct Ctx {
   bool spmd = false, sim = false;
   void *nccl_comm = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t comm_stream = nullptr;  // SPMD: pack / all-to-all / unpack of the first transpose
+  cudaEvent_t ev_in = nullptr, ev_comm = nullptr;
   int64_t launches = 0;
   int sm_count = 148;
   Options opt;

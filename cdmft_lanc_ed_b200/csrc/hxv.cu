@@ -998,12 +998,46 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   // sharded: diag -> UP -> transpose -> DW on vt -> transpose back -> add  (spMatVec_mpi_main order)
   int64_t off = 0;
   std::vector<int64_t> offs;
+  const int P = c.p_eff;
+  const bool overlap = c.spmd && P > 1 && !c.rk.empty() && c.opt.overlap && c.comm_stream;
+  std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
+  if (overlap) {
+    // the transpose of v does not depend on the diag+Hup pass: run pack -> all-to-all -> unpack on the
+    // communication stream while the column pass runs on the compute stream
+    RankState &me = c.rk[0];
+    cudaStream_t main = c.stream;
+    CB_CUDA(cudaEventRecord(c.ev_in, main));
+    CB_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_in, 0));
+    c.stream = c.comm_stream;
+    int64_t so = 0, ro = 0;
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {
+      Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
+      cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];
+      cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];
+      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+    }
+    prof_end();
+    prof_begin(3);
+    int rc = nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data());
+    prof_end();
+    if (rc == 0) {
+      prof_begin(2);
+      for (int p = 0; p < P; p++) {
+        Split pd = split_of(c.dimdw, P, p);
+        copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
+      }
+      prof_end();
+      cudaEventRecord(c.ev_comm, c.comm_stream);
+    }
+    c.stream = main;
+    if (rc) return rc;
+  }
   for (auto &r : c.rk) {
     offs.push_back(off);
     CB_CHECK(colpass(c.up, r.dw.q, v + off, hv + off, diag_args(r.dw.off)));
     off += r.nloc;
   }
-  const int P = c.p_eff;
   if (!c.spmd || P == 1) {
     // device-local exchange: write straight into the destination rank's buffer
     prof_begin(2);
@@ -1026,25 +1060,28 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   // SPMD over NCCL: pack (transposing) -> grouped send/recv -> unpack
   if (c.rk.empty()) return 0;  // rank outside the shrunk communicator
   RankState &me = c.rk[0];
-  std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
   int64_t so = 0, ro = 0;
-  prof_begin(2);
-  for (int p = 0; p < P; p++) {
-    Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
-    cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];   // my columns, p's rows
-    cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];  // my rows, p's columns
-    transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+  if (overlap) {
+    CB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
+  } else {
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {
+      Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
+      cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];   // my columns, p's rows
+      cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];  // my rows, p's columns
+      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+    }
+    prof_end();
+    prof_begin(3);
+    CB_CHECK(nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data()));
+    prof_end();
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {
+      Split pd = split_of(c.dimdw, P, p);
+      copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
+    }
+    prof_end();
   }
-  prof_end();
-  prof_begin(3);
-  CB_CHECK(nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data()));
-  prof_end();
-  prof_begin(2);
-  for (int p = 0; p < P; p++) {
-    Split pd = split_of(c.dimdw, P, p);
-    copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
-  }
-  prof_end();
   CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
   so = ro = 0;
   prof_begin(2);

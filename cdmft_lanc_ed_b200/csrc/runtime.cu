@@ -197,6 +197,9 @@ int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const voi
   ncclUniqueId_t id;
   memcpy(&id, uid128, sizeof id);
   CB_NCCL(nccl.CommInitRank(&c.nccl_comm, nranks, id, rank));
+  CB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  CB_CUDA(cudaEventCreateWithFlags(&c.ev_in, cudaEventDisableTiming));
+  CB_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
   return 0;
 }
 
@@ -211,6 +214,9 @@ int cdmft_b200_finalize(void) {
   for (auto &k : c.kv) dev_free(k);
   c.kv_n = 0;
   if (c.red_host) { cudaFreeHost(c.red_host); c.red_host = nullptr; }
+  if (c.comm_stream) { cudaStreamSynchronize(c.comm_stream); cudaStreamDestroy(c.comm_stream); c.comm_stream = nullptr; }
+  if (c.ev_in) { cudaEventDestroy(c.ev_in); c.ev_in = nullptr; }
+  if (c.ev_comm) { cudaEventDestroy(c.ev_comm); c.ev_comm = nullptr; }
   if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
   c.stream = nullptr;
   c.inited = false; c.have_model = false;
@@ -265,6 +271,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "row_slab") c.opt.row_slab = value;
   else if (k == "tile_rows") c.opt.tile_rows = value;
   else if (k == "l1_rows") c.opt.l1_rows = value;
+  else if (k == "overlap") c.opt.overlap = value;
   else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);
   return 0;

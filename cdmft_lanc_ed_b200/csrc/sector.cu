@@ -522,6 +522,7 @@ int cdmft_b200_delete_hv_sector(void) {
   Ctx &c = ctx();
   if (!c.inited) return 0;
   if (c.stream) cudaStreamSynchronize(c.stream);
+  if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
   free_spin_op(c.up);
   free_spin_op(c.dw);
   for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }
