@@ -197,6 +197,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         E.ed_set_MpiComm(local)
     else:

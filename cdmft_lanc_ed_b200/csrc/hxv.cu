@@ -1006,11 +1006,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     // communication stream while the column pass runs on the compute stream
     RankState &me = c.rk[0];
     cudaStream_t main = c.stream;
-    CB_CUDA(cudaEventRecord(c.ev_in, main));
-    CB_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_in, 0));
-    c.stream = c.comm_stream;
     int64_t so = 0, ro = 0;
-    prof_begin(2);
+    prof_begin(2);  // pack on the compute stream (alone, at full speed) ...
     for (int p = 0; p < P; p++) {
       Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
       cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];
@@ -1018,6 +1015,9 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
       transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
     }
     prof_end();
+    CB_CUDA(cudaEventRecord(c.ev_in, main));
+    CB_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_in, 0));
+    c.stream = c.comm_stream;  // ... all-to-all + unpack on the (high-priority) communication stream
     prof_begin(3);
     int rc = nccl_all_to_all(me.sendbuf, me.recvbuf, cs.data(), os.data(), cr.data(), orr.data());
     prof_end();

@@ -197,7 +197,11 @@ int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const voi
   ncclUniqueId_t id;
   memcpy(&id, uid128, sizeof id);
   CB_NCCL(nccl.CommInitRank(&c.nccl_comm, nranks, id, rank));
-  CB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CB_CUDA(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, hi));
+  }
   CB_CUDA(cudaEventCreateWithFlags(&c.ev_in, cudaEventDisableTiming));
   CB_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
   return 0;
