@@ -178,7 +178,7 @@ def _config(workload, ngpus, sparse):
         "dim": dim, "bytes_alg_per_step": 32 * dim,
         "l2": f"vector {16 * dim / 1e6:.0f} MB per pass vs 126 MB L2 (inputs larger than L2, no flush needed)"
               if 16 * dim > 4 * 126e6 else "L2 flushed between steps by a 512 MB memset",
-        "sharding": "none (single rank)" if ngpus == 1 else f"Ndw split over {ngpus} ranks (ED_HAMILTONIAN.f90:92-105), NCCL all-to-all transposes",
+        "sharding": "none (single rank)" if ngpus == 1 else f"Ndw split over {ngpus} ranks (ED_HAMILTONIAN.f90:92-105), distributed transposes over NVLink",
     }
 
 
@@ -212,6 +212,8 @@ def run_ours(args):
     dim = E.getDim(isec)[0]
     sparse = not args.direct
     nloc = E.build_Hv_sector(isec, sparse)
+    if world > 1 and not args.no_ipc:
+        E.ipc_exchange()  # peer-memory transposes (CUDA IPC windows over NVLink)
     small = 16 * dim <= 4 * 126e6
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if small else None
 
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="K3", choices=list(WORKLOADS))
     ap.add_argument("--direct", action="store_true", help="ed_sparse_H=F (matrix-free kernels)")
+    ap.add_argument("--no-ipc", action="store_true", help="N>1: NCCL all-to-all transposes instead of peer-memory stores")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lanczos", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -83,6 +83,7 @@ struct Options {
   int64_t col_batch = 4;
   int64_t row_slab = 256;
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
+  int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
   int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)
 };
@@ -122,6 +123,11 @@ struct Ctx {
   int p_eff = 1;  // min(P, DimDw)
   SpinOp up, dw;
   std::vector<RankState> rk;
+  // CUDA-IPC peer windows (SPMD, optional): peers' vt and recvbuf mapped into this process so the
+  // transposing kernel stores straight into the destination GPU over NVLink (pack + exchange + unpack
+  // in one kernel).  Indexed by rank; entry for this rank = local pointer.
+  bool ipc_ready = false;
+  std::vector<double2 *> peer_vt, peer_recv;
   double2 *vfull = nullptr;  // all-gathered vector for the non-local (Jx/Jp) term, SPMD only
   // staging for host-pointer calls
   double2 *stage_v = nullptr, *stage_hv = nullptr;
@@ -167,6 +173,8 @@ int nccl_allreduce_sum(double *dev_buf, int n);
 int nccl_all_to_all(const double2 *send, double2 *recv, const int64_t *counts_send, const int64_t *offs_send,
                     const int64_t *counts_recv, const int64_t *offs_recv);
 int nccl_load();
+int nccl_barrier();
+void ipc_close_peers();
 int ensure_stage(int64_t n);
 bool is_device_ptr(const void *p);
 

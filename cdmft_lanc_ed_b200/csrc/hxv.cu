@@ -999,7 +999,21 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   int64_t off = 0;
   std::vector<int64_t> offs;
   const int P = c.p_eff;
-  const bool overlap = c.spmd && P > 1 && !c.rk.empty() && c.opt.overlap && c.comm_stream;
+  const bool use_ipc = c.spmd && P > 1 && !c.rk.empty() && c.ipc_ready && c.opt.use_ipc;
+  const bool overlap = !use_ipc && c.spmd && P > 1 && !c.rk.empty() && c.opt.overlap && c.comm_stream;
+  if (use_ipc) {
+    // peer-memory transpose: every rank stores its transposed blocks straight into the owners' vt
+    // over NVLink (pack + exchange + unpack + local_transpose of vector_transpose_MPI in one kernel);
+    // barrier A: every peer has finished reading its vt from the previous product
+    RankState &me = c.rk[0];
+    CB_CHECK(nccl_barrier());
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {
+      Split pu = split_of(c.dimup, P, p);
+      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, c.peer_vt[p], c.dimdw, me.dw.off);
+    }
+    prof_end();
+  }
   std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
   if (overlap) {
     // the transpose of v does not depend on the diag+Hup pass: run pack -> all-to-all -> unpack on the
@@ -1060,6 +1074,24 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   // SPMD over NCCL: pack (transposing) -> grouped send/recv -> unpack
   if (c.rk.empty()) return 0;  // rank outside the shrunk communicator
   RankState &me = c.rk[0];
+  if (use_ipc) {
+    CB_CHECK(nccl_barrier());  // B: all blocks of vt have landed
+    CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {  // back: my rows (up) x p's columns (dw) -> p's receive window, transposed
+      Split pd = split_of(c.dimdw, P, p);
+      transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me.up.q, c.peer_recv[p] + pd.q * me.up.off, me.up.q, 0);
+    }
+    prof_end();
+    CB_CHECK(nccl_barrier());  // C: my receive window is complete
+    prof_begin(2);
+    for (int p = 0; p < P; p++) {
+      Split pu = split_of(c.dimup, P, p);
+      copy_block<true>(me.recvbuf + me.dw.q * pu.off, me.dw.q, pu.q, hv, c.dimup, pu.off);
+    }
+    prof_end();
+    return 0;
+  }
   int64_t so = 0, ro = 0;
   if (overlap) {
     CB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));

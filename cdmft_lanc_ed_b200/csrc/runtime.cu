@@ -120,6 +120,28 @@ int nccl_allreduce_sum(double *dev_buf, int n) {
   return 0;
 }
 
+// cross-rank barrier in stream order (a 1-double all-reduce): brackets the peer-memory transposes
+int nccl_barrier() {
+  Ctx &c = ctx();
+  if (!c.spmd || c.nranks == 1) return 0;
+  double *b = c.red + 3000;
+  CB_NCCL(nccl.AllReduce(b, b, 1, kNcclDouble, kNcclSum, c.nccl_comm, c.stream));
+  return 0;
+}
+
+void ipc_close_peers() {
+  Ctx &c = ctx();
+  if (!c.ipc_ready) return;
+  for (int p = 0; p < (int)c.peer_vt.size(); p++) {
+    if (p == c.rank) continue;
+    if (c.peer_vt[p]) cudaIpcCloseMemHandle(c.peer_vt[p]);
+    if (c.peer_recv[p]) cudaIpcCloseMemHandle(c.peer_recv[p]);
+  }
+  c.peer_vt.clear();
+  c.peer_recv.clear();
+  c.ipc_ready = false;
+}
+
 // all-to-all of complex(8) blocks = the MPI_AllToAllV of vector_transpose_MPI, one grouped call
 int nccl_all_to_all(const double2 *send, double2 *recv, const int64_t *cs, const int64_t *os, const int64_t *cr,
                     const int64_t *orr) {
@@ -227,6 +249,49 @@ int cdmft_b200_finalize(void) {
   return 0;
 }
 
+// ---- CUDA IPC peer windows for the active sector (SPMD) --------------------------------------
+// 1. every rank: cdmft_b200_ipc_export(buf)   -> 2 x 64-byte handles of its vt and recvbuf
+// 2. host program all-gathers the 128-byte records (MPI_Allgather / torch.distributed.all_gather)
+// 3. every rank: cdmft_b200_ipc_import(all, nranks) -> peers' buffers are mapped; the distributed
+//    transpose then runs as one kernel per direction that stores straight into peer memory.
+int cdmft_b200_ipc_export(void *handles128) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  memset(handles128, 0, 128);
+  if (!c.spmd || !c.hstatus) return fail("ipc_export: needs SPMD mode and an active sector");
+  if (c.rk.empty() || !c.rk[0].vt || !c.rk[0].recvbuf) return 0;  // rank outside the shrunk communicator
+  cudaIpcMemHandle_t h[2];
+  CB_CUDA(cudaIpcGetMemHandle(&h[0], c.rk[0].vt));
+  CB_CUDA(cudaIpcGetMemHandle(&h[1], c.rk[0].recvbuf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  memcpy(handles128, h, 128);
+  return 0;
+}
+
+int cdmft_b200_ipc_import(const void *all_handles, int32_t nranks) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.spmd || !c.hstatus) return fail("ipc_import: needs SPMD mode and an active sector");
+  if (nranks != c.nranks) return fail("ipc_import: nranks mismatch");
+  ipc_close_peers();
+  if (c.rk.empty() || c.p_eff < 2) return 0;
+  c.peer_vt.assign(c.nranks, nullptr);
+  c.peer_recv.assign(c.nranks, nullptr);
+  const char *hp = (const char *)all_handles;
+  for (int p = 0; p < c.p_eff; p++) {
+    if (p == c.rank) { c.peer_vt[p] = c.rk[0].vt; c.peer_recv[p] = c.rk[0].recvbuf; continue; }
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, hp + (size_t)p * 128, 128);
+    void *a = nullptr, *b = nullptr;
+    CB_CUDA(cudaIpcOpenMemHandle(&a, h[0], cudaIpcMemLazyEnablePeerAccess));
+    CB_CUDA(cudaIpcOpenMemHandle(&b, h[1], cudaIpcMemLazyEnablePeerAccess));
+    c.peer_vt[p] = (double2 *)a;
+    c.peer_recv[p] = (double2 *)b;
+  }
+  c.ipc_ready = true;
+  return 0;
+}
+
 int cdmft_b200_set_stream(void *s) {
   CB_REQUIRE_INIT();
   ctx().stream = (cudaStream_t)s;  // NULL = the legacy default stream, as in CUDA
@@ -276,6 +341,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "tile_rows") c.opt.tile_rows = value;
   else if (k == "l1_rows") c.opt.l1_rows = value;
   else if (k == "overlap") c.opt.overlap = value;
+  else if (k == "use_ipc") c.opt.use_ipc = value;
   else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);
   return 0;

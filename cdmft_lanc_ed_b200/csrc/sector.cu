@@ -523,6 +523,13 @@ int cdmft_b200_delete_hv_sector(void) {
   if (!c.inited) return 0;
   if (c.stream) cudaStreamSynchronize(c.stream);
   if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
+  if (c.ipc_ready) {  // nobody may still be storing into the windows we are about to free
+    nccl_barrier();
+    cudaStreamSynchronize(c.stream);
+    ipc_close_peers();
+    nccl_barrier();
+    cudaStreamSynchronize(c.stream);
+  }
   free_spin_op(c.up);
   free_spin_op(c.dw);
   for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }

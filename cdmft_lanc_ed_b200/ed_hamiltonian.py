@@ -46,7 +46,7 @@ _lib = None
 ABI_SYMBOLS = [
     "cdmft_b200_last_error", "cdmft_b200_init", "cdmft_b200_nccl_unique_id", "cdmft_b200_init_rank",
     "cdmft_b200_init_sim", "cdmft_b200_finalize", "cdmft_b200_set_stream", "cdmft_b200_reset_stream",
-    "cdmft_b200_profile_query", "cdmft_b200_launch_count",
+    "cdmft_b200_profile_query", "cdmft_b200_launch_count", "cdmft_b200_ipc_export", "cdmft_b200_ipc_import",
     "cdmft_b200_set_option", "cdmft_b200_set_model", "cdmft_b200_get_ns", "cdmft_b200_get_sector_dims",
     "cdmft_b200_vecdim_hv_sector", "cdmft_b200_build_hv_sector", "cdmft_b200_delete_hv_sector",
     "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
@@ -219,6 +219,25 @@ def build_Hv_sector(isector: int, ed_sparse_H: bool = True) -> int:
     _sector.update(isector=isector, nloc=nloc.value)
     spHtimesV_p = _hxv
     return nloc.value
+
+
+def ipc_exchange():
+    """SPMD, after build_Hv_sector: map every peer's transpose windows (CUDA IPC) so the distributed
+    transposes store straight into peer memory over NVLink.  Collective over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    L = load_library()
+    mine = (C.c_ubyte * 128)()
+    _chk(L.cdmft_b200_ipc_export(mine))
+    world = dist.get_world_size()
+    t = torch.tensor(list(bytes(mine)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    allh = bytes(torch.cat(out).cpu().tolist())
+    buf = (C.c_ubyte * len(allh))(*allh)
+    _chk(L.cdmft_b200_ipc_import(buf, C.c_int32(world)))
 
 
 def delete_Hv_sector():

@@ -69,6 +69,14 @@ int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const voi
  * in rank order, the layout of gather_vector_MPI, ED_SETUP.f90:633-668). Test/debug aid. */
 int cdmft_b200_init_sim(int32_t device, int32_t nranks);
 int cdmft_b200_finalize(void);
+/* SPMD, optional, after build_hv_sector: peer-memory windows for the distributed transpose.
+ * Every rank exports 128 bytes (two CUDA IPC handles), the host program all-gathers them
+ * (MPI_Allgather / torch.distributed) and every rank imports the nranks*128-byte array.  The
+ * transposes then store straight into the destination GPU over NVLink (one kernel per direction,
+ * bracketed by stream-ordered NCCL barriers) instead of pack -> all-to-all -> unpack.
+ * delete_hv_sector unmaps the windows (collectively). */
+int cdmft_b200_ipc_export(void *handles128);
+int cdmft_b200_ipc_import(const void *all_handles, int32_t nranks);
 /* launch on this cudaStream_t (NULL = CUDA's legacy default stream) instead of the library's own
  * non-blocking stream; reset_stream goes back to the library's stream */
 int cdmft_b200_set_stream(void *cuda_stream);

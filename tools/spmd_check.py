@@ -15,6 +15,9 @@ from cdmft_lanc_ed_b200 import models, shard_plan as sp  # noqa: E402
 from cdmft_lanc_ed_b200 import ed_hamiltonian as E  # noqa: E402
 
 
+USE_IPC = "--ipc" in sys.argv
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -31,6 +34,8 @@ def main():
         dim, dimup, dimdw = E.getDim(isec)
         for sparse in (True, False):
             nloc = E.build_Hv_sector(isec, sparse)
+            if USE_IPC:
+                E.ipc_exchange()
             assert nloc == E.vecDim_Hv_sector(isec) == sp.vecdim(dimup, dimdw, world, rank)
             p_eff = E.active_ranks()
             rng = np.random.default_rng(100 + isec)
@@ -65,7 +70,7 @@ def main():
     E.ed_finalize()
     dist.destroy_process_group()
     if rank == 0:
-        print("SPMD_CHECK", "PASS" if ok else "FAIL", flush=True)
+        print("SPMD_CHECK", "ipc" if USE_IPC else "nccl", "PASS" if ok else "FAIL", flush=True)
     sys.exit(0 if int(flag.item()) else 1)
 
 
