@@ -1005,14 +1005,31 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     // peer-memory transpose: every rank stores its transposed blocks straight into the owners' vt
     // over NVLink (pack + exchange + unpack + local_transpose of vector_transpose_MPI in one kernel);
     // barrier A: every peer has finished reading its vt from the previous product
+    // The forward transpose only reads v: it runs on the communication stream, overlapped with the
+    // diag+Hup pass on the compute stream.
     RankState &me = c.rk[0];
-    CB_CHECK(nccl_barrier());
+    cudaStream_t main = c.stream;
+    // (measured on 2 B200: overlapping it with the column pass slows both -- they share the LSU
+    // pipe -- so it is sequential unless overlap == 2)
+    const bool ov = c.opt.overlap == 2 && c.comm_stream;
+    if (ov) {
+      CB_CUDA(cudaEventRecord(c.ev_in, main));
+      CB_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_in, 0));
+      c.stream = c.comm_stream;
+    }
+    int rc = nccl_barrier();
     prof_begin(2);
-    for (int p = 0; p < P; p++) {
+    for (int p = 0; p < P && rc == 0; p++) {
       Split pu = split_of(c.dimup, P, p);
       transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, c.peer_vt[p], c.dimdw, me.dw.off);
     }
     prof_end();
+    if (rc == 0) rc = nccl_barrier();  // B: all blocks of every vt have landed
+    if (ov) {
+      cudaEventRecord(c.ev_comm, c.comm_stream);
+      c.stream = main;
+    }
+    if (rc) return rc;
   }
   std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
   if (overlap) {
@@ -1075,7 +1092,7 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   if (c.rk.empty()) return 0;  // rank outside the shrunk communicator
   RankState &me = c.rk[0];
   if (use_ipc) {
-    CB_CHECK(nccl_barrier());  // B: all blocks of vt have landed
+    if (c.opt.overlap == 2 && c.comm_stream) CB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
     CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
     prof_begin(2);
     for (int p = 0; p < P; p++) {  // back: my rows (up) x p's columns (dw) -> p's receive window, transposed
