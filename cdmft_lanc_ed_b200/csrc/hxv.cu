@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) k_tile_pk(int64_t ld, int64_t nbatch,
 // touch the same column at a step own 4 consecutive rows: stores and off-block loads move 64-byte
 // runs (full sectors).  Hops that change the top bits gather from global memory / L2.
 // ------------------------------------------------------------------------------------
-template <bool REALH>
+template <bool REALH, bool INBLOCK_ONLY>
 __global__ void __launch_bounds__(576, 1) k_colpass_rot(int64_t n, int64_t ncols, const double2 *__restrict__ v,
                                                          double2 *__restrict__ out, const int2 *__restrict__ blocks,
                                                          int nblocks, const uint32_t *__restrict__ pkell,
@@ -425,8 +425,10 @@ __global__ void __launch_bounds__(576, 1) k_colpass_rot(int64_t n, int64_t ncols
         }
       }
     };
-    off_block(0, sp.x);
-    off_block(sp.y, len);
+    if (!INBLOCK_ONLY) {  // otherwise the row-pass kernel adds the off-block terms (see k_rowpass UPOFF)
+      off_block(0, sp.x);
+      off_block(sp.y, len);
+    }
     {
       uint32_t wnext = sp.x < sp.y ? __ldg(pw + (int64_t)sp.x * n) : 0u;
       for (int k = sp.x; k < sp.y; k++) {
@@ -455,15 +457,45 @@ __global__ void __launch_bounds__(576, 1) k_colpass_rot(int64_t n, int64_t ncols
 // loads).  Grid x = columns (fastest) inside one slab of rows, so a slab (rows x all columns)
 // stays L2-resident while every column of it is produced.
 // ------------------------------------------------------------------------------------
-template <bool REALH, bool DIRECT>
+struct UpOffArgs {  // off-block Hup terms folded into the row pass (colpass_variant 5)
+  const uint32_t *pkell;  // packed ELL of Hup: (col << 7) | coef_id, [k*n + i]
+  const int32_t *rowlen;
+  const int2 *rowsplit;   // entries [x,y) are in-block (done by k_colpass_rot<.,true>)
+  const double2 *coef;    // [128]
+};
+
+template <bool REALH, bool DIRECT, bool UPOFF>
 __global__ void __launch_bounds__(256) k_rowpass(int64_t n /*rows=DimUp*/, int64_t ncols /*DimDw*/,
                                                   const double2 *__restrict__ v, double2 *__restrict__ out,
                                                   const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                                  const double2 *__restrict__ val, OpArgs op) {
+                                                  const double2 *__restrict__ val, OpArgs op, UpOffArgs uo) {
+  __shared__ double2 ucoef[UPOFF ? 128 : 1];
+  if (UPOFF) {
+    if (threadIdx.x < 128) ucoef[threadIdx.x] = uo.coef[threadIdx.x];
+    __syncthreads();
+  }
   const int64_t c = blockIdx.x;
   const int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 acc = make_double2(0.0, 0.0);
+  if (UPOFF) {
+    // Hup entries whose source row lies outside row i's block: lanes = adjacent rows of ONE column, so
+    // neighbouring sources share 128-byte lines (the cheap way to do the scattered gathers)
+    const int len = __ldg(uo.rowlen + i);
+    const int2 sp = __ldg(uo.rowsplit + i);
+    const double2 *vc = v + c * n;
+    const uint32_t *pw = uo.pkell + i;
+    for (int k = 0; k < sp.x; k++) {
+      const uint32_t w = __ldg(pw + (int64_t)k * n);
+      const double2 x = ldg2(vc + (w >> 7)), h = ucoef[w & 127u];
+      if (REALH) rfma(acc, h.x, x); else cfma(acc, h, x);
+    }
+    for (int k = sp.y; k < len; k++) {
+      const uint32_t w = __ldg(pw + (int64_t)k * n);
+      const double2 x = ldg2(vc + (w >> 7)), h = ucoef[w & 127u];
+      if (REALH) rfma(acc, h.x, x); else cfma(acc, h, x);
+    }
+  }
   if (!DIRECT) {
     const int32_t p0 = __ldg(rowptr + c), p1 = __ldg(rowptr + c + 1);
     int32_t p = p0;
@@ -759,26 +791,30 @@ static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double
   if (ncols <= 0 || s.n <= 0) return 0;
   // variant 0/2 = shared-memory tiles (default), 1 = generic global-gather kernel
   const int64_t var = ctx().opt.colpass_variant;
-  if (var == 4 && ctx().mode == CDMFT_B200_SPARSE && s.pkell && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+  if ((var == 4 || var == 5) && ctx().mode == CDMFT_B200_SPARSE && s.pkell && s.nblocks > 0 &&
+      (size_t)s.max_block * 128 + 2048 <= 232448) {
     Ctx &c = ctx();
+    // variant 5: only the in-block terms here; the caller's row pass adds the off-block ones (UPOFF)
+    const bool inonly = var == 5 && dg.enabled && !(c.spmd || c.sim || c.opt.force_sharded);
     const size_t smem = ((size_t)s.max_block * 8 + 128) * sizeof(double2);
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[c.real_h ? 1 : 0]) {
-      if (c.real_h) CB_CUDA(cudaFuncSetAttribute(k_colpass_rot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else CB_CUDA(cudaFuncSetAttribute(k_colpass_rot<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[c.real_h ? 1 : 0] = smem;
+    auto kern = c.real_h ? (inonly ? k_colpass_rot<true, true> : k_colpass_rot<true, false>)
+                         : (inonly ? k_colpass_rot<false, true> : k_colpass_rot<false, false>);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const int slot = (c.real_h ? 2 : 0) + (inonly ? 1 : 0);
+    if (smem > configured[slot]) {
+      CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[slot] = smem;
     }
     const int64_t nct = ((ncols + 7) / 8) * s.nblocks;
     if (nct > 0x7fffffffLL) return fail("colpass_rot: grid too large");
     const int niter = (s.max_block + 575) / 576;
     int threads = ((s.max_block + niter - 1) / niter + 31) / 32 * 32;
     threads = std::max(64, std::min(576, threads));
-    if (c.real_h) k_colpass_rot<true><<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.pkell, s.rowlen, s.rowsplit, s.coef, dg);
-    else k_colpass_rot<false><<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.pkell, s.rowlen, s.rowsplit, s.coef, dg);
+    kern<<<(unsigned)nct, threads, smem, c.stream>>>(s.n, ncols, v, out, s.blocks, s.nblocks, s.pkell, s.rowlen, s.rowsplit, s.coef, dg);
     c.launches++;
     return 0;
   }
-  if (var != 1 && var != 4 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+  if (var != 1 && var != 4 && var != 5 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
     if (var != 2 && ctx().mode == CDMFT_B200_SPARSE && s.pk_in && s.pk_swizzled)
       return ctx().real_h ? launch_tile_pk<true, true>(s, s.n, ncols, v, out, dg) : launch_tile_pk<false, true>(s, s.n, ncols, v, out, dg);
     return launch_colpass_tile(s, ncols, v, out, dg);
@@ -819,7 +855,9 @@ static int rowpass(const SpinOp &s, int64_t nrows, const double2 *v, double2 *ou
 static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
   Ctx &c = ctx();
   if (s.n <= 0 || nrows <= 0) return 0;
-  if (c.opt.rowpass_variant == 3 && c.mode == CDMFT_B200_SPARSE && s.nblocks_l1 > 0) {
+  // colpass_variant 5 leaves the off-block Hup terms to the generic row-pass kernel
+  const int64_t rv = c.opt.colpass_variant == 5 ? 1 : c.opt.rowpass_variant;
+  if (rv == 3 && c.mode == CDMFT_B200_SPARSE && s.nblocks_l1 > 0) {
     static bool configured = false;
     if (!configured) {  // all of the unified L1/shared array as L1
       cudaFuncSetAttribute(k_rowpass_l1<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -833,9 +871,9 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
     c.launches++;
     return 0;
   }
-  if (c.opt.rowpass_variant != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
+  if (rv != 1 && s.nblocks > 0 && (size_t)s.max_block * 128 + 2048 <= 232448) {
     const bool direct = c.mode == CDMFT_B200_DIRECT;
-    if (c.opt.rowpass_variant != 2 && !direct && s.pk_in && !s.pk_swizzled) {
+    if (rv != 2 && !direct && s.pk_in && !s.pk_swizzled) {
       DiagArgs nodiag{};
       return c.real_h ? launch_tile_pk<true, false>(s, nrows, nrows, v, out, nodiag) : launch_tile_pk<false, false>(s, nrows, nrows, v, out, nodiag);
     }
@@ -846,12 +884,19 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
   if (grid.y > 65535) return fail("rowpass: too many row chunks");
   OpArgs op = op_args(s);
   const bool direct = c.mode == CDMFT_B200_DIRECT;
+  UpOffArgs uo{};
+  const SpinOp &u = c.up;
+  const bool upoff = c.opt.colpass_variant == 5 && !direct && u.pkell && u.rowsplit && u.nblocks > 0 &&
+                     (size_t)u.max_block * 128 + 2048 <= 232448 && &s == &c.dw;
+  if (upoff) { uo.pkell = u.pkell; uo.rowlen = u.rowlen; uo.rowsplit = u.rowsplit; uo.coef = u.coef; }
   if (c.real_h) {
-    if (direct) k_rowpass<true, true><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op);
-    else k_rowpass<true, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op);
+    if (direct) k_rowpass<true, true, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
+    else if (upoff) k_rowpass<true, false, true><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
+    else k_rowpass<true, false, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
   } else {
-    if (direct) k_rowpass<false, true><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op);
-    else k_rowpass<false, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op);
+    if (direct) k_rowpass<false, true, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
+    else if (upoff) k_rowpass<false, false, true><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
+    else k_rowpass<false, false, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
   }
   c.launches++;
   return 0;

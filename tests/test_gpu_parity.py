@@ -252,6 +252,9 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     dict(colpass_variant=1, rowpass_variant=3, l1_rows=256),     # L1-blocked row pass
     dict(colpass_variant=4, rowpass_variant=1, tile_rows=1800),  # rotating-slot shared-memory column pass
     dict(colpass_variant=4, rowpass_variant=1, tile_rows=21),
+    dict(colpass_variant=5, tile_rows=1800),   # in-block Hup in shared memory, off-block Hup folded into the row pass
+    dict(colpass_variant=5, tile_rows=21),
+    dict(colpass_variant=5, tile_rows=33, force_sharded=1),
     dict(colpass_variant=4, rowpass_variant=1, tile_rows=50, force_sharded=1),
     dict(colpass_variant=0, rowpass_variant=3, l1_rows=12),
     dict(colpass_variant=2, rowpass_variant=0, tile_rows=30, force_sharded=1),

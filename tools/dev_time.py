@@ -29,9 +29,8 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=4, rowpass_variant=1),
-         dict(colpass_variant=4, rowpass_variant=1, tile_rows=1000), dict(colpass_variant=4, rowpass_variant=1, force_sharded=1),
-         dict(colpass_variant=1, rowpass_variant=1, force_sharded=1)]
+SWEEP = [dict(colpass_variant=1, rowpass_variant=1), dict(colpass_variant=5), dict(colpass_variant=5, tile_rows=1000),
+         dict(colpass_variant=4)]
 
 
 def main():
@@ -51,9 +50,13 @@ def main():
             n = E.build_Hv_sector(isec, sparse)
             tb = time.time() - t0
             ms = time_hxv(n)
+            E.set_option("profile", 1)
+            time_hxv(n, iters=5, warm=0)
+            kt = {k: round(E.profile_query(k)[0] / 5, 3) for k in (0, 1, 2)}
+            E.set_option("profile", 0)
             E.delete_Hv_sector()
             print(json.dumps(dict(cfg=which, sparse=sparse, **opts, n=n, build_s=round(tb, 3), ms=round(ms, 4),
-                                  gbs_alg=round(32 * n / ms / 1e6, 1))), flush=True)
+                                  gbs_alg=round(32 * n / ms / 1e6, 1), col_ms=kt[0], row_ms=kt[1], tr_ms=kt[2])), flush=True)
     E.ed_finalize()
 
 
