@@ -18,6 +18,8 @@
 
 namespace cb {
 
+int hxv_device_real(const double *v, double *hv);  // hxv_real.cu
+
 static const int kRedBlocks = 1024;  // stage-1 partials (fixed => deterministic)
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -42,44 +44,35 @@ __device__ __forceinline__ void block_sum2(double &a, double &b) {
   }
 }
 
+// element helpers: T = double2 (complex(8), the reference's vector type) or double (real mode)
+__device__ __forceinline__ void dot_acc(double &re, double &im, double2 x, double2 y) {  // conj(x)*y
+  re += x.x * y.x + x.y * y.y;
+  im += x.x * y.y - x.y * y.x;
+}
+__device__ __forceinline__ void dot_acc(double &re, double &, double x, double y) { re += x * y; }
+__device__ __forceinline__ double2 lin3(double a, double2 x, double b, double2 y, double c, double2 z) {
+  return make_double2(a * x.x - b * y.x - c * z.x, a * x.y - b * y.y - c * z.y);
+}
+__device__ __forceinline__ double lin3(double a, double x, double b, double y, double c, double z) { return a * x - b * y - c * z; }
+__device__ __forceinline__ double norm2(double2 x) { return x.x * x.x + x.y * x.y; }
+__device__ __forceinline__ double norm2(double x) { return x * x; }
+__device__ __forceinline__ double2 scaled(double2 x, double s) { return make_double2(x.x * s, x.y * s); }
+__device__ __forceinline__ double scaled(double x, double s) { return x * s; }
+__device__ __forceinline__ double2 axpy1(double2 a, double z, double2 x) { return make_double2(fma(z, x.x, a.x), fma(z, x.y, a.y)); }
+__device__ __forceinline__ double axpy1(double a, double z, double x) { return fma(z, x, a); }
+__device__ __forceinline__ void set_real(double2 &y, double re) { y = make_double2(re, 0.0); }
+__device__ __forceinline__ void set_real(double &y, double re) { y = re; }
+
+#define GRID_STRIDE(i, n) \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
 // partial[blk] = sum conj(a)*b over the block's grid-stride share
-__global__ void __launch_bounds__(256) k_dot(int64_t n, const double2 *__restrict__ a, const double2 *__restrict__ b,
-                                             double2 *__restrict__ partial) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_dot(int64_t n, const T *__restrict__ a, const T *__restrict__ b, double2 *__restrict__ partial) {
   double re = 0, im = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 x = a[i], y = b[i];
-    re += x.x * y.x + x.y * y.y;
-    im += x.x * y.y - x.y * y.x;
-  }
+  GRID_STRIDE(i, n) dot_acc(re, im, a[i], b[i]);
   block_sum2(re, im);
   if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, im);
-}
-// vout += tmp ; partial <vin, vout>
-__global__ void __launch_bounds__(256) k_add_dot(int64_t n, double2 *__restrict__ vout, const double2 *__restrict__ tmp,
-                                                 const double2 *__restrict__ vin, double2 *__restrict__ partial) {
-  double re = 0, im = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 y = vout[i], t = tmp[i], x = vin[i];
-    y.x += t.x; y.y += t.y;
-    vout[i] = y;
-    re += x.x * y.x + x.y * y.y;
-    im += x.x * y.y - x.y * y.x;
-  }
-  block_sum2(re, im);
-  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, im);
-}
-// vout -= alfa*vin ; partial <vout, vout>
-__global__ void __launch_bounds__(256) k_axpy_norm(int64_t n, double2 *__restrict__ vout, const double2 *__restrict__ vin,
-                                                   double alfa, double2 *__restrict__ partial) {
-  double re = 0, im = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 y = vout[i], x = vin[i];
-    y.x -= alfa * x.x; y.y -= alfa * x.y;
-    vout[i] = y;
-    re += y.x * y.x + y.y * y.y;
-  }
-  block_sum2(re, im);
-  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
 }
 __global__ void k_reduce_final(int nparts, const double2 *__restrict__ partial, double *__restrict__ out) {
   double re = 0, im = 0;
@@ -87,34 +80,32 @@ __global__ void k_reduce_final(int nparts, const double2 *__restrict__ partial, 
   block_sum2(re, im);
   if (threadIdx.x == 0) { out[0] = re; out[1] = im; }
 }
-__global__ void __launch_bounds__(256) k_scale(int64_t n, double2 *__restrict__ v, double s) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 x = v[i];
-    v[i] = make_double2(x.x * s, x.y * s);
-  }
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale(int64_t n, T *__restrict__ v, double s) {
+  GRID_STRIDE(i, n) v[i] = scaled(v[i], s);
 }
-__global__ void __launch_bounds__(256) k_fill(int64_t n, double2 *__restrict__ v, double re) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    v[i] = make_double2(re, 0.0);
-}
-// tmp=vin; vin=vout/beta; vout=-beta*tmp   (lanczos_iteration, iter>1)
-__global__ void __launch_bounds__(256) k_swap_scale(int64_t n, double2 *__restrict__ vin, double2 *__restrict__ vout,
-                                                    double beta) {
-  const double ib = 1.0 / beta;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 t = vin[i], y = vout[i];
-    vin[i] = make_double2(y.x / beta, y.y / beta);
-    vout[i] = make_double2(-beta * t.x, -beta * t.y);
-  }
-  (void)ib;
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill(int64_t n, T *__restrict__ v, double re) {
+  GRID_STRIDE(i, n) set_real(v[i], re);
 }
 // acc += z * v
-__global__ void __launch_bounds__(256) k_axpy_real(int64_t n, double2 *__restrict__ acc, const double2 *__restrict__ v,
-                                                   double z) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double2 a = acc[i], x = v[i];
-    acc[i] = make_double2(fma(z, x.x, a.x), fma(z, x.y, a.y));
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpy_real(int64_t n, T *__restrict__ acc, const T *__restrict__ v, double z) {
+  GRID_STRIDE(i, n) acc[i] = axpy1(acc[i], z, v[i]);
+}
+// real <-> complex conversion; c2r also reduces sum |Im|^2 (real mode is only entered when it is 0)
+__global__ void __launch_bounds__(256) k_c2r(int64_t n, const double2 *__restrict__ z, double *__restrict__ r, double2 *__restrict__ partial) {
+  double im2 = 0, dummy = 0;
+  GRID_STRIDE(i, n) {
+    const double2 x = z[i];
+    if (r) r[i] = x.x;
+    im2 += x.y * x.y;
   }
+  block_sum2(im2, dummy);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(im2, 0.0);
+}
+__global__ void __launch_bounds__(256) k_r2c(int64_t n, const double *__restrict__ r, double2 *__restrict__ z) {
+  GRID_STRIDE(i, n) z[i] = make_double2(r[i], 0.0);
 }
 
 static unsigned vec_grid(int64_t n) {
@@ -142,11 +133,12 @@ static int zero_partials() {
   CB_CUDA(cudaMemsetAsync(c.red, 0, 2 * kRedBlocks * sizeof(double), c.stream));
   return 0;
 }
-static int dot(int64_t n, const double2 *a, const double2 *b, std::complex<double> *out) {
+template <typename T>
+static int dot(int64_t n, const T *a, const T *b, std::complex<double> *out) {
   Ctx &c = ctx();
   CB_CHECK(zero_partials());
   if (n > 0) {
-    k_dot<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, a, b, (double2 *)c.red);
+    k_dot<T><<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, a, b, (double2 *)c.red);
     c.launches++;
   }
   return finish_reduce(out);
@@ -169,6 +161,9 @@ static int64_t local_n() {
   return n;
 }
 
+static inline int hxv_t(const double2 *v, double2 *hv) { return hxv_device(v, hv); }
+static inline int hxv_t(const double *v, double *hv) { return hxv_device_real(v, hv); }
+
 // ------------------------------------------------------------------------------------
 // The 3-term recurrence of SciFortran's lanczos_iteration, restated on UNNORMALISED
 // vectors u_j = beta_j v_j so that no separate normalise / swap sweeps are needed:
@@ -177,32 +172,31 @@ static int64_t local_n() {
 //     u_{j+1}  = t/beta_j - (alfa_j/beta_j) u_j - (beta_j/beta_{j-1}) u_{j-1},   beta_{j+1} = |u_{j+1}|
 // (identical to vout = H vin - alfa vin - beta vin_prev with vin = u_j/beta_j).  Per iteration the
 // vector kernels move 96 B/state (one dot, one fused 3-term update + norm) instead of the textbook
-// 176 B/state (swap/scale, add+dot, axpy+norm).
+// 176 B/state (swap/scale, add+dot, axpy+norm); half of that in real mode.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lanczos_update(int64_t n, double2 *__restrict__ um, const double2 *__restrict__ u,
-                                                        const double2 *__restrict__ t, double ct, double cu, double cum,
-                                                        double2 *__restrict__ partial) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_lanczos_update(int64_t n, T *__restrict__ um, const T *__restrict__ u, const T *__restrict__ t,
+                                                        double ct, double cu, double cum, double2 *__restrict__ partial) {
   double re = 0, im = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double2 a = um[i], b = u[i], x = t[i];
-    double2 y;
-    y.x = ct * x.x - cu * b.x - cum * a.x;
-    y.y = ct * x.y - cu * b.y - cum * a.y;
+  GRID_STRIDE(i, n) {
+    const T y = lin3(ct, t[i], cu, u[i], cum, um[i]);
     um[i] = y;
-    re += y.x * y.x + y.y * y.y;
+    re += norm2(y);
   }
   block_sum2(re, im);
   if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
 }
 
+template <typename T>
 struct LanczosRun {
   int64_t n = 0;
-  double2 *um = nullptr, *u = nullptr, *t = nullptr;  // u_{j-1}, u_j, H u_j
+  T *um = nullptr, *u = nullptr, *t = nullptr;  // u_{j-1}, u_j, H u_j
   double beta_prev = 1.0, beta_cur = 1.0;
 };
 
 // u holds the start vector on entry; normalises it (iter == 1 branch of lanczos_iteration)
-static int lanczos_start(LanczosRun &L) {
+template <typename T>
+static int lanczos_start(LanczosRun<T> &L) {
   Ctx &c = ctx();
   std::complex<double> z;
   CB_CHECK(dot(L.n, L.u, L.u, &z));
@@ -210,9 +204,9 @@ static int lanczos_start(LanczosRun &L) {
   if (norm == 0.0) return fail("LANCZOS_ITERATION: norm(vin)=0");
   if (L.n > 0) {
     prof_begin(4);
-    k_scale<<<vec_grid(L.n), 256, 0, c.stream>>>(L.n, L.u, 1.0 / norm);
+    k_scale<T><<<vec_grid(L.n), 256, 0, c.stream>>>(L.n, L.u, 1.0 / norm);
     c.launches++;
-    CB_CUDA(cudaMemsetAsync(L.um, 0, (size_t)L.n * 16, c.stream));
+    CB_CUDA(cudaMemsetAsync(L.um, 0, (size_t)L.n * sizeof(T), c.stream));
     prof_end();
   }
   L.beta_prev = L.beta_cur = 1.0;
@@ -221,10 +215,11 @@ static int lanczos_start(LanczosRun &L) {
 
 // one Lanczos step; on return alfa = alfa_j, beta = beta_{j+1}; the normalised vector of this step is
 // v_j = L.um / L.beta_prev (buffers are rotated)
-static int lanczos_step(LanczosRun &L, double *alfa, double *beta) {
+template <typename T>
+static int lanczos_step(LanczosRun<T> &L, double *alfa, double *beta) {
   Ctx &c = ctx();
   std::complex<double> z;
-  CB_CHECK(hxv_device(L.u, L.t));
+  CB_CHECK(hxv_t(L.u, L.t));
   prof_begin(4);
   CB_CHECK(dot(L.n, L.u, L.t, &z));
   prof_end();
@@ -232,7 +227,7 @@ static int lanczos_step(LanczosRun &L, double *alfa, double *beta) {
   CB_CHECK(zero_partials());
   if (L.n > 0) {
     prof_begin(4);
-    k_lanczos_update<<<std::min<unsigned>(vec_grid(L.n), kRedBlocks), 256, 0, c.stream>>>(
+    k_lanczos_update<T><<<std::min<unsigned>(vec_grid(L.n), kRedBlocks), 256, 0, c.stream>>>(
         L.n, L.um, L.u, L.t, 1.0 / L.beta_cur, a / L.beta_cur, L.beta_cur / L.beta_prev, (double2 *)c.red);
     c.launches++;
     prof_end();
@@ -330,24 +325,28 @@ __global__ void __launch_bounds__(256) k_apply_op(int64_t idim, int64_t idimup, 
   out[j] = o;
 }
 
-}  // namespace cb
 
-using namespace cb;
-
-extern "C" {
-
-int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, double threshold, double *alanc,
-                               double *blanc, int32_t *ndone) {
-  CB_REQUIRE_INIT();
+// real mode = real Hamiltonian, one rank, no Jx/Jp, and a start vector without imaginary part
+static bool real_mode_possible() {
   Ctx &c = ctx();
-  if (!c.hstatus) return fail("lanczos_tridiag: Hsector NOT set");
-  if (nloc != local_n()) return fail("lanczos_tridiag: nloc mismatch");
-  if (threshold <= 0) threshold = 1e-12;
-  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
-  LanczosRun L;
-  L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
-  if (nloc > 0)
-    CB_CUDA(cudaMemcpyAsync(L.u, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+  return c.opt.real_lanczos && c.real_h && !c.jhflag && !c.spmd && !c.sim && !c.opt.force_sharded;
+}
+// sum |Im z|^2 (and optionally r = Re z)
+static int split_real(int64_t n, const double2 *z, double *r, double *im2) {
+  Ctx &c = ctx();
+  CB_CHECK(zero_partials());
+  if (n > 0) {
+    k_c2r<<<std::min<unsigned>(vec_grid(n), kRedBlocks), 256, 0, c.stream>>>(n, z, r, (double2 *)c.red);
+    c.launches++;
+  }
+  std::complex<double> s;
+  CB_CHECK(finish_reduce(&s));
+  *im2 = s.real();
+  return 0;
+}
+
+template <typename T>
+static int tridiag_run(LanczosRun<T> &L, int32_t nitermax, double threshold, double *alanc, double *blanc, int32_t *ndone) {
   for (int i = 0; i < nitermax; i++) { alanc[i] = 0; blanc[i] = 0; }
   CB_CHECK(lanczos_start(L));
   double a = 0, b = 0;
@@ -363,31 +362,13 @@ int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, d
   return 0;
 }
 
-int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double threshold, int32_t ncheck, double *egs,
-                          int32_t *niter, double *alanc_out, double *blanc_out) {
-  CB_REQUIRE_INIT();
+// gs: start vector in (already on device, type T), eigenvector out (same buffer)
+template <typename T>
+static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, int32_t ncheck, double *egs, int32_t *niter,
+                  double *alanc_out, double *blanc_out) {
   Ctx &c = ctx();
-  if (!c.hstatus) return fail("lanczos_gs: Hsector NOT set");
-  if (nloc != local_n()) return fail("lanczos_gs: nloc mismatch");
-  if ((int64_t)nitermax > c.dim) nitermax = (int32_t)c.dim;
-  if (ncheck <= 0) ncheck = 10;
-  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
-  const bool dev = is_device_ptr(vect);
-  LanczosRun L;
-  L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
-  double2 *gs = nullptr;  // start vector, later the accumulated eigenvector
-  if (dev) gs = (double2 *)vect;
-  else {
-    CB_CHECK(ensure_stage(std::max<int64_t>(nloc, 1)));
-    gs = c.stage_v;
-    if (nloc > 0) CB_CUDA(cudaMemcpyAsync(gs, vect, (size_t)nloc * 16, cudaMemcpyHostToDevice, c.stream));
-  }
-  std::complex<double> z;
-  CB_CHECK(dot(nloc, gs, gs, &z));
-  if (z.real() == 0.0) {  // SciFortran start vector is unpinned; constant 1/sqrt(Dim) (SURVEY App. B)
-    if (nloc > 0) { k_fill<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt((double)c.dim)); c.launches++; }
-  }
-  if (nloc > 0) CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
+  const int64_t nloc = L.n;
+  if (nloc > 0) CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
   CB_CHECK(lanczos_start(L));
   std::vector<double> al, bl;  // bl[i] couples i-1,i ; bl[0]=0
   std::vector<double> d, Z;
@@ -414,27 +395,105 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
   e0 = d[0];
   // second pass: vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter (same recurrence, same start)
   if (nloc > 0) {
-    CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * 16, cudaMemcpyDeviceToDevice, c.stream));
-    CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * 16, c.stream));
+    CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+    CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * sizeof(T), c.stream));
   }
   CB_CHECK(lanczos_start(L));
   for (int iter = 1; iter <= nlanc; iter++) {
     CB_CHECK(lanczos_step(L, &a, &b));
     if (nloc > 0) {
       prof_begin(4);
-      k_axpy_real<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, Z[(size_t)(iter - 1) * nlanc + 0] / L.beta_prev);
+      k_axpy_real<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, Z[(size_t)(iter - 1) * nlanc + 0] / L.beta_prev);
       c.launches++;
       prof_end();
     }
   }
+  std::complex<double> z;
   CB_CHECK(dot(nloc, gs, gs, &z));
-  if (nloc > 0) { k_scale<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt(z.real())); c.launches++; }
-  if (!dev && nloc > 0) CB_CUDA(cudaMemcpyAsync(vect, gs, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
-  CB_CUDA(cudaStreamSynchronize(c.stream));
+  if (nloc > 0) { k_scale<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt(z.real())); c.launches++; }
   *egs = e0;
   if (niter) *niter = nlanc;
   if (alanc_out) std::copy(al.begin(), al.end(), alanc_out);
   if (blanc_out) std::copy(bl.begin(), bl.begin() + nlanc, blanc_out);
+  return 0;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, double threshold, double *alanc,
+                               double *blanc, int32_t *ndone) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("lanczos_tridiag: Hsector NOT set");
+  if (nloc != local_n()) return fail("lanczos_tridiag: nloc mismatch");
+  if (threshold <= 0) threshold = 1e-12;
+  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
+  double2 *z0 = c.kv[0];
+  if (nloc > 0)
+    CB_CUDA(cudaMemcpyAsync(z0, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+  if (real_mode_possible() && nloc > 0) {
+    double *r = (double *)c.kv[1];  // u (real) in the first half of kv[1]
+    double im2 = 1.0;
+    CB_CHECK(split_real(nloc, z0, r, &im2));
+    if (im2 == 0.0) {
+      LanczosRun<double> L;
+      L.n = nloc; L.u = r; L.um = r + nloc; L.t = (double *)c.kv[2];
+      return tridiag_run(L, nitermax, threshold, alanc, blanc, ndone);
+    }
+  }
+  LanczosRun<double2> L;
+  L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
+  return tridiag_run(L, nitermax, threshold, alanc, blanc, ndone);
+}
+
+int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double threshold, int32_t ncheck, double *egs,
+                          int32_t *niter, double *alanc_out, double *blanc_out) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("lanczos_gs: Hsector NOT set");
+  if (nloc != local_n()) return fail("lanczos_gs: nloc mismatch");
+  if ((int64_t)nitermax > c.dim) nitermax = (int32_t)c.dim;
+  if (ncheck <= 0) ncheck = 10;
+  CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
+  const bool dev = is_device_ptr(vect);
+  double2 *gs = nullptr;  // start vector, later the accumulated eigenvector
+  if (dev) gs = (double2 *)vect;
+  else {
+    CB_CHECK(ensure_stage(std::max<int64_t>(nloc, 1)));
+    gs = c.stage_v;
+    if (nloc > 0) CB_CUDA(cudaMemcpyAsync(gs, vect, (size_t)nloc * 16, cudaMemcpyHostToDevice, c.stream));
+  }
+  std::complex<double> z;
+  CB_CHECK(dot(nloc, gs, gs, &z));
+  if (z.real() == 0.0) {  // SciFortran start vector is unpinned; constant 1/sqrt(Dim) (SURVEY App. B)
+    if (nloc > 0) { k_fill<double2><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt((double)c.dim)); c.launches++; }
+  }
+  bool done = false;
+  if (real_mode_possible() && nloc > 0) {
+    // real mode: u, um in kv[0] (two halves), t and the real eigenvector in kv[1]
+    double *gr = (double *)c.kv[1] + nloc;
+    double im2 = 1.0;
+    CB_CHECK(split_real(nloc, gs, gr, &im2));
+    if (im2 == 0.0) {
+      LanczosRun<double> L;
+      L.n = nloc; L.u = (double *)c.kv[0]; L.um = (double *)c.kv[0] + nloc; L.t = (double *)c.kv[1];
+      CB_CHECK(gs_run(L, gr, nitermax, threshold, ncheck, egs, niter, alanc_out, blanc_out));
+      k_r2c<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gr, gs);
+      c.launches++;
+      done = true;
+    }
+  }
+  if (!done) {
+    LanczosRun<double2> L;
+    L.n = nloc; L.u = c.kv[0]; L.um = c.kv[1]; L.t = c.kv[2];
+    CB_CHECK(gs_run(L, gs, nitermax, threshold, ncheck, egs, niter, alanc_out, blanc_out));
+  }
+  if (!dev && nloc > 0) CB_CUDA(cudaMemcpyAsync(vect, gs, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
   return 0;
 }
 

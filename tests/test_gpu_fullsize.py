@@ -109,3 +109,31 @@ def test_fullsize_K3_against_oracle(ed, oracle_lib):
     assert np.abs(hv - ref).max() / np.abs(ref).max() < RTOL
     # checksum of checksums: column sums of |Hv|^2 agree as well
     assert abs(np.vdot(hv, hv).real - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
+
+
+def test_K2_gimp_matsubara_vs_oracle(ed, oracle_lib):
+    """BASELINE config 2 (Ns=12, sector (6,6) Dim 853 776; GF sectors (7,6)/(5,6) Dim 731 808): Matsubara
+    Gimp_11 through the full device pipeline (c^+/c on device, 200-step tridiagonalisation, pole/weight
+    accumulation) against the oracle, same ground state fed to both: 1e-10 relative (north_star)."""
+    import os
+    from tests.gf_pipeline import gimp_element
+    mdl = models.hm2x2(2)
+    oracle_lib.lib().edo_set_num_threads(os.cpu_count() or 1)
+    orc = oracle_lib.Oracle(mdl)
+    isec = models.get_sector(12, 6, 6)
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_MPI, os.cpu_count() or 1)
+    e0, vec, nit, _, _ = orc.lanc_eigh(512, 1e-13)
+    orc.delete_hv_sector()
+    # product ground state agrees with the oracle's (energy 1e-10, vector up to phase)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(isec)
+    pv = np.zeros(n, dtype=np.complex128)
+    pe0, pnit, _, _ = ed.sp_lanc_eigh(pv, 512, 1e-13)
+    ed.delete_Hv_sector()
+    assert abs(pe0 - e0) <= RTOL * abs(e0)
+    assert abs(abs(np.vdot(vec, pv)) - 1) < 1e-8
+    beta = 100.0
+    wm = np.pi / beta * (2 * np.arange(1, 129) - 1)
+    g_prod = gimp_element("product", mdl, 1, 1, wm, ed=ed, gs=(e0, vec))
+    g_orc = gimp_element("oracle", mdl, 1, 1, wm, edo=oracle_lib, gs=(e0, vec))
+    assert np.abs(g_prod - g_orc).max() / np.abs(g_orc).max() < RTOL

@@ -283,3 +283,37 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     finally:
         for k, v in defaults.items():
             ed.set_option(k, v)
+
+
+def test_real_mode_krylov_equals_complex_mode(ed, oracle_lib):
+    """Real Hamiltonian + real start vector: the Krylov drivers keep 8-byte real vectors (hxv_real.cu);
+    coefficients, E0 and eigenvector must agree with the complex(8) path and with the oracle."""
+    for mdl, (nup, ndw), sparse in [(models.hm2x2(2), (6, 6), True), (models.hm2x2(2), (5, 6), False),
+                                     (models.random_model(3, 1, 1, complex_h=False, seed=13), (3, 3), True)]:
+        orc = oracle_lib.Oracle(mdl)
+        ed.ed_set_model(mdl)
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        n = ed.build_Hv_sector(isec, sparse)
+        orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+        v0 = _rand_vec(n, seed=21, real=True)
+        res = {}
+        for mode in (1, 0):
+            ed.set_option("real_lanczos", mode)
+            nd, a, b = ed.sp_lanc_tridiag(v0, 40)
+            vec = np.zeros(n, dtype=np.complex128)
+            e0, nit, _, _ = ed.sp_lanc_eigh(vec, 300, 1e-13)
+            res[mode] = (nd, a, b, e0, vec)
+        ed.set_option("real_lanczos", 1)
+        ond, oa, ob = orc.lanc_tridiag(v0, 40)
+        oe0 = orc.lanc_eigh(300, 1e-13)[0]
+        for mode in (1, 0):
+            nd, a, b, e0, vec = res[mode]
+            assert nd == ond
+            assert np.abs(a[:30] - oa[:30]).max() <= RTOL * np.abs(oa[:30]).max()
+            assert np.abs(b[:30] - ob[:30]).max() <= RTOL * np.abs(ob[:30]).max()
+            assert abs(e0 - oe0) <= RTOL * abs(oe0)
+            assert np.abs(vec.imag).max() == 0.0
+            assert np.linalg.norm(orc.hxv(vec) - e0 * vec) < 1e-5
+        assert abs(abs(np.vdot(res[0][4], res[1][4])) - 1) < 1e-8
+        ed.delete_Hv_sector()
+        orc.delete_hv_sector()
