@@ -317,7 +317,8 @@ def run_ours(args):
         e0, nit, _, _ = E.sp_lanc_eigh(vec, args.lanc_niter, args.lanc_tol)
         barrier()
         gs = {"seconds": time.perf_counter() - t0, "iterations": nit, "hxv_calls": 2 * nit, "e0": e0,
-              "threshold": args.lanc_tol, "nitermax": args.lanc_niter, "start": "constant 1/sqrt(Dim)"}
+              "threshold": args.lanc_tol, "nitermax": args.lanc_niter, "start": "constant 1/sqrt(Dim)",
+              "vectors": "real (8 B) -- H and start vector real, single rank" if (mdl.is_real and world == 1) else "complex(8)"}
         del vec
 
     peaks = _load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))

@@ -477,6 +477,49 @@ __global__ void __launch_bounds__(256) k_rowpass(int64_t n /*rows=DimUp*/, int64
 }
 
 // ------------------------------------------------------------------------------------
+// Row pass, RB row chunks per thread (SPARSE): the warp-uniform operator entry (column index +
+// coefficient = 2 L1 wavefronts) is fetched once per RB coalesced gathers instead of once per gather,
+// and the RB gathers of an entry are independent loads in flight.
+// ------------------------------------------------------------------------------------
+template <bool REALH, int RB>
+__global__ void __launch_bounds__(256) k_rowpass_rb(int64_t n /*rows=DimUp*/, const double2 *__restrict__ v,
+                                                     double2 *__restrict__ out, const int32_t *__restrict__ rowptr,
+                                                     const int32_t *__restrict__ col, const double2 *__restrict__ val) {
+  const int64_t c = blockIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * (blockDim.x * RB) + threadIdx.x;
+  double2 acc[RB];
+  const double2 *vi[RB];
+#pragma unroll
+  for (int r = 0; r < RB; r++) {
+    acc[r] = make_double2(0.0, 0.0);
+    vi[r] = v + min(i0 + (int64_t)r * blockDim.x, n - 1);  // clamped: rows past the end are not stored
+  }
+  const int32_t p0 = __ldg(rowptr + c), p1 = __ldg(rowptr + c + 1);
+  for (int32_t p = p0; p < p1; p++) {
+    const int64_t off = (int64_t)__ldg(col + p) * n;
+    const double2 h = ldg2(val + p);
+    double2 x[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) x[r] = ldg2(vi[r] + off);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+      if (REALH) rfma(acc[r], h.x, x[r]); else cfma(acc[r], h, x[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; r++) {
+    const int64_t i = i0 + (int64_t)r * blockDim.x;
+    if (i < n) {
+      double2 *o = out + i + c * n;
+      double2 y = *o;
+      y.x += acc[r].x;
+      y.y += acc[r].y;
+      *o = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Row pass, shared-memory tile variant: one CTA owns (block of dw states) x (8 consecutive iup).
 // Same structure as k_colpass_tile with the roles swapped: the 8 batch entries of one dw state
 // are 128 contiguous bytes in global memory, so staging, the gathers (tile[j][0..7]), the
@@ -833,6 +876,20 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
   const bool upoff = c.opt.colpass_variant == 5 && !direct && u.pkell && u.rowsplit && u.nblocks > 0 &&
                      (size_t)u.max_block * 128 + 2048 <= 232448 && &s == &c.dw;
   if (upoff) { uo.pkell = u.pkell; uo.rowlen = u.rowlen; uo.rowsplit = u.rowsplit; uo.coef = u.coef; }
+  if (!direct && !upoff && c.opt.row_rb > 1) {
+    // RB row chunks per thread: grid.y covers 256*RB rows per CTA
+    const int rb = c.opt.row_rb >= 4 ? 4 : 2;
+    dim3 g2((unsigned)s.n, (unsigned)((nrows + 256 * rb - 1) / (256 * rb)));
+    if (c.real_h) {
+      if (rb == 4) k_rowpass_rb<true, 4><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else k_rowpass_rb<true, 2><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+    } else {
+      if (rb == 4) k_rowpass_rb<false, 4><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else k_rowpass_rb<false, 2><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+    }
+    c.launches++;
+    return 0;
+  }
   if (c.real_h) {
     if (direct) k_rowpass<true, true, false><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
     else if (upoff) k_rowpass<true, false, true><<<grid, 256, 0, c.stream>>>(nrows, s.n, v, out, s.rowptr, s.col, s.val, op, uo);
@@ -1008,7 +1065,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     }
     int rc = nccl_barrier();
     prof_begin(2);
-    for (int p = 0; p < P && rc == 0; p++) {
+    for (int k = 0; k < P && rc == 0; k++) {
+      const int p = (me.rank + k) % P;  // staggered schedule: at step k every rank targets a different GPU
       Split pu = split_of(c.dimup, P, p);
       transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, c.peer_vt[p], c.dimdw, me.dw.off);
     }
@@ -1084,7 +1142,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     if (c.opt.overlap == 2 && c.comm_stream) CB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
     CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
     prof_begin(2);
-    for (int p = 0; p < P; p++) {  // back: my rows (up) x p's columns (dw) -> p's receive window, transposed
+    for (int k = 0; k < P; k++) {  // back: my rows (up) x p's columns (dw) -> p's receive window, transposed
+      const int p = (me.rank + k) % P;
       Split pd = split_of(c.dimdw, P, p);
       transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me.up.q, c.peer_recv[p] + pd.q * me.up.off, me.up.q, 0);
     }
