@@ -81,10 +81,10 @@ struct Options {
   int64_t rowpass_variant = 1;
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
-  int64_t row_slab = 256;
+  int64_t row_slab = 128;       // rows swept per grid.y index of the row pass (slab x all columns stays in L2)
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
   int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
-  int64_t row_rb = 4;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
+  int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
   int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)

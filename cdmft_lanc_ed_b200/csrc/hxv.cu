@@ -876,16 +876,22 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
   const bool upoff = c.opt.colpass_variant == 5 && !direct && u.pkell && u.rowsplit && u.nblocks > 0 &&
                      (size_t)u.max_block * 128 + 2048 <= 232448 && &s == &c.dw;
   if (upoff) { uo.pkell = u.pkell; uo.rowlen = u.rowlen; uo.rowsplit = u.rowsplit; uo.coef = u.coef; }
-  if (!direct && !upoff && c.opt.row_rb > 1) {
+  if (!direct && !upoff && (c.opt.row_rb > 1 || c.opt.row_slab != 256)) {
     // RB row chunks per thread: grid.y covers 256*RB rows per CTA
-    const int rb = c.opt.row_rb >= 4 ? 4 : 2;
-    dim3 g2((unsigned)s.n, (unsigned)((nrows + 256 * rb - 1) / (256 * rb)));
+    // the slab of rows one grid.y index sweeps (threads*RB rows x all columns) must stay L2-resident:
+    // 256 rows x 12870 columns x 16 B = 53 MB at K3 -> threads = row_slab / RB
+    const int rb = c.opt.row_rb >= 4 ? 4 : (c.opt.row_rb >= 2 ? 2 : 1);
+    const int slab = (int)std::max<int64_t>(64, std::min<int64_t>(1024, c.opt.row_slab));
+    const int thr = std::max(32, slab / rb / 32 * 32);
+    dim3 g2((unsigned)s.n, (unsigned)((nrows + (int64_t)thr * rb - 1) / ((int64_t)thr * rb)));
     if (c.real_h) {
-      if (rb == 4) k_rowpass_rb<true, 4><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else k_rowpass_rb<true, 2><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      if (rb == 4) k_rowpass_rb<true, 4><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else if (rb == 2) k_rowpass_rb<true, 2><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else k_rowpass_rb<true, 1><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
     } else {
-      if (rb == 4) k_rowpass_rb<false, 4><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else k_rowpass_rb<false, 2><<<g2, 256, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      if (rb == 4) k_rowpass_rb<false, 4><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else if (rb == 2) k_rowpass_rb<false, 2><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+      else k_rowpass_rb<false, 1><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
     }
     c.launches++;
     return 0;

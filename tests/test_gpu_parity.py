@@ -244,7 +244,7 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
 @pytest.mark.parametrize("opts", [
     dict(colpass_variant=1, rowpass_variant=1, col_batch=1),   # generic global-gather kernels
     dict(colpass_variant=1, rowpass_variant=1, col_batch=8),
-    dict(row_rb=1), dict(row_rb=2),
+    dict(row_rb=4, row_slab=256), dict(row_rb=1, row_slab=256), dict(row_rb=1, row_slab=64),
     dict(colpass_variant=0, rowpass_variant=0, tile_rows=1800),  # shared-memory tiles, one block
     dict(colpass_variant=0, rowpass_variant=0, tile_rows=40),    # many row blocks: off-block gathers
     dict(colpass_variant=0, rowpass_variant=0, tile_rows=9),
@@ -267,7 +267,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=1, rowpass_variant=1, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=4)
+    defaults = dict(colpass_variant=1, rowpass_variant=1, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)
