@@ -16,6 +16,19 @@ struct Term {  // h(a,b) c^+_a c_b, a != b, 0-based bit positions inside one spi
   double re, im;
 };
 
+// Conflict-free schedule of a per-spin operator for the column-resident kernels (k_colres, hxv.cu):
+// rows are taken in groups of G consecutive rows (G lanes = one shared-memory phase: 8 lanes x 16 B for
+// complex vectors, 16 lanes x 8 B for real ones); the entries of a group are edge-coloured (rows x banks,
+// bank = source row mod G) so that at every step the G lanes read G different banks.  Groups are sorted
+// by their number of steps and dealt 32/G to a warp task.
+struct Sched {
+  int32_t G = 0, ntask = 0;
+  int64_t nsteps = 0;           // sum of the tasks' step counts (each a multiple of 4)
+  int32_t *task_off = nullptr;  // [ntask+1] first step of each warp task (device)
+  int32_t *task_grp = nullptr;  // [ntask*(32/G)] row group of each lane group, -1 = none (device)
+  uint32_t *words = nullptr;    // [nsteps*32] one uint4 (4 consecutive steps) per lane and step quad; formats in sector.cu
+};
+
 // Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).
 struct SpinOp {
   int32_t npart = 0;        // Nup or Ndw
@@ -53,6 +66,10 @@ struct SpinOp {
   double2 *coef = nullptr;       // [ncoef] distinct signed coefficients, coef[0] = 0
   int32_t ncoef = 0;
   bool pk_swizzled = false;      // built for the column pass (slot swizzled with rel&7)
+  // column-resident kernels: schedules for 16-byte (sc8) and 8-byte (sc16) vector elements
+  Sched sc8, sc16;
+  bool sc_fast = false;          // real H with <= 2 distinct |coefficients|: sign and class bits instead of table ids
+  double sc_mag[2] = {0.0, 0.0};
 };
 
 struct Split {  // first (n mod P) ranks get one more (ED_HAMILTONIAN.f90:92-105)
@@ -75,9 +92,11 @@ struct RankState {
 };
 
 struct Options {
-  // kernel variants: 1 = generic global-gather kernels (default: fastest measured on B200, see
-  // DESIGN.md), 0 = packed shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass
-  int64_t colpass_variant = 1;
+  // kernel variants: 6 = column-resident shared-memory kernel (default; falls back to 1 when a column does
+  // not fit in shared memory or in DIRECT mode), 1 = generic global-gather kernels, 0 = packed
+  // shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass, 4/5 = rotating-slot tiles
+  int64_t colpass_variant = 6;
+  int64_t sched = 1;            // 1 = conflict-free edge-coloured schedule, 0 = natural CSR order (for comparison)
   int64_t rowpass_variant = 1;
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;

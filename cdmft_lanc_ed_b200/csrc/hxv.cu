@@ -776,8 +776,14 @@ static int colpass(const SpinOp &s, int64_t ncols, const double2 *v, double2 *ou
 }
 static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double2 *out, const DiagArgs &dg) {
   if (ncols <= 0 || s.n <= 0) return 0;
-  // variant 0/2 = shared-memory tiles (default), 1 = generic global-gather kernel
-  const int64_t var = ctx().opt.colpass_variant;
+  // variant 6 = column-resident shared-memory kernel (default), 1 = generic global-gather kernel,
+  // 0/2 = shared-memory tiles, 4/5 = rotating-slot tiles
+  int64_t var = ctx().opt.colpass_variant;
+  if (var == 6) {
+    const int rc = launch_colres<double2>(s, ncols, v, out, dg);
+    if (rc <= 0) return rc;
+    var = 1;  // does not apply (DIRECT mode, column larger than shared memory): generic kernel
+  }
   if ((var == 4 || var == 5) && ctx().mode == CDMFT_B200_SPARSE && s.pkell && s.nblocks > 0 &&
       (size_t)s.max_block * 128 + 2048 <= 232448) {
     Ctx &c = ctx();

@@ -1,5 +1,7 @@
 // hxv_common.cuh -- device helpers shared by the H x v translation units (hxv.cu, hxv_real.cu)
 #pragma once
+#include <algorithm>
+
 #include "ctx.h"
 
 namespace cb {
@@ -59,6 +61,175 @@ __device__ __forceinline__ double diag_value(const DiagArgs &d, int64_t i, uint3
     val += __ldg(d.cross_tab + (int64_t)b * nst + mu_imp);
   }
   return val;
+}
+
+// ------------------------------------------------------------------------------------
+// Column-resident column pass (SPARSE mode; the default when a column fits in shared memory).
+//   out(i,c) = [diag] d(i,c) v(i,c) + sum_k H(i,j_k) v(j_k,c)
+// A persistent CTA per SM walks over columns c = blockIdx.x, +gridDim.x, ...: the whole column
+// (DimUp x sizeof(T): 206 KB for complex(8) at Ns=16) is brought into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier, no registers, no L1 wavefronts), so v is read from HBM exactly once and
+// EVERY gather of the operator is a shared-memory read -- 128 B/clk/SM instead of the 64 B/clk of the
+// L1 path that bounds the generic kernels.  The gathers follow the edge-coloured schedule (Sched,
+// ctx.h): at every step the G lanes of a shared-memory phase read G different banks, and a warp's
+// four (two) row groups have about the same number of steps.  Operator words stream from L2,
+// coalesced, two steps per 8-byte load, prefetched two loads ahead.
+// T = double2 (G = 8) or double (G = 16, real Krylov mode).  FAST: real H with <= 2 |coefficients|,
+// decoded with selects; otherwise a 128-entry coefficient table in shared memory.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+struct ColResArgs {
+  const int32_t *task_off, *task_grp;
+  const uint32_t *words;
+  int ntask;
+  const double2 *coef;  // [128] (general decode)
+  double m0, m1;        // FAST decode
+};
+
+__device__ __forceinline__ void colres_fma(double2 &acc, double h, double2 x) { rfma(acc, h, x); }
+__device__ __forceinline__ void colres_fma(double &acc, double h, double x) { acc = fma(h, x, acc); }
+__device__ __forceinline__ void colres_cfma(double2 &acc, double2 h, double2 x) { cfma(acc, h, x); }
+__device__ __forceinline__ void colres_cfma(double &acc, double2 h, double x) { acc = fma(h.x, x, acc); }
+__device__ __forceinline__ void colres_zero(double2 &a) { a = make_double2(0.0, 0.0); }
+__device__ __forceinline__ void colres_zero(double &a) { a = 0.0; }
+__device__ __forceinline__ double2 colres_scale(double d, double2 x) { return make_double2(d * x.x, d * x.y); }
+__device__ __forceinline__ double colres_scale(double d, double x) { return d * x; }
+
+template <typename T, bool REALH, bool FAST>
+__device__ __forceinline__ void colres_step(T &acc, uint32_t w, const char *xs, const char *coef_b, double m0, double m1) {
+  if (FAST) {
+    // w = (negative << 31) | byte offset | class : branch-free, idle lanes read a zero element
+    const T x = *(const T *)(xs + (w & 0x7FFFFFF8u & ~(uint32_t)(sizeof(T) - 1)));
+    const double m = (w & 1u) ? m1 : m0;
+    const double h = __hiloint2double(__double2hiint(m) ^ (int)(w & 0x80000000u), __double2loint(m));
+    colres_fma(acc, h, x);
+  } else {
+    const T x = *(const T *)(xs + (size_t)(w >> 7) * sizeof(T));
+    if (REALH) colres_fma(acc, *(const double *)(coef_b + ((w & 127u) << 4)), x);
+    else colres_cfma(acc, *(const double2 *)(coef_b + ((w & 127u) << 4)), x);
+  }
+}
+
+template <typename T, bool REALH, bool FAST>
+__global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, const T *__restrict__ v, T *__restrict__ out,
+                                                     ColResArgs a, DiagArgs dg) {
+  constexpr int G = sizeof(T) == 16 ? 8 : 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [0,8) mbarrier | [128, 128+2048) coefficient table | dtab [2^nimp doubles] | column + G zero elements
+  uint64_t *bar = (uint64_t *)smem_raw;
+  double2 *coef = (double2 *)(smem_raw + 128);
+  double *dtab = (double *)(smem_raw + 128 + 2048);
+  const int ndt = dg.enabled ? (1 << dg.nimp) : 0;
+  T *xs = (T *)(smem_raw + 128 + 2048 + (((size_t)ndt * 8 + 127) & ~(size_t)127));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t npad = (n + G - 1) / G * G;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  if (threadIdx.x < 128) coef[threadIdx.x] = FAST ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
+  for (int64_t k = n + threadIdx.x; k < npad + G; k += blockDim.x) colres_zero(xs[k]);  // idle lanes gather these
+  __syncthreads();
+  const uint32_t bytes = (uint32_t)(n * sizeof(T));
+  const char *xs_b = (const char *)xs;
+  const char *coef_b = (const char *)coef;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < ncols; c += gridDim.x) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      const char *src = (const char *)(v + c * n);
+      for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s((char *)xs + off, src + off, min(32768u, bytes - off), bar);
+    }
+    for (int mu = threadIdx.x; mu < ndt; mu += blockDim.x) {  // diagonal of this column per impurity configuration of the row
+      const int64_t cg = dg.coloff + c;
+      double val = __ldg(dg.f_col + cg);
+      uint32_t md = (uint32_t)__ldg(dg.map_col + cg) & ((1u << dg.nimp) - 1u);
+      while (md) {
+        const int b = __ffs(md) - 1;
+        md &= md - 1;
+        val += __ldg(dg.cross_tab + ((int64_t)b << dg.nimp) + mu);
+      }
+      dtab[mu] = val;
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncthreads();
+    T *oc = out + c * n;
+    for (int task = warp; task < a.ntask; task += nwarps) {
+      const int grp = __ldg(a.task_grp + task * (32 / G) + lane / G);
+      const int64_t i = (int64_t)grp * G + (lane & (G - 1));
+      const bool valid = grp >= 0 && i < n;
+      const int k0 = __ldg(a.task_off + task), nquad = (__ldg(a.task_off + task + 1) - k0) >> 2;
+      const uint4 *wp = (const uint4 *)a.words + (int64_t)(k0 >> 2) * 32 + lane;
+      uint4 wn = nquad > 0 ? __ldg(wp) : make_uint4(0u, 0u, 0u, 0u);
+      T acc;
+      colres_zero(acc);
+      if (dg.enabled && valid) {
+        const uint32_t mu = (uint32_t)__ldg(dg.map_row + i) & ((1u << dg.nimp) - 1u);
+        acc = colres_scale(__ldg(dg.f_row + i) + dtab[mu], xs[i]);
+      }
+      for (int kq = 0; kq < nquad; kq++) {
+        const uint4 w = wn;
+        if (kq + 1 < nquad) wn = __ldg(wp + (int64_t)(kq + 1) * 32);
+        colres_step<T, REALH, FAST>(acc, w.x, xs_b, coef_b, a.m0, a.m1);
+        colres_step<T, REALH, FAST>(acc, w.y, xs_b, coef_b, a.m0, a.m1);
+        colres_step<T, REALH, FAST>(acc, w.z, xs_b, coef_b, a.m0, a.m1);
+        colres_step<T, REALH, FAST>(acc, w.w, xs_b, coef_b, a.m0, a.m1);
+      }
+      if (valid) oc[i] = acc;
+    }
+    __syncthreads();  // every gather of this column is done before the next bulk copy lands
+  }
+}
+
+// shared memory the kernel needs for a column of n elements of elem bytes
+inline size_t colres_smem(int64_t n, int elem, int nimp_diag) {
+  const size_t ndt = nimp_diag >= 0 ? ((size_t)1 << nimp_diag) : 0;
+  return 128 + 2048 + ((ndt * 8 + 127) & ~(size_t)127) + ((size_t)n + 32) * elem;  // + padding and zero elements
+}
+
+// launch on the context's stream; returns 1 when the kernel does not apply (caller falls back)
+template <typename T>
+inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
+  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return 1;
+  if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return 1;  // bulk copies need 16-byte aligned columns
+  const size_t smem = colres_smem(s.n, (int)sizeof(T), dg.enabled ? dg.nimp : -1);
+  if (smem > 232448) return 1;
+  ColResArgs a{};
+  a.task_off = sc.task_off; a.task_grp = sc.task_grp; a.words = sc.words; a.ntask = sc.ntask;
+  a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
+  void (*kern)(int64_t, int64_t, const T *, T *, ColResArgs, DiagArgs) =
+      s.sc_fast ? k_colres<T, true, true> : (c.real_h ? k_colres<T, true, false> : k_colres<T, false, false>);
+  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(128, (int64_t)sc.ntask * 32));
+  int per_sm = 1;
+  CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return 1;
+  const int64_t grid = std::min<int64_t>(ncols, (int64_t)c.sm_count * per_sm);
+  kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);
+  c.launches++;
+  return 0;
 }
 
 

@@ -10,6 +10,7 @@
 // The scan over 2^Ns integers + recursive binary_search (ED_SETUP.f90:1044-1061) of the
 // reference is replaced by ranking with two Lin tables: rank(s) = hi[s >> L] + lo[s & (2^L-1)].
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "ctx.h"
@@ -246,6 +247,146 @@ static int64_t binom64(int n, int k) {
     }                                                                              \
   } while (0)
 
+// ------------------------------------------------------------------------------------
+// Conflict-free schedule for the column-resident kernels (see Sched in ctx.h).
+// One group = G consecutive rows.  Its entries are the edges of a bipartite multigraph rows x banks
+// (bank = source row mod G = the shared-memory bank group the gather hits); a proper edge colouring
+// with Delta = max(longest row, busiest bank) colours (Koenig) makes every colour class a step in
+// which the G lanes read G different banks.  Alternating-path recolouring, O(E * G) per group.
+// `natural` skips the colouring (step k = k-th entry of the row) -- kept for comparison runs.
+// ------------------------------------------------------------------------------------
+static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
+                                const std::vector<uint8_t> &code, int G, bool fast, bool natural,
+                                std::vector<int32_t> &task_off, std::vector<int32_t> &task_grp, std::vector<uint32_t> &words) {
+  const int64_t ngroups = (n + G - 1) / G;
+  const int64_t npad = ngroups * G;  // G zero elements follow the column in shared memory: [npad, npad+G)
+  const int esz = G == 8 ? 16 : 8;   // bytes per vector element
+  // word of an entry (source row j, code) / of an idle lane parked on the zero element of bank b.
+  // FAST:    (negative << 31) | (j * esz) | class      -- the address is one AND away
+  // general: (j << 7) | coefficient id                 -- id 0 = 0.0
+  auto mkword = [&](int64_t j, uint32_t cd) -> uint32_t {
+    if (fast) return ((cd & 1u) << 31) | (uint32_t)(j * esz) | ((cd >> 1) & 1u);
+    return ((uint32_t)j << 7) | cd;
+  };
+  auto idle = [&](int b) -> uint32_t { return fast ? (uint32_t)((npad + b) * esz) : ((uint32_t)(npad + b) << 7); };
+  std::vector<std::vector<uint32_t>> steps(ngroups);  // [K_g * G] words of each group
+  std::vector<int32_t> K(ngroups, 0);
+  struct Edge { int r, b, c; uint32_t w; };
+  std::vector<Edge> ed;
+  std::vector<int> at_row, at_bank, path;
+  for (int64_t g = 0; g < ngroups; g++) {
+    const int64_t r0 = g * G;
+    const int nr = (int)std::min<int64_t>(G, n - r0);
+    ed.clear();
+    int deg_r[16] = {0}, deg_b[16] = {0};
+    for (int r = 0; r < nr; r++)
+      for (int32_t p = rowptr[r0 + r]; p < rowptr[r0 + r + 1]; p++) {
+        const int b = col[p] % G;
+        ed.push_back({r, b, natural ? deg_r[r] : -1, mkword(col[p], code[p])});
+        deg_r[r]++; deg_b[b]++;
+      }
+    int delta = 0;
+    for (int x = 0; x < G; x++) delta = std::max(delta, natural ? deg_r[x] : std::max(deg_r[x], deg_b[x]));
+    if (!natural && delta > 0) {
+      at_row.assign((size_t)G * delta, -1);
+      at_bank.assign((size_t)G * delta, -1);
+      for (int e = 0; e < (int)ed.size(); e++) {
+        const int r = ed[e].r, b = ed[e].b;
+        int a = 0, bb = 0;
+        while (at_row[(size_t)r * delta + a] >= 0) a++;
+        while (at_bank[(size_t)b * delta + bb] >= 0) bb++;
+        if (a != bb) {
+          // free colour a at bank b: flip a <-> bb along the alternating path that leaves b with colour a
+          path.clear();
+          int cur = b, want = a;
+          bool at_bank_side = true;
+          for (;;) {
+            const int e2 = at_bank_side ? at_bank[(size_t)cur * delta + want] : at_row[(size_t)cur * delta + want];
+            if (e2 < 0) break;
+            path.push_back(e2);
+            cur = at_bank_side ? ed[e2].r : ed[e2].b;
+            at_bank_side = !at_bank_side;
+            want = want == a ? bb : a;
+          }
+          for (int e2 : path) {
+            at_row[(size_t)ed[e2].r * delta + ed[e2].c] = -1;
+            at_bank[(size_t)ed[e2].b * delta + ed[e2].c] = -1;
+          }
+          for (int e2 : path) {
+            ed[e2].c = ed[e2].c == a ? bb : a;
+            at_row[(size_t)ed[e2].r * delta + ed[e2].c] = e2;
+            at_bank[(size_t)ed[e2].b * delta + ed[e2].c] = e2;
+          }
+        }
+        ed[e].c = a;
+        at_row[(size_t)r * delta + a] = e;
+        at_bank[(size_t)b * delta + a] = e;
+      }
+    }
+    K[g] = delta;
+    // idle lanes of a step are parked on the zero elements of the banks the step leaves free
+    std::vector<int8_t> lane_bank((size_t)delta * G, -1);
+    steps[g].assign((size_t)delta * G, 0u);
+    for (auto &e : ed) { steps[g][(size_t)e.c * G + e.r] = e.w; lane_bank[(size_t)e.c * G + e.r] = (int8_t)e.b; }
+    for (int k = 0; k < delta; k++) {
+      bool used[16] = {false};
+      for (int r = 0; r < G; r++) if (lane_bank[(size_t)k * G + r] >= 0) used[lane_bank[(size_t)k * G + r]] = true;
+      int nb = 0;
+      for (int r = 0; r < G; r++)
+        if (lane_bank[(size_t)k * G + r] < 0) {
+          while (nb < G - 1 && used[nb]) nb++;  // natural order may leave fewer free banks than idle lanes
+          steps[g][(size_t)k * G + r] = idle(nb);
+          used[nb] = true;
+        }
+    }
+  }
+  // warp tasks: groups sorted by step count (descending, stable), 32/G per task
+  const int per = 32 / G;
+  std::vector<int32_t> order(ngroups);
+  for (int64_t g = 0; g < ngroups; g++) order[g] = (int32_t)g;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return K[x] > K[y]; });
+  const int64_t ntask = (ngroups + per - 1) / per;
+  task_off.assign(ntask + 1, 0);
+  task_grp.assign((size_t)ntask * per, -1);
+  for (int64_t t = 0; t < ntask; t++) {
+    int kt = 0;
+    for (int q = 0; q < per; q++) {
+      const int64_t idx = t * per + q;
+      if (idx < ngroups) { task_grp[idx] = order[idx]; kt = std::max(kt, K[order[idx]]); }
+    }
+    kt = (kt + 3) & ~3;  // the kernel fetches four steps per 16-byte load
+    task_off[t + 1] = task_off[t] + kt;
+  }
+  words.assign((size_t)task_off[ntask] * 32, 0u);
+  for (int64_t t = 0; t < ntask; t++) {
+    const int kt = task_off[t + 1] - task_off[t];
+    for (int q = 0; q < per; q++) {
+      const int32_t g = task_grp[(size_t)t * per + q];
+      for (int k = 0; k < kt; k++)
+        for (int r = 0; r < G; r++)
+          // uint4 per lane = 4 consecutive steps: index ((off/4 + k/4)*32 + lane)*4 + k%4
+          words[(((size_t)task_off[t] / 4 + k / 4) * 32 + q * G + r) * 4 + (k & 3)] =
+              (g >= 0 && k < K[g]) ? steps[g][(size_t)k * G + r] : idle(r);
+    }
+  }
+}
+
+static int upload_schedule(Sched &sc, int G, const std::vector<int32_t> &task_off, const std::vector<int32_t> &task_grp,
+                           const std::vector<uint32_t> &words) {
+  Ctx &c = ctx();
+  sc.G = G;
+  sc.ntask = (int32_t)task_off.size() - 1;
+  sc.nsteps = task_off.back();
+  CB_CHECK(dev_alloc(&sc.task_off, (int64_t)task_off.size()));
+  CB_CHECK(dev_alloc(&sc.task_grp, (int64_t)task_grp.size()));
+  CB_CHECK(dev_alloc(&sc.words, (int64_t)words.size()));
+  CB_CUDA(cudaMemcpyAsync(sc.task_off, task_off.data(), task_off.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(sc.task_grp, task_grp.data(), task_grp.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  if (!words.empty()) CB_CUDA(cudaMemcpyAsync(sc.words, words.data(), words.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
                   double const_add, bool want_csr, bool pack_swizzled) {
   Ctx &c = ctx();
@@ -408,6 +549,43 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
       CB_CUDA(cudaMemcpyAsync(op.coef, table.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice, c.stream));
       op.pk_swizzled = pack_swizzled;
       CB_CUDA(cudaStreamSynchronize(c.stream));
+      // schedules of the column-resident kernels (only when a column can live in shared memory)
+      if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 25)) {
+        std::vector<int32_t> hrp(op.n + 1), hcol(op.nnz);
+        CB_CUDA(cudaMemcpy(hrp.data(), op.rowptr, (op.n + 1) * 4, cudaMemcpyDeviceToHost));
+        CB_CUDA(cudaMemcpy(hcol.data(), op.col, op.nnz * 4, cudaMemcpyDeviceToHost));
+        // fast decode: real H with at most two distinct |coefficient| -> code = class<<1 | negative
+        std::vector<double> mags;
+        bool fast = op.real_h;
+        for (int t = 1; t < op.ncoef && fast; t++) {
+          if (table[t].y != 0.0) { fast = false; break; }
+          const double m = std::fabs(table[t].x);
+          if (std::find(mags.begin(), mags.end(), m) == mags.end()) mags.push_back(m);
+          if (mags.size() > 2) fast = false;
+        }
+        std::vector<uint8_t> code(ids);
+        op.sc_fast = fast;
+        if (fast) {
+          op.sc_mag[0] = mags.size() > 0 ? mags[0] : 0.0;
+          op.sc_mag[1] = mags.size() > 1 ? mags[1] : 0.0;
+          for (int64_t k = 0; k < op.nnz; k++) {
+            const double x = table[ids[k]].x;
+            const int cls = (mags.size() > 1 && std::fabs(x) == mags[1]) ? 1 : 0;
+            code[k] = (uint8_t)((cls << 1) | (std::signbit(x) ? 1 : 0));
+          }
+        }
+        std::vector<int32_t> toff, tgrp;
+        std::vector<uint32_t> words;
+        const bool natural = c.opt.sched == 0;
+        if ((size_t)op.n * 16 + 4096 <= 232448) {
+          build_schedule_host(op.n, hrp, hcol, code, 8, fast, natural, toff, tgrp, words);
+          CB_CHECK(upload_schedule(op.sc8, 8, toff, tgrp, words));
+        }
+        if (op.real_h) {
+          build_schedule_host(op.n, hrp, hcol, code, 16, fast, natural, toff, tgrp, words);
+          CB_CHECK(upload_schedule(op.sc16, 16, toff, tgrp, words));
+        }
+      }
       cudaFree(d_ids);
       cudaFree(d_rounds);
     }
@@ -423,6 +601,8 @@ void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
   dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
+  dev_free(op.sc8.task_off); dev_free(op.sc8.task_grp); dev_free(op.sc8.words);
+  dev_free(op.sc16.task_off); dev_free(op.sc16.task_grp); dev_free(op.sc16.words);
   op = SpinOp();
 }
 
@@ -451,6 +631,25 @@ static int sector_np(int32_t isector, int32_t *nup, int32_t *ndw) {
 using namespace cb;
 
 extern "C" {
+
+int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *col, const uint8_t *code, int32_t g,
+                             int32_t natural, int32_t *ntask, int64_t *nsteps, int32_t *task_off, int32_t *task_grp,
+                             uint32_t *words) {
+  if (g != 8 && g != 16) return fail("schedule_host: g must be 8 or 16");
+  if (n <= 0 || n >= (1 << 25)) return fail("schedule_host: n out of range");
+  std::vector<int32_t> rp(rowptr, rowptr + n + 1), cl(col, col + rowptr[n]), toff, tgrp;
+  std::vector<uint8_t> cd(code, code + rowptr[n]);
+  std::vector<uint32_t> w;
+  build_schedule_host(n, rp, cl, cd, g, false, natural != 0, toff, tgrp, w);
+  *ntask = (int32_t)toff.size() - 1;
+  *nsteps = toff.back();
+  if (words) {
+    std::copy(toff.begin(), toff.end(), task_off);
+    std::copy(tgrp.begin(), tgrp.end(), task_grp);
+    std::copy(w.begin(), w.end(), words);
+  }
+  return 0;
+}
 
 int cdmft_b200_get_sector_dims(int32_t isector, int64_t *dimup, int64_t *dimdw, int64_t *dim) {
   int32_t nup, ndw;

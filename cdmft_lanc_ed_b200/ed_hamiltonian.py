@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
     "cdmft_b200_get_csr_nnz", "cdmft_b200_get_csr", "cdmft_b200_get_diag", "cdmft_b200_get_sparse_map",
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
-    "cdmft_b200_add_to_lanczos_gf",
+    "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host",
 ]
 
 
@@ -272,6 +272,26 @@ def hxv(v: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 # inspection
 # --------------------------------------------------------------------------------------
+def schedule_host(rowptr, col, code, g: int = 8, natural: bool = False):
+    """Gather schedule of the column-resident kernel for a CSR pattern (host only, no GPU needed):
+    returns (task_off, task_grp, words[nsteps, 32]) with words[k, lane] = (source row << 7) | code."""
+    L = load_library()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    code = np.ascontiguousarray(code, dtype=np.uint8)
+    n = len(rowptr) - 1
+    ntask, nsteps = C.c_int32(0), C.c_int64(0)
+    args = (C.c_int64(n), _ptr(rowptr), _ptr(col), _ptr(code), C.c_int32(g), C.c_int32(1 if natural else 0))
+    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nsteps), None, None, None))
+    toff = np.zeros(ntask.value + 1, np.int32)
+    tgrp = np.zeros(ntask.value * (32 // g), np.int32)
+    words = np.zeros(nsteps.value * 32, np.uint32)
+    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nsteps), _ptr(toff), _ptr(tgrp), _ptr(words)))
+    # device layout: one uint4 (4 consecutive steps) per lane and step quad -> [step, lane]
+    w = words.reshape(-1, 32, 4).transpose(0, 2, 1).reshape(-1, 32)
+    return toff, tgrp, w
+
+
 def get_sector_map(which: int) -> np.ndarray:
     _, du, dd = getDim(_sector["isector"])
     m = np.empty(du if which == 1 else dd, dtype=np.int32)

@@ -130,6 +130,16 @@ int cdmft_b200_get_diag(int64_t nloc, double *d);
  * ED_SPARSE_MAP.f90:101-121): for imp state k in [0,2^Nimp) entries rowptr[k]..rowptr[k+1]-1 */
 int cdmft_b200_get_sparse_map(int32_t which, int64_t *rowptr, int32_t *bath_state, int32_t *sector_indx);
 
+/* Host-only (no CUDA call): the conflict-free gather schedule the column-resident kernel runs
+ * (k_colres) for a CSR pattern with 0-based ascending columns.  g = 8 (16-byte vector
+ * elements) or 16 (8-byte).  code[nnz] = 7-bit coefficient id per entry.  Sizes: task_off[ntask+1],
+ * task_grp[ntask*(32/g)], words[nsteps*32]; call with words == NULL to get *ntask / *nsteps first.
+ * Word = (source row << 7) | code, idle lanes read one of the g zero elements behind the column
+ * (rows >= ceil(n/g)*g, code 0).  Used by the CPU tests to check the schedule. */
+int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *col, const uint8_t *code,
+                             int32_t g, int32_t natural, int32_t *ntask, int64_t *nsteps,
+                             int32_t *task_off, int32_t *task_grp, uint32_t *words);
+
 /* ---- fused device-resident Krylov drivers (SciFortran SF_SP_LINALG semantics) --------- */
 /* sp_lanc_tridiag(MatVec,vin,alanc,blanc): v0 = local shard of the start vector (host or
  * device; not modified), alanc/blanc host arrays of size nitermax (blanc[0] = 0);
