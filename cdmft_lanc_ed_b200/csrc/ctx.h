@@ -23,10 +23,13 @@ struct Term {  // h(a,b) c^+_a c_b, a != b, 0-based bit positions inside one spi
 // by their number of steps and dealt 32/G to a warp task.
 struct Sched {
   int32_t G = 0, ntask = 0;
-  int64_t nsteps = 0;           // sum of the tasks' step counts (each a multiple of 4)
-  int32_t *task_off = nullptr;  // [ntask+1] first step of each warp task (device)
-  int32_t *task_grp = nullptr;  // [ntask*(32/G)] row group of each lane group, -1 = none (device)
-  uint32_t *words = nullptr;    // [nsteps*32] one uint4 (4 consecutive steps) per lane and step quad; formats in sector.cu
+  int32_t fmt = 0;              // word format: 0 general (table ids), 1 fast 32-bit, 2 fast 16-bit (sector.cu)
+  int32_t nwarps = 0;           // warps per CTA the streams were dealt for (= launch configuration)
+  int64_t nquads = 0;           // quads (4 steps) over all tasks
+  int32_t *tbase = nullptr;     // [nwarps+1] first task of each warp (tasks are numbered warp-major) (device)
+  int32_t *qbase = nullptr;     // [nwarps+1] first quad of each warp's contiguous word stream
+  uint32_t *meta = nullptr;     // [ntask*32] uint4 per task and lane: f_row, row index (-1 none), mu | nquad << 16
+  uint32_t *words = nullptr;    // [(nquads+2)*32] uint4 / uint2 per quad and lane; formats in sector.cu
 };
 
 // Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).

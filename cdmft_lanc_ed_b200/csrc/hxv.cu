@@ -781,7 +781,7 @@ static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double
   int64_t var = ctx().opt.colpass_variant;
   if (var == 6) {
     const int rc = launch_colres<double2>(s, ncols, v, out, dg);
-    if (rc <= 0) return rc;
+    if (rc != kColresNA) return rc;
     var = 1;  // does not apply (DIRECT mode, column larger than shared memory): generic kernel
   }
   if ((var == 4 || var == 5) && ctx().mode == CDMFT_B200_SPARSE && s.pkell && s.nblocks > 0 &&

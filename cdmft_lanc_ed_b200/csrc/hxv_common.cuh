@@ -1,6 +1,7 @@
 // hxv_common.cuh -- device helpers shared by the H x v translation units (hxv.cu, hxv_real.cu)
 #pragma once
 #include <algorithm>
+#include <type_traits>
 
 #include "ctx.h"
 
@@ -101,11 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 struct ColResArgs {
-  const int32_t *task_off, *task_grp;
+  const int32_t *tbase, *qbase;  // [nwarps+1]
+  const uint4 *meta;             // [ntask*32]
   const uint32_t *words;
-  int ntask;
-  const double2 *coef;  // [128] (general decode)
-  double m0, m1;        // FAST decode
+  const double2 *coef;  // [128] (table decode)
+  double m0, m1;        // fast decode
 };
 
 __device__ __forceinline__ void colres_fma(double2 &acc, double h, double2 x) { rfma(acc, h, x); }
@@ -117,22 +118,35 @@ __device__ __forceinline__ void colres_zero(double &a) { a = 0.0; }
 __device__ __forceinline__ double2 colres_scale(double d, double2 x) { return make_double2(d * x.x, d * x.y); }
 __device__ __forceinline__ double colres_scale(double d, double x) { return d * x; }
 
-template <typename T, bool REALH, bool FAST>
+// decode modes: 0 = coefficient table, complex values; 1 = coefficient table, real values;
+// 2 = fast 32-bit words; 3 = fast 16-bit words (formats in sector.cu, build_schedule_host)
+__device__ __forceinline__ double colres_signed(double m, uint32_t signbit31) {
+  return __hiloint2double(__double2hiint(m) ^ (int)signbit31, __double2loint(m));
+}
+template <typename T, int MODE>
 __device__ __forceinline__ void colres_step(T &acc, uint32_t w, const char *xs, const char *coef_b, double m0, double m1) {
-  if (FAST) {
+  if (MODE == 2) {
     // w = (negative << 31) | byte offset | class : branch-free, idle lanes read a zero element
     const T x = *(const T *)(xs + (w & 0x7FFFFFF8u & ~(uint32_t)(sizeof(T) - 1)));
-    const double m = (w & 1u) ? m1 : m0;
-    const double h = __hiloint2double(__double2hiint(m) ^ (int)(w & 0x80000000u), __double2loint(m));
-    colres_fma(acc, h, x);
+    colres_fma(acc, colres_signed((w & 1u) ? m1 : m0, w & 0x80000000u), x);
   } else {
     const T x = *(const T *)(xs + (size_t)(w >> 7) * sizeof(T));
-    if (REALH) colres_fma(acc, *(const double *)(coef_b + ((w & 127u) << 4)), x);
+    if (MODE == 1) colres_fma(acc, *(const double *)(coef_b + ((w & 127u) << 4)), x);
     else colres_cfma(acc, *(const double2 *)(coef_b + ((w & 127u) << 4)), x);
   }
 }
+// two 16-bit words (negative << 15 | class << 14 | source row) in one register
+template <typename T>
+__device__ __forceinline__ void colres_step16x2(T &acc, uint32_t w, const char *xs, double m0, double m1) {
+  constexpr int SH = sizeof(T) == 16 ? 4 : 3;
+  constexpr uint32_t AM = 0x3FFFu << SH;
+  const T x0 = *(const T *)(xs + ((w << SH) & AM));
+  const T x1 = *(const T *)(xs + ((w >> (16 - SH)) & AM));
+  colres_fma(acc, colres_signed((w & 0x4000u) ? m1 : m0, (w << 16) & 0x80000000u), x0);
+  colres_fma(acc, colres_signed((w & 0x40000000u) ? m1 : m0, w & 0x80000000u), x1);
+}
 
-template <typename T, bool REALH, bool FAST>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, const T *__restrict__ v, T *__restrict__ out,
                                                      ColResArgs a, DiagArgs dg) {
   constexpr int G = sizeof(T) == 16 ? 8 : 16;
@@ -143,11 +157,17 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
   double *dtab = (double *)(smem_raw + 128 + 2048);
   const int ndt = dg.enabled ? (1 << dg.nimp) : 0;
   T *xs = (T *)(smem_raw + 128 + 2048 + (((size_t)ndt * 8 + 127) & ~(size_t)127));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t npad = (n + G - 1) / G * G;
   if (threadIdx.x == 0) mbar_init(bar, 1);
-  if (threadIdx.x < 128) coef[threadIdx.x] = FAST ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
+  if (threadIdx.x < 128) coef[threadIdx.x] = MODE >= 2 ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
   for (int64_t k = n + threadIdx.x; k < npad + G; k += blockDim.x) colres_zero(xs[k]);  // idle lanes gather these
+  // this warp's stream: tasks [t0,t1) and the quads from q0 on (the same for every column)
+  const int t0 = __ldg(a.tbase + warp), t1 = __ldg(a.tbase + warp + 1);
+  const int64_t q0 = __ldg(a.qbase + warp);
+  const uint4 *mp = a.meta + (int64_t)t0 * 32 + lane;
+  using WQ = typename std::conditional<MODE == 3, uint2, uint4>::type;  // one quad (4 steps) of a lane
+  const WQ *wbase = (const WQ *)a.words + q0 * 32 + lane;
   __syncthreads();
   const uint32_t bytes = (uint32_t)(n * sizeof(T));
   const char *xs_b = (const char *)xs;
@@ -170,32 +190,40 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
       }
       dtab[mu] = val;
     }
+    // operator stream: nothing of it depends on the column, so the first loads fly while the column arrives
+    const WQ *wp = wbase;
+    WQ wa = __ldg(wp), wb = __ldg(wp + 32);  // two quads of slack behind every stream
+    uint4 m = t0 < t1 ? __ldg(mp) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
     mbar_wait(bar, phase);
     phase ^= 1u;
     __syncthreads();
     T *oc = out + c * n;
-    for (int task = warp; task < a.ntask; task += nwarps) {
-      const int grp = __ldg(a.task_grp + task * (32 / G) + lane / G);
-      const int64_t i = (int64_t)grp * G + (lane & (G - 1));
-      const bool valid = grp >= 0 && i < n;
-      const int k0 = __ldg(a.task_off + task), nquad = (__ldg(a.task_off + task + 1) - k0) >> 2;
-      const uint4 *wp = (const uint4 *)a.words + (int64_t)(k0 >> 2) * 32 + lane;
-      uint4 wn = nquad > 0 ? __ldg(wp) : make_uint4(0u, 0u, 0u, 0u);
+    for (int t = t0; t < t1; t++) {
+      uint4 mnext = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+      if (t + 1 < t1) mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
+      const int nquad = (int)(m.w >> 16);
+      const bool valid = m.z != 0xFFFFFFFFu;
       T acc;
       colres_zero(acc);
-      if (dg.enabled && valid) {
-        const uint32_t mu = (uint32_t)__ldg(dg.map_row + i) & ((1u << dg.nimp) - 1u);
-        acc = colres_scale(__ldg(dg.f_row + i) + dtab[mu], xs[i]);
-      }
+      if (dg.enabled && valid)
+        acc = colres_scale(__hiloint2double((int)m.y, (int)m.x) + dtab[m.w & 0xFFFFu], xs[m.z]);
       for (int kq = 0; kq < nquad; kq++) {
-        const uint4 w = wn;
-        if (kq + 1 < nquad) wn = __ldg(wp + (int64_t)(kq + 1) * 32);
-        colres_step<T, REALH, FAST>(acc, w.x, xs_b, coef_b, a.m0, a.m1);
-        colres_step<T, REALH, FAST>(acc, w.y, xs_b, coef_b, a.m0, a.m1);
-        colres_step<T, REALH, FAST>(acc, w.z, xs_b, coef_b, a.m0, a.m1);
-        colres_step<T, REALH, FAST>(acc, w.w, xs_b, coef_b, a.m0, a.m1);
+        const WQ w = wa;
+        wa = wb;
+        wp += 32;
+        wb = __ldg(wp + 32);
+        if constexpr (MODE == 3) {
+          colres_step16x2<T>(acc, w.x, xs_b, a.m0, a.m1);
+          colres_step16x2<T>(acc, w.y, xs_b, a.m0, a.m1);
+        } else {
+          colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1);
+          colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1);
+          colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1);
+          colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1);
+        }
       }
-      if (valid) oc[i] = acc;
+      if (valid) oc[m.z] = acc;
+      m = mnext;
     }
     __syncthreads();  // every gather of this column is done before the next bulk copy lands
   }
@@ -207,25 +235,28 @@ inline size_t colres_smem(int64_t n, int elem, int nimp_diag) {
   return 128 + 2048 + ((ndt * 8 + 127) & ~(size_t)127) + ((size_t)n + 32) * elem;  // + padding and zero elements
 }
 
-// launch on the context's stream; returns 1 when the kernel does not apply (caller falls back)
+// launch on the context's stream; returns kColresNA when the kernel does not apply (the caller then uses the
+// generic kernel), 0 on success, the usual non-zero rc on a CUDA error
+constexpr int kColresNA = -7;
 template <typename T>
 inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg) {
   Ctx &c = ctx();
   const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
-  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return 1;
-  if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return 1;  // bulk copies need 16-byte aligned columns
+  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return kColresNA;
+  if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return kColresNA;  // bulk copies need 16-byte aligned columns
   const size_t smem = colres_smem(s.n, (int)sizeof(T), dg.enabled ? dg.nimp : -1);
-  if (smem > 232448) return 1;
+  if (smem > 232448) return kColresNA;
+  if (dg.enabled && dg.f_row != s.f) return kColresNA;  // the schedule carries the operator's own row diagonal
   ColResArgs a{};
-  a.task_off = sc.task_off; a.task_grp = sc.task_grp; a.words = sc.words; a.ntask = sc.ntask;
+  a.tbase = sc.tbase; a.qbase = sc.qbase; a.meta = (const uint4 *)sc.meta; a.words = sc.words;
   a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
   void (*kern)(int64_t, int64_t, const T *, T *, ColResArgs, DiagArgs) =
-      s.sc_fast ? k_colres<T, true, true> : (c.real_h ? k_colres<T, true, false> : k_colres<T, false, false>);
+      sc.fmt == 2 ? k_colres<T, 3> : (sc.fmt == 1 ? k_colres<T, 2> : (c.real_h ? k_colres<T, 1> : k_colres<T, 0>));
   CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(128, (int64_t)sc.ntask * 32));
+  const int threads = sc.nwarps * 32;  // the streams were dealt for exactly this many warps
   int per_sm = 1;
   CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) return 1;
+  if (per_sm < 1) return kColresNA;
   const int64_t grid = std::min<int64_t>(ncols, (int64_t)c.sm_count * per_sm);
   kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);
   c.launches++;

@@ -106,9 +106,12 @@ int hxv_device_real(const double *v, double *hv) {
     dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((c.dimdw + 3) / 4));
     if (grid.y > 65535) return fail("colpass_r: too many column groups");
     prof_begin(0);
-    if (direct) k_colpass_r<true, 4><<<grid, 256, 0, c.stream>>>(s.n, c.dimdw, v, hv, op_args(s), diag_args(0));
+    const int rc = c.opt.colpass_variant == 6 ? launch_colres<double>(s, c.dimdw, v, hv, diag_args(0)) : kColresNA;
+    if (rc != 0 && rc != kColresNA) { prof_end(); return rc; }
+    if (rc == 0) {}  // column-resident kernel launched
+    else if (direct) k_colpass_r<true, 4><<<grid, 256, 0, c.stream>>>(s.n, c.dimdw, v, hv, op_args(s), diag_args(0));
     else k_colpass_r<false, 4><<<grid, 256, 0, c.stream>>>(s.n, c.dimdw, v, hv, op_args(s), diag_args(0));
-    c.launches++;
+    if (rc != 0) c.launches++;
     prof_end();
   }
   {

@@ -11,6 +11,7 @@
 // reference is replaced by ranking with two Lin tables: rank(s) = hi[s >> L] + lo[s & (2^L-1)].
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "ctx.h"
@@ -255,20 +256,35 @@ static int64_t binom64(int n, int k) {
 // which the G lanes read G different banks.  Alternating-path recolouring, O(E * G) per group.
 // `natural` skips the colouring (step k = k-th entry of the row) -- kept for comparison runs.
 // ------------------------------------------------------------------------------------
+struct SchedHost {
+  int G = 0, fmt = 0, nwarps = 0;
+  int32_t ntask = 0;
+  int64_t nquads = 0;
+  std::vector<int32_t> tbase, qbase;  // [nwarps+1] first task / first quad of each warp's stream
+  std::vector<uint32_t> meta;         // [ntask*32] uint4 per task and lane: f_row (8 B), row (-1 = none), mu | nquad << 16
+  std::vector<uint32_t> words;        // [(nquads+2)*32] uint4 (fmt 0,1) or uint2 (fmt 2) per quad and lane
+};
+
 static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
-                                const std::vector<uint8_t> &code, int G, bool fast, bool natural,
-                                std::vector<int32_t> &task_off, std::vector<int32_t> &task_grp, std::vector<uint32_t> &words) {
+                                const std::vector<uint8_t> &code, int G, int fmt, bool natural, int nwarps,
+                                const double *f_row, const uint32_t *mu_row, SchedHost &out) {
+  const bool fast = fmt != 0, w16 = fmt == 2;
   const int64_t ngroups = (n + G - 1) / G;
   const int64_t npad = ngroups * G;  // G zero elements follow the column in shared memory: [npad, npad+G)
   const int esz = G == 8 ? 16 : 8;   // bytes per vector element
   // word of an entry (source row j, code) / of an idle lane parked on the zero element of bank b.
-  // FAST:    (negative << 31) | (j * esz) | class      -- the address is one AND away
-  // general: (j << 7) | coefficient id                 -- id 0 = 0.0
+  // fmt 0 (general): (j << 7) | coefficient id, id 0 = 0.0       four steps per uint4
+  // fmt 1 (fast32):  (negative << 31) | (j * esz) | class         four steps per uint4, address one AND away
+  // fmt 2 (fast16):  (negative << 15) | (class << 14) | j         two steps per uint32 (needs npad+G <= 2^14)
   auto mkword = [&](int64_t j, uint32_t cd) -> uint32_t {
+    if (w16) return ((cd & 1u) << 15) | (((cd >> 1) & 1u) << 14) | (uint32_t)j;
     if (fast) return ((cd & 1u) << 31) | (uint32_t)(j * esz) | ((cd >> 1) & 1u);
     return ((uint32_t)j << 7) | cd;
   };
-  auto idle = [&](int b) -> uint32_t { return fast ? (uint32_t)((npad + b) * esz) : ((uint32_t)(npad + b) << 7); };
+  auto idle = [&](int b) -> uint32_t {
+    if (w16) return (uint32_t)(npad + b);
+    return fast ? (uint32_t)((npad + b) * esz) : ((uint32_t)(npad + b) << 7);
+  };
   std::vector<std::vector<uint32_t>> steps(ngroups);  // [K_g * G] words of each group
   std::vector<int32_t> K(ngroups, 0);
   struct Edge { int r, b, c; uint32_t w; };
@@ -340,49 +356,75 @@ static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, c
         }
     }
   }
-  // warp tasks: groups sorted by step count (descending, stable), 32/G per task
+  // warp tasks: groups sorted by step count (descending, stable), 32/G per task; tasks dealt round-robin to
+  // the nwarps warps of the CTA and stored warp-major, so that a warp's words form one contiguous stream
   const int per = 32 / G;
   std::vector<int32_t> order(ngroups);
   for (int64_t g = 0; g < ngroups; g++) order[g] = (int32_t)g;
   std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return K[x] > K[y]; });
   const int64_t ntask = (ngroups + per - 1) / per;
-  task_off.assign(ntask + 1, 0);
-  task_grp.assign((size_t)ntask * per, -1);
+  out.G = G; out.fmt = fmt; out.nwarps = nwarps; out.ntask = (int32_t)ntask;
+  out.tbase.assign(nwarps + 1, 0);
+  out.qbase.assign(nwarps + 1, 0);
+  out.meta.assign((size_t)ntask * 32 * 4, 0u);
+  std::vector<int64_t> sorted_of_task(ntask);  // warp-major task -> index in the sorted list
+  {
+    int64_t t = 0;
+    for (int w = 0; w < nwarps; w++) {
+      out.tbase[w] = (int32_t)t;
+      for (int64_t st = w; st < ntask; st += nwarps) sorted_of_task[t++] = st;
+    }
+    out.tbase[nwarps] = (int32_t)t;
+  }
+  std::vector<int32_t> qoff(ntask + 1, 0);
   for (int64_t t = 0; t < ntask; t++) {
     int kt = 0;
     for (int q = 0; q < per; q++) {
-      const int64_t idx = t * per + q;
-      if (idx < ngroups) { task_grp[idx] = order[idx]; kt = std::max(kt, K[order[idx]]); }
+      const int64_t idx = sorted_of_task[t] * per + q;
+      if (idx < ngroups) kt = std::max(kt, K[order[idx]]);
     }
-    kt = (kt + 3) & ~3;  // the kernel fetches four steps per 16-byte load
-    task_off[t + 1] = task_off[t] + kt;
+    qoff[t + 1] = qoff[t] + (kt + 3) / 4;  // four steps per load (uint4 of 32-bit words / uint2 of 16-bit words)
   }
-  words.assign((size_t)task_off[ntask] * 32, 0u);
+  for (int w = 0; w <= nwarps; w++) out.qbase[w] = qoff[out.tbase[w]];
+  out.nquads = qoff[ntask];
+  const size_t wpq = w16 ? 2 : 4;  // 32-bit registers per lane and quad
+  out.words.assign(((size_t)out.nquads + 2) * 32 * wpq, 0u);  // two quads of slack: the prefetch runs ahead unguarded
   for (int64_t t = 0; t < ntask; t++) {
-    const int kt = task_off[t + 1] - task_off[t];
+    const int nq = qoff[t + 1] - qoff[t];
     for (int q = 0; q < per; q++) {
-      const int32_t g = task_grp[(size_t)t * per + q];
-      for (int k = 0; k < kt; k++)
-        for (int r = 0; r < G; r++)
-          // uint4 per lane = 4 consecutive steps: index ((off/4 + k/4)*32 + lane)*4 + k%4
-          words[(((size_t)task_off[t] / 4 + k / 4) * 32 + q * G + r) * 4 + (k & 3)] =
-              (g >= 0 && k < K[g]) ? steps[g][(size_t)k * G + r] : idle(r);
+      const int64_t idx = sorted_of_task[t] * per + q;
+      const int32_t g = idx < ngroups ? order[idx] : -1;
+      for (int r = 0; r < G; r++) {
+        const int lane = q * G + r;
+        const int64_t i = g >= 0 ? (int64_t)g * G + r : -1;
+        uint32_t *m = &out.meta[((size_t)t * 32 + lane) * 4];
+        const bool valid = i >= 0 && i < n;
+        double f = valid && f_row ? f_row[i] : 0.0;
+        memcpy(m, &f, 8);
+        m[2] = valid ? (uint32_t)i : 0xFFFFFFFFu;
+        m[3] = (valid && mu_row ? (mu_row[i] & 0xFFFFu) : 0u) | ((uint32_t)nq << 16);
+        for (int k = 0; k < nq * 4; k++) {
+          const uint32_t w = (g >= 0 && k < K[g]) ? steps[g][(size_t)k * G + r] : idle(r);
+          const size_t base = (((size_t)qoff[t] + k / 4) * 32 + lane) * wpq;
+          if (w16) out.words[base + (k & 3) / 2] |= w << ((k & 1) * 16);
+          else out.words[base + (k & 3)] = w;
+        }
+      }
     }
   }
 }
 
-static int upload_schedule(Sched &sc, int G, const std::vector<int32_t> &task_off, const std::vector<int32_t> &task_grp,
-                           const std::vector<uint32_t> &words) {
+static int upload_schedule(Sched &sc, const SchedHost &h) {
   Ctx &c = ctx();
-  sc.G = G;
-  sc.ntask = (int32_t)task_off.size() - 1;
-  sc.nsteps = task_off.back();
-  CB_CHECK(dev_alloc(&sc.task_off, (int64_t)task_off.size()));
-  CB_CHECK(dev_alloc(&sc.task_grp, (int64_t)task_grp.size()));
-  CB_CHECK(dev_alloc(&sc.words, (int64_t)words.size()));
-  CB_CUDA(cudaMemcpyAsync(sc.task_off, task_off.data(), task_off.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(sc.task_grp, task_grp.data(), task_grp.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  if (!words.empty()) CB_CUDA(cudaMemcpyAsync(sc.words, words.data(), words.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  sc.G = h.G; sc.fmt = h.fmt; sc.nwarps = h.nwarps; sc.ntask = h.ntask; sc.nquads = h.nquads;
+  CB_CHECK(dev_alloc(&sc.tbase, (int64_t)h.tbase.size()));
+  CB_CHECK(dev_alloc(&sc.qbase, (int64_t)h.qbase.size()));
+  CB_CHECK(dev_alloc(&sc.meta, (int64_t)h.meta.size()));
+  CB_CHECK(dev_alloc(&sc.words, (int64_t)h.words.size()));
+  CB_CUDA(cudaMemcpyAsync(sc.tbase, h.tbase.data(), h.tbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(sc.qbase, h.qbase.data(), h.qbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  if (!h.meta.empty()) CB_CUDA(cudaMemcpyAsync(sc.meta, h.meta.data(), h.meta.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(sc.words, h.words.data(), h.words.size() * 4, cudaMemcpyHostToDevice, c.stream));
   CB_CUDA(cudaStreamSynchronize(c.stream));
   return 0;
 }
@@ -574,16 +616,25 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
             code[k] = (uint8_t)((cls << 1) | (std::signbit(x) ? 1 : 0));
           }
         }
-        std::vector<int32_t> toff, tgrp;
-        std::vector<uint32_t> words;
         const bool natural = c.opt.sched == 0;
+        const int fmt = !fast ? 0 : (op.n + 32 <= (1 << 14) ? 2 : 1);
+        // per-row part of the diagonal and the row's impurity configuration travel with the schedule
+        std::vector<double> hf(op.n);
+        std::vector<int32_t> hmap(op.n);
+        std::vector<uint32_t> hmu(op.n);
+        CB_CUDA(cudaMemcpy(hf.data(), op.f, op.n * 8, cudaMemcpyDeviceToHost));
+        CB_CUDA(cudaMemcpy(hmap.data(), op.map, op.n * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < op.n; i++) hmu[i] = (uint32_t)hmap[i] & ((1u << c.nimp) - 1u);
+        SchedHost sh;
         if ((size_t)op.n * 16 + 4096 <= 232448) {
-          build_schedule_host(op.n, hrp, hcol, code, 8, fast, natural, toff, tgrp, words);
-          CB_CHECK(upload_schedule(op.sc8, 8, toff, tgrp, words));
+          build_schedule_host(op.n, hrp, hcol, code, 8, fmt, natural, 32, hf.data(), hmu.data(), sh);
+          CB_CHECK(upload_schedule(op.sc8, sh));
         }
         if (op.real_h) {
-          build_schedule_host(op.n, hrp, hcol, code, 16, fast, natural, toff, tgrp, words);
-          CB_CHECK(upload_schedule(op.sc16, 16, toff, tgrp, words));
+          // 8-byte elements: two 512-thread CTAs per SM when two columns fit, else one of 1024
+          const int nw = (size_t)op.n * 8 * 2 + 8192 <= 232448 ? 16 : 32;
+          build_schedule_host(op.n, hrp, hcol, code, 16, fmt, natural, nw, hf.data(), hmu.data(), sh);
+          CB_CHECK(upload_schedule(op.sc16, sh));
         }
       }
       cudaFree(d_ids);
@@ -601,8 +652,7 @@ void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
   dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
-  dev_free(op.sc8.task_off); dev_free(op.sc8.task_grp); dev_free(op.sc8.words);
-  dev_free(op.sc16.task_off); dev_free(op.sc16.task_grp); dev_free(op.sc16.words);
+  for (Sched *sc : {&op.sc8, &op.sc16}) { dev_free(sc->tbase); dev_free(sc->qbase); dev_free(sc->meta); dev_free(sc->words); }
   op = SpinOp();
 }
 
@@ -633,20 +683,22 @@ using namespace cb;
 extern "C" {
 
 int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *col, const uint8_t *code, int32_t g,
-                             int32_t natural, int32_t *ntask, int64_t *nsteps, int32_t *task_off, int32_t *task_grp,
-                             uint32_t *words) {
+                             int32_t natural, int32_t nwarps, int32_t *ntask, int64_t *nquads, int32_t *tbase,
+                             int32_t *qbase, uint32_t *meta, uint32_t *words) {
   if (g != 8 && g != 16) return fail("schedule_host: g must be 8 or 16");
   if (n <= 0 || n >= (1 << 25)) return fail("schedule_host: n out of range");
-  std::vector<int32_t> rp(rowptr, rowptr + n + 1), cl(col, col + rowptr[n]), toff, tgrp;
+  if (nwarps < 1 || nwarps > 32) return fail("schedule_host: nwarps must be in [1,32]");
+  std::vector<int32_t> rp(rowptr, rowptr + n + 1), cl(col, col + rowptr[n]);
   std::vector<uint8_t> cd(code, code + rowptr[n]);
-  std::vector<uint32_t> w;
-  build_schedule_host(n, rp, cl, cd, g, false, natural != 0, toff, tgrp, w);
-  *ntask = (int32_t)toff.size() - 1;
-  *nsteps = toff.back();
+  SchedHost sh;
+  build_schedule_host(n, rp, cl, cd, g, 0, natural != 0, nwarps, nullptr, nullptr, sh);
+  *ntask = sh.ntask;
+  *nquads = sh.nquads;
   if (words) {
-    std::copy(toff.begin(), toff.end(), task_off);
-    std::copy(tgrp.begin(), tgrp.end(), task_grp);
-    std::copy(w.begin(), w.end(), words);
+    std::copy(sh.tbase.begin(), sh.tbase.end(), tbase);
+    std::copy(sh.qbase.begin(), sh.qbase.end(), qbase);
+    std::copy(sh.meta.begin(), sh.meta.end(), meta);
+    std::copy(sh.words.begin(), sh.words.begin() + (size_t)sh.nquads * 32 * 4, words);
   }
   return 0;
 }

@@ -272,24 +272,39 @@ def hxv(v: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 # inspection
 # --------------------------------------------------------------------------------------
-def schedule_host(rowptr, col, code, g: int = 8, natural: bool = False):
-    """Gather schedule of the column-resident kernel for a CSR pattern (host only, no GPU needed):
-    returns (task_off, task_grp, words[nsteps, 32]) with words[k, lane] = (source row << 7) | code."""
+def schedule_host(rowptr, col, code, g: int = 8, natural: bool = False, nwarps: int = 32):
+    """Gather schedule of the column-resident kernel for a CSR pattern (host only, no GPU needed).
+    Returns a list over warps of lists of tasks; a task = (rows[32] (-1 = no row), words[nsteps, 32]) with
+    words[k, lane] = (source row << 7) | code, in the order the warp executes them."""
     L = load_library()
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
     col = np.ascontiguousarray(col, dtype=np.int32)
     code = np.ascontiguousarray(code, dtype=np.uint8)
     n = len(rowptr) - 1
-    ntask, nsteps = C.c_int32(0), C.c_int64(0)
-    args = (C.c_int64(n), _ptr(rowptr), _ptr(col), _ptr(code), C.c_int32(g), C.c_int32(1 if natural else 0))
-    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nsteps), None, None, None))
-    toff = np.zeros(ntask.value + 1, np.int32)
-    tgrp = np.zeros(ntask.value * (32 // g), np.int32)
-    words = np.zeros(nsteps.value * 32, np.uint32)
-    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nsteps), _ptr(toff), _ptr(tgrp), _ptr(words)))
-    # device layout: one uint4 (4 consecutive steps) per lane and step quad -> [step, lane]
-    w = words.reshape(-1, 32, 4).transpose(0, 2, 1).reshape(-1, 32)
-    return toff, tgrp, w
+    ntask, nquads = C.c_int32(0), C.c_int64(0)
+    args = (C.c_int64(n), _ptr(rowptr), _ptr(col), _ptr(code), C.c_int32(g), C.c_int32(1 if natural else 0), C.c_int32(nwarps))
+    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nquads), None, None, None, None))
+    tbase = np.zeros(nwarps + 1, np.int32)
+    qbase = np.zeros(nwarps + 1, np.int32)
+    meta = np.zeros(ntask.value * 32 * 4, np.uint32)
+    words = np.zeros(nquads.value * 32 * 4, np.uint32)
+    _chk(L.cdmft_b200_schedule_host(*args, C.byref(ntask), C.byref(nquads), _ptr(tbase), _ptr(qbase), _ptr(meta), _ptr(words)))
+    meta = meta.reshape(-1, 32, 4)
+    words = words.reshape(-1, 32, 4)  # [quad, lane, step in quad]
+    out = []
+    for w in range(nwarps):
+        q = int(qbase[w])
+        tasks = []
+        for t in range(tbase[w], tbase[w + 1]):
+            nq = int(meta[t, 0, 3] >> 16)
+            assert (meta[t, :, 3] >> 16 == nq).all()
+            rows = meta[t, :, 2].astype(np.int64)
+            rows[rows == 0xFFFFFFFF] = -1
+            tasks.append((rows, words[q:q + nq].transpose(0, 2, 1).reshape(nq * 4, 32)))
+            q += nq
+        assert q == qbase[w + 1]
+        out.append(tasks)
+    return out
 
 
 def get_sector_map(which: int) -> np.ndarray:

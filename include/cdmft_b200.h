@@ -132,13 +132,15 @@ int cdmft_b200_get_sparse_map(int32_t which, int64_t *rowptr, int32_t *bath_stat
 
 /* Host-only (no CUDA call): the conflict-free gather schedule the column-resident kernel runs
  * (k_colres) for a CSR pattern with 0-based ascending columns.  g = 8 (16-byte vector
- * elements) or 16 (8-byte).  code[nnz] = 7-bit coefficient id per entry.  Sizes: task_off[ntask+1],
- * task_grp[ntask*(32/g)], words[nsteps*32]; call with words == NULL to get *ntask / *nsteps first.
- * Word = (source row << 7) | code, idle lanes read one of the g zero elements behind the column
- * (rows >= ceil(n/g)*g, code 0).  Used by the CPU tests to check the schedule. */
+ * elements) or 16 (8-byte); nwarps = warps per CTA the tasks are dealt to.  code[nnz] = 7-bit coefficient id.
+ * Tasks are numbered warp-major: warp w owns tasks tbase[w]..tbase[w+1]-1 and the quads (4 steps x 32 lanes)
+ * from qbase[w] on, task after task.  meta[ntask*32*4]: per task and lane {f_row (2 words, 0 here), row index
+ * (0xFFFFFFFF = none), mu | nquad << 16}; words[nquads*32*4]: per quad and lane 4 words (source row << 7) | code;
+ * idle lanes read one of the g zero elements behind the column (rows >= ceil(n/g)*g, code 0).
+ * Call with words == NULL to get *ntask / *nquads first.  Used by the CPU tests to check the schedule. */
 int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *col, const uint8_t *code,
-                             int32_t g, int32_t natural, int32_t *ntask, int64_t *nsteps,
-                             int32_t *task_off, int32_t *task_grp, uint32_t *words);
+                             int32_t g, int32_t natural, int32_t nwarps, int32_t *ntask, int64_t *nquads,
+                             int32_t *tbase, int32_t *qbase, uint32_t *meta, uint32_t *words);
 
 /* ---- fused device-resident Krylov drivers (SciFortran SF_SP_LINALG semantics) --------- */
 /* sp_lanc_tridiag(MatVec,vin,alanc,blanc): v0 = local shard of the start vector (host or

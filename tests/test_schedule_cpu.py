@@ -1,6 +1,7 @@
 """CPU checks of the gather schedule the column-resident kernel (k_colres) executes: built on the host by
 cdmft_b200_schedule_host from a CSR pattern, so it can be verified without a GPU.
-  * every CSR entry (row, col, code) appears exactly once, in the lane that owns the row;
+  * every row is owned by exactly one lane of one warp task, every CSR entry (row, col, code) appears exactly
+    once, in that lane;
   * edge colouring: inside one shared-memory phase (g consecutive lanes) the g gathers of a step hit g
     different banks (bank = source row mod g), idle lanes included (they read distinct zero elements);
   * the number of steps of a group is max(longest row, busiest bank) -- Koenig's bound is reached.
@@ -14,45 +15,47 @@ from cdmft_lanc_ed_b200 import models
 from oracle import edo
 
 
-def _check(rowptr, col, code, g, natural=False):
+def _check(rowptr, col, code, g, natural=False, nwarps=32):
     n = len(rowptr) - 1
-    toff, tgrp, w = E.schedule_host(rowptr, col, code, g, natural)
+    sched = E.schedule_host(rowptr, col, code, g, natural, nwarps)
     per = 32 // g
     ngroups = (n + g - 1) // g
     npad = ngroups * g
-    assert sorted(x for x in tgrp if x >= 0) == list(range(ngroups))
     seen = [[] for _ in range(n)]
-    for t in range(len(toff) - 1):
-        assert (toff[t + 1] - toff[t]) % 4 == 0
-        for q in range(per):
-            grp = tgrp[t * per + q]
-            blk = w[toff[t]:toff[t + 1], q * g:(q + 1) * g]
-            src = (blk >> 7).astype(np.int64)
-            cd = blk & 127
-            if not natural:  # conflict-free: g different banks in every step of every phase
-                banks = src % g
-                assert all(len(set(row)) == g for row in banks), (t, q)
-            idle = src >= n
-            assert (src[idle] >= npad).all() and (src[idle] < npad + g).all() and (cd[idle] == 0).all()
-            if grp < 0:
-                assert idle.all()
-                continue
-            for k, r in zip(*np.nonzero(~idle)):
-                i = grp * g + r
-                assert i < n
-                seen[i].append((int(src[k, r]), int(cd[k, r])))
-            if not natural:  # Koenig bound: steps actually used = max degree of the rows x banks multigraph
-                rows = range(grp * g, min(n, grp * g + g))
-                deg_r = max((rowptr[i + 1] - rowptr[i] for i in rows), default=0)
-                bl = np.zeros(g, int)
-                for i in rows:
-                    bl += np.bincount(col[rowptr[i]:rowptr[i + 1]] % g, minlength=g)
-                used = int((~idle).any(axis=1).sum())
-                assert used == max(deg_r, bl.max())
+    owned = np.zeros(n, int)
+    nsteps = 0
+    assert len(sched) == nwarps
+    for tasks in sched:
+        for rows, w in tasks:
+            nsteps += len(w)
+            for q in range(per):
+                r8 = rows[q * g:(q + 1) * g]
+                blk = w[:, q * g:(q + 1) * g]
+                src = (blk >> 7).astype(np.int64)
+                cd = blk & 127
+                if not natural:  # conflict-free: g different banks in every step of every phase
+                    banks = src % g
+                    assert all(len(set(row)) == g for row in banks)
+                idle = src >= n
+                assert (src[idle] >= npad).all() and (src[idle] < npad + g).all() and (cd[idle] == 0).all()
+                live = r8[r8 >= 0]
+                owned[live] += 1
+                if len(live):  # a lane group owns g consecutive rows (one 128-byte line of the output)
+                    assert live[0] % g == 0 and (np.diff(live) == 1).all()
+                assert idle[:, r8 < 0].all()
+                for k, r in zip(*np.nonzero(~idle)):
+                    seen[r8[r]].append((int(src[k, r]), int(cd[k, r])))
+                if not natural and len(live):  # Koenig bound: steps used = max degree of the rows x banks multigraph
+                    deg_r = max(rowptr[i + 1] - rowptr[i] for i in live)
+                    bl = np.zeros(g, int)
+                    for i in live:
+                        bl += np.bincount(col[rowptr[i]:rowptr[i + 1]] % g, minlength=g)
+                    assert int((~idle).any(axis=1).sum()) == max(deg_r, bl.max())
+    assert (owned == 1).all()
     for i in range(n):
         want = sorted(zip(col[rowptr[i]:rowptr[i + 1]].tolist(), code[rowptr[i]:rowptr[i + 1]].tolist()))
         assert sorted(seen[i]) == want, i
-    return toff[-1]
+    return nsteps
 
 
 @pytest.mark.parametrize("g", [8, 16])
@@ -87,3 +90,5 @@ def test_schedule_of_ragged_random_patterns(n, g):
     rowptr = np.concatenate([[0], np.cumsum([min(l, n) for l in lens])])
     code = rng.integers(1, 128, size=len(col)).astype(np.uint8)
     _check(rowptr, col.astype(np.int64), code, g)
+    _check(rowptr, col.astype(np.int64), code, g, nwarps=16)
+    _check(rowptr, col.astype(np.int64), code, g, nwarps=3)
