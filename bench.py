@@ -326,16 +326,27 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks and "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     prof = _load_json(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) or {}
     roofline = None
-    if "column_pass" in kern:
-        # dominant kernel = column pass: algorithmic bytes per launch = read v + write Hv = 32 B/state of the shard
-        nl = kern["column_pass"]["launches_per_step"]
-        dur = kern["column_pass"]["ms_per_step"] / max(nl, 1)
-        bytes_launch = 32.0 * nloc  # one column pass reads its nloc-element operand once and writes nloc outputs
+    # dominant kernel of the step = the kind with the largest share of the profiled loop.  Algorithmic bytes per
+    # launch: column pass reads its operand once and writes its output once (32 B/state of
+    # the shard, 16 B/state in real mode is not timed here); row pass reads v and read-modify-writes Hv (48 B/state).
+    cand = {k: kern[k] for k in ("column_pass", "row_pass") if k in kern}
+    if cand:
+        dom = max(cand, key=lambda k: cand[k]["ms_per_step"])
+        nl = cand[dom]["launches_per_step"]
+        dur = cand[dom]["ms_per_step"] / max(nl, 1)
+        per_state = 32.0 if dom == "column_pass" else 48.0
+        bytes_launch = per_state * nloc
         ach = bytes_launch / (dur * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "column pass (k_colpass*)", "achieved": ach, "peak": peak, "unit": "GB/s",
+        names = {"column_pass": "column pass (k_colres: column-resident shared-memory kernel; k_colpass when a column does not fit)",
+                 "row_pass": "row pass (k_rowpass_rb)"}
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_source": peak_src,
-                    "traffic": (prof.get(args.workload, {}).get("column_pass", {}) or {}).get("dram_bytes_per_launch") if world == 1 else None,
-                    "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": dur,
+                    "traffic": (prof.get(args.workload, {}).get(dom, {}) or {}).get("dram_bytes_per_launch") if world == 1 else None,
+                    "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_state": per_state, "avg_launch_ms": dur,
+                    "share_of_step": cand[dom]["ms_per_step"] / sum(x["ms_per_step"] for x in kern.values()),
+                    "other_kernels": {k: {"achieved": (32.0 if k == "column_pass" else 48.0) * nloc * x["launches_per_step"] / (x["ms_per_step"] * 1e-3) / 1e9,
+                                          "frac": (32.0 if k == "column_pass" else 48.0) * nloc * x["launches_per_step"] / (x["ms_per_step"] * 1e-3) / 1e9 / peak}
+                                      for k, x in cand.items() if k != dom},
                     "step_frac_of_peak": value / world / peak}
 
     cpu = None

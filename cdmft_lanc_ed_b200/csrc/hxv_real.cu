@@ -16,6 +16,7 @@
 namespace cb {
 
 OpArgs op_args(const SpinOp &s);
+int rowpass_real_as_pairs(int64_t nrows, const double *v, double *out);  // hxv.cu
 DiagArgs diag_args(int64_t coloff);
 
 template <bool DIRECT, int CB>
@@ -114,6 +115,7 @@ int hxv_device_real(const double *v, double *hv) {
     if (rc != 0) c.launches++;
     prof_end();
   }
+  if (!direct && !(c.dimup & 1) && c.opt.colpass_variant != 5) return rowpass_real_as_pairs(c.dimup, v, hv);  // 16-byte gathers (two rows per lane)
   {
     const SpinOp &s = c.dw;
     dim3 grid((unsigned)s.n, (unsigned)((c.dimup + 255) / 256));
