@@ -32,6 +32,21 @@ struct Sched {
   uint32_t *words = nullptr;    // [(nquads+2)*32] uint4 / uint2 per quad and lane; formats in sector.cu
 };
 
+// Operator streams of the block-resident row pass (k_rowres, hxv.cu).  Columns (states of this spin) are cut
+// into blocks sharing their top bits; a CTA owns one block x 8 rows of the other spin's index, keeps that tile
+// in shared memory and runs, per warp task of 4 columns (one per 8-lane group), the in-block entries against
+// the tile and the off-block entries (hops that change the top bits) against global memory / L2.
+struct RowRes {
+  int32_t nblocks = 0, max_block = 0, ntask = 0;
+  int32_t fmt = 0;              // 0 = coefficient-table ids, 1 = fast (sign / class bits)
+  int2 *blocks = nullptr;       // [nblocks] (first column, columns)
+  int32_t *tbase = nullptr;     // [nblocks+1] first task of each block
+  uint4 *task = nullptr;        // [ntask] {first in-block quad, in-block quads, first off-block step, off-block steps}
+  int32_t *task_col = nullptr;  // [ntask*4] column (relative to the block) of each lane group, -1 = none
+  uint32_t *win = nullptr;      // [quads*4 groups] uint4: 4 steps, word = sign<<31 | tile row*128 | class  (or | id)
+  uint32_t *woff = nullptr;     // [steps*4 groups]: sign<<31 | column<<1 | class, 0xFFFFFFFF = none  (or column<<7 | id)
+};
+
 // Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).
 struct SpinOp {
   int32_t npart = 0;        // Nup or Ndw
@@ -71,6 +86,7 @@ struct SpinOp {
   bool pk_swizzled = false;      // built for the column pass (slot swizzled with rel&7)
   // column-resident kernels: schedules for 16-byte (sc8) and 8-byte (sc16) vector elements
   Sched sc8, sc16;
+  RowRes rr;
   bool sc_fast = false;          // real H with <= 2 distinct |coefficients|: sign and class bits instead of table ids
   double sc_mag[2] = {0.0, 0.0};
 };
@@ -100,7 +116,8 @@ struct Options {
   // shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass, 4/5 = rotating-slot tiles
   int64_t colpass_variant = 6;
   int64_t sched = 1;            // 1 = conflict-free edge-coloured schedule, 0 = natural CSR order (for comparison)
-  int64_t rowpass_variant = 1;
+  int64_t rowres_cols = 570;    // max columns of a block of the block-resident row pass ((cols+1) x 128 B of shared memory)
+  int64_t rowpass_variant = 1;  // 1 = generic L2-slab kernel (default, fastest measured), 4 = block-resident shared-memory row pass
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
   int64_t row_slab = 128;       // rows swept per grid.y index of the row pass (slab x all columns stays in L2)

@@ -838,6 +838,142 @@ static int launch_rowpass_tile_t(const SpinOp &s, int64_t nrows, const double2 *
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// Row pass, block-resident (SPARSE mode, rowpass_variant 4; tested, NOT default -- measured 3.9 ms vs 2.7 ms for
+// the generic L2-slab kernel at K3: latency-bound, and the off-block gathers cost twice an in-block one):
+//   out(i,c) += sum_k Hd(c,j_k) v(i,j_k).
+// One CTA owns (block of columns sharing their top bits) x (8 consecutive rows i0..i0+7).  The tile
+// v(i0..i0+7, block) -- one 128-byte line per column -- is brought into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier; no registers, no L1 wavefronts).  A warp task is 4 columns, one per 8-lane group;
+// the 8 lanes of a group are the 8 rows.  Entries whose source column lies inside the block read the tile
+// (one conflict-free 128-byte line per group and step); entries that change the top bits read global memory /
+// L2 (one line per group).  The generic kernel fetches every v element ~15 times from L2; here the in-block
+// share (60-75 %) is fetched once per tile.  Operator words are warp-task streams built on the host
+// (RowRes, ctx.h / build_rowres, sector.cu), shared by all row strips of a block.
+// MODE: 0 = coefficient table, complex; 1 = coefficient table, real; 2 = sign/class bits (fast).
+// ------------------------------------------------------------------------------------
+struct RowResArgs {
+  const int2 *blocks;
+  const int32_t *tbase;
+  const uint4 *task;
+  const int32_t *task_col;
+  const uint4 *win;
+  const uint32_t *woff;
+  const double2 *coef;
+  double m0, m1;
+  int nblocks;
+};
+
+template <int MODE>
+__device__ __forceinline__ void rowres_fma(double2 &acc, uint32_t w, double2 x, const char *coef_b, double m0, double m1) {
+  if (MODE == 2) rfma(acc, colres_signed((w & 1u) ? m1 : m0, w & 0x80000000u), x);
+  else if (MODE == 1) rfma(acc, *(const double *)(coef_b + ((w & 127u) << 4)), x);
+  else cfma(acc, *(const double2 *)(coef_b + ((w & 127u) << 4)), x);
+}
+
+template <int MODE>
+__device__ __forceinline__ bool rowres_on(uint32_t w) { return MODE == 2 ? (w != 0xFFFFFFFFu) : ((w & 127u) != 0u); }
+template <int MODE>
+__device__ __forceinline__ int64_t rowres_col(uint32_t w) { return MODE == 2 ? ((w & 0x7FFFFFFFu) >> 1) : (w >> 7); }
+
+template <int MODE>
+__global__ void __launch_bounds__(384, 3) k_rowres(int64_t n /*rows = DimUp*/, const double2 *__restrict__ v,
+                                                    double2 *__restrict__ out, RowResArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bar = (uint64_t *)smem_raw;
+  double2 *coef = (double2 *)(smem_raw + 128);
+  double2 *tile = (double2 *)(smem_raw + 128 + 2048);  // [ng+1][8], the last line stays zero
+  const int blk = blockIdx.x % a.nblocks;
+  const int64_t i0 = (int64_t)(blockIdx.x / a.nblocks) * 8;
+  const int2 b = a.blocks[blk];
+  const int g0 = b.x, ng = b.y;
+  const int nb = (int)min((int64_t)8, n - i0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int r = lane & 7, grp = lane >> 3;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (uint32_t)ng * (uint32_t)nb * 16u);
+  }
+  if (threadIdx.x < 128) coef[threadIdx.x] = MODE == 2 ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
+  if (threadIdx.x < 8) tile[(size_t)ng * 8 + threadIdx.x] = make_double2(0.0, 0.0);
+  if (nb < 8)  // ragged last strip: rows past the end read as zero
+    for (int k = threadIdx.x; k < ng * 8; k += blockDim.x)
+      if ((k & 7) >= nb) tile[k] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int cidx = threadIdx.x; cidx < ng; cidx += blockDim.x)
+    bulk_g2s(tile + (size_t)cidx * 8, v + (int64_t)(g0 + cidx) * n + i0, (uint32_t)nb * 16u, bar);
+  const int t0 = __ldg(a.tbase + blk), t1 = __ldg(a.tbase + blk + 1);
+  const char *tile_b = (const char *)tile + r * 16;
+  const char *coef_b = (const char *)coef;
+  const int rc = min(r, nb - 1);  // clamped on the ragged last strip (never stored)
+  const double2 *vrow = v + i0 + rc;
+  bool waited = false;
+  for (int t = t0 + warp; t < t1; t += nwarps) {
+    const uint4 tk = __ldg(a.task + t);
+    const int cl = __ldg(a.task_col + t * 4 + grp);
+    double2 *o = out + (int64_t)(g0 + max(cl, 0)) * n + i0 + rc;
+    const double2 y = *o;  // read-modify-write operand: requested first, needed last
+    double2 acc = make_double2(0.0, 0.0);
+    {  // ---- sources outside the block (long latency): global memory / L2, one 128-byte line per group
+      const uint32_t *wo = a.woff + (int64_t)tk.z * 4 + grp;
+      const int noff = (int)tk.w;
+      int k = 0;
+      for (; k + 2 <= noff; k += 2) {
+        const uint32_t w0 = __ldg(wo + k * 4), w1 = __ldg(wo + k * 4 + 4);
+        const bool on0 = rowres_on<MODE>(w0), on1 = rowres_on<MODE>(w1);
+        double2 x0 = make_double2(0.0, 0.0), x1 = make_double2(0.0, 0.0);
+        if (on0) x0 = ldg2(vrow + rowres_col<MODE>(w0) * n);
+        if (on1) x1 = ldg2(vrow + rowres_col<MODE>(w1) * n);
+        if (on0) rowres_fma<MODE>(acc, w0, x0, coef_b, a.m0, a.m1);
+        if (on1) rowres_fma<MODE>(acc, w1, x1, coef_b, a.m0, a.m1);
+      }
+      if (k < noff) {
+        const uint32_t w0 = __ldg(wo + k * 4);
+        if (rowres_on<MODE>(w0)) rowres_fma<MODE>(acc, w0, ldg2(vrow + rowres_col<MODE>(w0) * n), coef_b, a.m0, a.m1);
+      }
+    }
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
+    {  // ---- sources inside the block: shared memory, four steps per operator load
+      const uint4 *wi = a.win + (int64_t)tk.x * 4 + grp;
+      const int nq = (int)tk.y;
+      uint4 wn = __ldg(wi);  // slack behind the stream: always readable
+      for (int q = 0; q < nq; q++) {
+        const uint4 w = wn;
+        wn = __ldg(wi + (q + 1) * 4);
+        rowres_fma<MODE>(acc, w.x, *(const double2 *)(tile_b + (w.x & 0x7FFFFF80u)), coef_b, a.m0, a.m1);
+        rowres_fma<MODE>(acc, w.y, *(const double2 *)(tile_b + (w.y & 0x7FFFFF80u)), coef_b, a.m0, a.m1);
+        rowres_fma<MODE>(acc, w.z, *(const double2 *)(tile_b + (w.z & 0x7FFFFF80u)), coef_b, a.m0, a.m1);
+        rowres_fma<MODE>(acc, w.w, *(const double2 *)(tile_b + (w.w & 0x7FFFFF80u)), coef_b, a.m0, a.m1);
+      }
+    }
+    if (cl >= 0 && r < nb) *o = make_double2(y.x + acc.x, y.y + acc.y);
+  }
+  if (!waited) mbar_wait(bar, 0);  // a warp without tasks still must not leave before the copies have landed
+}
+
+static int launch_rowres(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
+  Ctx &c = ctx();
+  const RowRes &rr = s.rr;
+  if (c.mode != CDMFT_B200_SPARSE || !rr.win || rr.ntask <= 0) return kColresNA;
+  const size_t smem = 128 + 2048 + ((size_t)rr.max_block + 1) * 128;
+  if (smem > 232448) return kColresNA;
+  RowResArgs a{};
+  a.blocks = rr.blocks; a.tbase = rr.tbase; a.task = rr.task; a.task_col = rr.task_col;
+  a.win = (const uint4 *)rr.win; a.woff = rr.woff; a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
+  a.nblocks = rr.nblocks;
+  void (*kern)(int64_t, const double2 *, double2 *, RowResArgs) =
+      rr.fmt == 1 ? k_rowres<2> : (c.real_h ? k_rowres<1> : k_rowres<0>);
+  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nct = ((nrows + 7) / 8) * rr.nblocks;
+  if (nct > 0x7fffffffLL) return fail("rowres: grid too large");
+  // 384 threads x 3 CTAs per SM at K3 (59 KB tiles): the tile load of one CTA overlaps the compute of the others
+  const int threads = (int)std::min<int64_t>(384, std::max<int64_t>(64, ((int64_t)rr.max_block / 4 / 4 + 1) * 32));
+  kern<<<(unsigned)nct, threads, smem, c.stream>>>(nrows, v, out, a);
+  c.launches++;
+  return 0;
+}
+
 static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out);
 static int rowpass(const SpinOp &s, int64_t nrows, const double2 *v, double2 *out) {
   prof_begin(1);
@@ -849,7 +985,12 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
   Ctx &c = ctx();
   if (s.n <= 0 || nrows <= 0) return 0;
   // colpass_variant 5 leaves the off-block Hup terms to the generic row-pass kernel
-  const int64_t rv = c.opt.colpass_variant == 5 ? 1 : c.opt.rowpass_variant;
+  int64_t rv = c.opt.colpass_variant == 5 ? 1 : c.opt.rowpass_variant;
+  if (rv == 4) {
+    const int rc = launch_rowres(s, nrows, v, out);
+    if (rc != kColresNA) return rc;
+    rv = 1;  // DIRECT mode / no operator streams: generic kernel
+  }
   if (rv == 3 && c.mode == CDMFT_B200_SPARSE && s.nblocks_l1 > 0) {
     static bool configured = false;
     if (!configured) {  // all of the unified L1/shared array as L1

@@ -345,6 +345,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "row_rb") c.opt.row_rb = value;
   else if (k == "use_ipc") c.opt.use_ipc = value;
   else if (k == "sched") c.opt.sched = value;
+  else if (k == "rowres_cols") c.opt.rowres_cols = value;
   else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);
   return 0;

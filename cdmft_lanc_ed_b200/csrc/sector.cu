@@ -429,6 +429,105 @@ static int upload_schedule(Sched &sc, const SchedHost &h) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// Operator streams of the block-resident row pass (RowRes in ctx.h).  Blocks = runs of states sharing their
+// top t bits, t the smallest value with every block <= cap columns.  Inside a block the columns are sorted by
+// their number of in-block entries and dealt four to a warp task (one column per 8-lane group).
+// ------------------------------------------------------------------------------------
+static int build_rowres(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
+                        const std::vector<uint8_t> &code, bool fast, int64_t cap) {
+  Ctx &c = ctx();
+  RowRes &rr = op.rr;
+  int t = 0;
+  for (; t <= ns; t++) {
+    int64_t mx = 0;
+    for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, op.npart - k));
+    if (mx <= cap) break;
+  }
+  std::vector<int2> blk;
+  int64_t start = 0, mx = 0;
+  for (uint32_t P = 0; P < (1u << t); P++) {
+    const int64_t sz = binom64(ns - t, op.npart - __builtin_popcount(P));
+    if (sz <= 0) continue;
+    blk.push_back(make_int2((int)start, (int)sz));
+    start += sz;
+    mx = std::max(mx, sz);
+  }
+  if (start != op.n) return fail("internal: rowres blocks do not cover the sector");
+  std::vector<int32_t> tbase(blk.size() + 1, 0), task_col;
+  std::vector<uint4> task;
+  std::vector<uint32_t> win, woff;
+  const uint32_t NONE = fast ? 0xFFFFFFFFu : 0u;
+  auto word_in = [&](int64_t rel, uint32_t cd) -> uint32_t {
+    return fast ? ((cd & 1u) << 31) | ((uint32_t)rel << 7) | ((cd >> 1) & 1u) : ((uint32_t)rel << 7) | cd;
+  };
+  auto word_off = [&](int64_t j, uint32_t cd) -> uint32_t {
+    return fast ? ((cd & 1u) << 31) | ((uint32_t)j << 1) | ((cd >> 1) & 1u) : ((uint32_t)j << 7) | cd;
+  };
+  for (size_t b = 0; b < blk.size(); b++) {
+    const int g0 = blk[b].x, ng = blk[b].y;
+    tbase[b] = (int32_t)task.size();
+    std::vector<int32_t> order(ng), nin(ng, 0);
+    for (int k = 0; k < ng; k++) {
+      order[k] = k;
+      for (int32_t p = rowptr[g0 + k]; p < rowptr[g0 + k + 1]; p++) nin[k] += (col[p] >= g0 && col[p] < g0 + ng);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return nin[x] > nin[y]; });
+    for (int k0 = 0; k0 < ng; k0 += 4) {
+      int cols[4], kin = 0, koff = 0;
+      for (int q = 0; q < 4; q++) {
+        cols[q] = k0 + q < ng ? order[k0 + q] : -1;
+        if (cols[q] >= 0) {
+          const int len = rowptr[g0 + cols[q] + 1] - rowptr[g0 + cols[q]];
+          kin = std::max(kin, nin[cols[q]]);
+          koff = std::max(koff, len - nin[cols[q]]);
+        }
+        task_col.push_back(cols[q]);
+      }
+      const int nq = (kin + 3) / 4;
+      const size_t qb = win.size() / 16, ob = woff.size() / 4;
+      task.push_back(make_uint4((uint32_t)qb, (uint32_t)nq, (uint32_t)ob, (uint32_t)koff));
+      win.resize(win.size() + (size_t)nq * 16, word_in(ng, 0));  // idle steps read the zero line behind the tile
+      woff.resize(woff.size() + (size_t)koff * 4, NONE);
+      for (int q = 0; q < 4; q++) {
+        if (cols[q] < 0) continue;
+        int ki = 0, ko = 0;
+        for (int32_t p = rowptr[g0 + cols[q]]; p < rowptr[g0 + cols[q] + 1]; p++) {
+          const int32_t j = col[p];
+          if (j >= g0 && j < g0 + ng) {
+            win[(qb + ki / 4) * 16 + q * 4 + (ki & 3)] = word_in(j - g0, code[p]);  // uint4 (4 steps) per quad and group
+            ki++;
+          } else {
+            woff[(ob + ko) * 4 + q] = word_off(j, code[p]);
+            ko++;
+          }
+        }
+      }
+    }
+  }
+  tbase[blk.size()] = (int32_t)task.size();
+  rr.nblocks = (int32_t)blk.size();
+  rr.max_block = (int32_t)mx;
+  rr.ntask = (int32_t)task.size();
+  rr.fmt = fast ? 1 : 0;
+  win.resize(win.size() + 64, 0u);  // slack for the one-quad-ahead prefetch
+  woff.resize(woff.size() + 16, NONE);
+  CB_CHECK(dev_alloc(&rr.blocks, (int64_t)blk.size()));
+  CB_CHECK(dev_alloc(&rr.tbase, (int64_t)tbase.size()));
+  CB_CHECK(dev_alloc(&rr.task, (int64_t)task.size()));
+  CB_CHECK(dev_alloc(&rr.task_col, (int64_t)task_col.size()));
+  CB_CHECK(dev_alloc(&rr.win, (int64_t)win.size()));
+  CB_CHECK(dev_alloc(&rr.woff, (int64_t)woff.size()));
+  CB_CUDA(cudaMemcpyAsync(rr.blocks, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(rr.tbase, tbase.data(), tbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(rr.task, task.data(), task.size() * sizeof(uint4), cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(rr.task_col, task_col.data(), task_col.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(rr.win, win.data(), win.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(rr.woff, woff.data(), woff.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
                   double const_add, bool want_csr, bool pack_swizzled) {
   Ctx &c = ctx();
@@ -591,31 +690,36 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
       CB_CUDA(cudaMemcpyAsync(op.coef, table.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice, c.stream));
       op.pk_swizzled = pack_swizzled;
       CB_CUDA(cudaStreamSynchronize(c.stream));
-      // schedules of the column-resident kernels (only when a column can live in shared memory)
-      if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 25)) {
-        std::vector<int32_t> hrp(op.n + 1), hcol(op.nnz);
+      std::vector<int32_t> hrp, hcol;
+      if (op.n < (1 << 24)) {
+        hrp.resize(op.n + 1); hcol.resize(op.nnz);
         CB_CUDA(cudaMemcpy(hrp.data(), op.rowptr, (op.n + 1) * 4, cudaMemcpyDeviceToHost));
         CB_CUDA(cudaMemcpy(hcol.data(), op.col, op.nnz * 4, cudaMemcpyDeviceToHost));
-        // fast decode: real H with at most two distinct |coefficient| -> code = class<<1 | negative
-        std::vector<double> mags;
-        bool fast = op.real_h;
-        for (int t = 1; t < op.ncoef && fast; t++) {
-          if (table[t].y != 0.0) { fast = false; break; }
-          const double m = std::fabs(table[t].x);
-          if (std::find(mags.begin(), mags.end(), m) == mags.end()) mags.push_back(m);
-          if (mags.size() > 2) fast = false;
+      }
+      // fast decode: real H with at most two distinct |coefficient| -> code = class<<1 | negative
+      std::vector<double> mags;
+      bool fast = op.real_h;
+      for (int t = 1; t < op.ncoef && fast; t++) {
+        if (table[t].y != 0.0) { fast = false; break; }
+        const double m = std::fabs(table[t].x);
+        if (std::find(mags.begin(), mags.end(), m) == mags.end()) mags.push_back(m);
+        if (mags.size() > 2) fast = false;
+      }
+      std::vector<uint8_t> code(ids);
+      op.sc_fast = fast;
+      if (fast) {
+        op.sc_mag[0] = mags.size() > 0 ? mags[0] : 0.0;
+        op.sc_mag[1] = mags.size() > 1 ? mags[1] : 0.0;
+        for (int64_t k = 0; k < op.nnz; k++) {
+          const double x = table[ids[k]].x;
+          const int cls = (mags.size() > 1 && std::fabs(x) == mags[1]) ? 1 : 0;
+          code[k] = (uint8_t)((cls << 1) | (std::signbit(x) ? 1 : 0));
         }
-        std::vector<uint8_t> code(ids);
-        op.sc_fast = fast;
-        if (fast) {
-          op.sc_mag[0] = mags.size() > 0 ? mags[0] : 0.0;
-          op.sc_mag[1] = mags.size() > 1 ? mags[1] : 0.0;
-          for (int64_t k = 0; k < op.nnz; k++) {
-            const double x = table[ids[k]].x;
-            const int cls = (mags.size() > 1 && std::fabs(x) == mags[1]) ? 1 : 0;
-            code[k] = (uint8_t)((cls << 1) | (std::signbit(x) ? 1 : 0));
-          }
-        }
+      }
+      // operator streams of the block-resident row pass
+      if (op.n < (1 << 24)) CB_CHECK(build_rowres(op, ns, hrp, hcol, code, fast, std::max<int64_t>(8, std::min<int64_t>(1760, c.opt.rowres_cols))));
+      // schedules of the column-resident kernels (only when a column can live in shared memory)
+      if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 24)) {
         const bool natural = c.opt.sched == 0;
         const int fmt = !fast ? 0 : (op.n + 32 <= (1 << 14) ? 2 : 1);
         // per-row part of the diagonal and the row's impurity configuration travel with the schedule
@@ -652,6 +756,7 @@ void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
   dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
+  dev_free(op.rr.blocks); dev_free(op.rr.tbase); dev_free(op.rr.task); dev_free(op.rr.task_col); dev_free(op.rr.win); dev_free(op.rr.woff);
   for (Sched *sc : {&op.sc8, &op.sc16}) { dev_free(sc->tbase); dev_free(sc->qbase); dev_free(sc->meta); dev_free(sc->words); }
   op = SpinOp();
 }

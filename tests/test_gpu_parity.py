@@ -242,6 +242,10 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
 
 
 @pytest.mark.parametrize("opts", [
+    dict(rowpass_variant=4, rowres_cols=570),                  # block-resident row pass (TMA-staged tiles)
+    dict(rowpass_variant=4, rowres_cols=9),                    # ... many small blocks: mostly off-block gathers
+    dict(rowpass_variant=4, rowres_cols=40),
+    dict(rowpass_variant=4, rowres_cols=1760),                 # ... one block
     dict(colpass_variant=6, sched=1),                          # column-resident kernel, edge-coloured schedule (default)
     dict(colpass_variant=6, sched=0),                          # ... natural CSR order
     dict(colpass_variant=6, force_sharded=1),                  # ... on both spins (transposed layout)
@@ -270,7 +274,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=6, sched=1, rowpass_variant=1, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
+    defaults = dict(colpass_variant=6, sched=1, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)

@@ -29,7 +29,7 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(colpass_variant=6, sched=1), dict(colpass_variant=6, sched=0), dict(colpass_variant=1)]
+SWEEP = [dict(rowpass_variant=4, rowres_cols=570), dict(rowpass_variant=4, rowres_cols=260), dict(rowpass_variant=1)]
 
 
 def main():
@@ -41,7 +41,7 @@ def main():
     isec = models.get_sector(mdl.ns, *sec)
     for sparse in (True,):
         for opts in SWEEP:
-            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=6, sched=1, rowpass_variant=1, tile_rows=1800, l1_rows=256, row_rb=2, row_slab=128).items():
+            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=6, sched=1, rowpass_variant=1, rowres_cols=570, tile_rows=1800, l1_rows=256, row_rb=2, row_slab=128).items():
                 E.set_option(k, v)
             for k, v in opts.items():
                 E.set_option(k, v)
