@@ -29,7 +29,7 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(rowpass_variant=4, rowres_cols=570), dict(rowpass_variant=4, rowres_cols=260), dict(rowpass_variant=1)]
+SWEEP = [dict(colpass_variant=6, sched=1), dict(colpass_variant=6, sched=0), dict(colpass_variant=1), dict(rowpass_variant=4)]
 
 
 def main():
