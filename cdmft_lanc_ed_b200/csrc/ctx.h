@@ -124,6 +124,7 @@ struct Options {
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
   int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
   int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
+  int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the row pass instead of a separate sweep
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
   int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)
@@ -181,6 +182,10 @@ struct Ctx {
   bool profile = false;
   struct ProfRec { int kind; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
+  // fused Lanczos dot: the row pass leaves one partial of Re<v,Hv> per CTA when dot_request is set
+  bool dot_request = false, dot_done = false;
+  double *dot_partial = nullptr;
+  int64_t dot_cap = 0, dot_npartial = 0;
   double *red = nullptr;       // device reduction scratch
   double *red_host = nullptr;  // pinned
 };

@@ -481,10 +481,13 @@ __global__ void __launch_bounds__(256) k_rowpass(int64_t n /*rows=DimUp*/, int64
 // coefficient = 2 L1 wavefronts) is fetched once per RB coalesced gathers instead of once per gather,
 // and the RB gathers of an entry are independent loads in flight.
 // ------------------------------------------------------------------------------------
-template <bool REALH, int RB>
+// DOT: also reduce Re<v, out> over the CTA's outputs (out is final after this pass) into dot_partial[CTA] --
+// the Lanczos alpha without a separate sweep over two vectors (fixed summation order: deterministic).
+template <bool REALH, int RB, bool DOT>
 __global__ void __launch_bounds__(256) k_rowpass_rb(int64_t n /*rows=DimUp*/, const double2 *__restrict__ v,
                                                      double2 *__restrict__ out, const int32_t *__restrict__ rowptr,
-                                                     const int32_t *__restrict__ col, const double2 *__restrict__ val) {
+                                                     const int32_t *__restrict__ col, const double2 *__restrict__ val,
+                                                     double *__restrict__ dot_partial) {
   const int64_t c = blockIdx.x;
   const int64_t i0 = (int64_t)blockIdx.y * (blockDim.x * RB) + threadIdx.x;
   double2 acc[RB];
@@ -506,6 +509,7 @@ __global__ void __launch_bounds__(256) k_rowpass_rb(int64_t n /*rows=DimUp*/, co
       if (REALH) rfma(acc[r], h.x, x[r]); else cfma(acc[r], h, x[r]);
     }
   }
+  double dsum = 0.0;
 #pragma unroll
   for (int r = 0; r < RB; r++) {
     const int64_t i = i0 + (int64_t)r * blockDim.x;
@@ -515,6 +519,22 @@ __global__ void __launch_bounds__(256) k_rowpass_rb(int64_t n /*rows=DimUp*/, co
       y.x += acc[r].x;
       y.y += acc[r].y;
       *o = y;
+      if (DOT) {
+        const double2 u = ldg2(v + i + c * n);
+        dsum = fma(u.x, y.x, fma(u.y, y.y, dsum));
+      }
+    }
+  }
+  if (DOT) {
+    __shared__ double wsum[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) tot += wsum[w];
+      dot_partial[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
     }
   }
 }
@@ -1031,15 +1051,30 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
     const int slab = (int)std::max<int64_t>(64, std::min<int64_t>(1024, c.opt.row_slab));
     const int thr = std::max(32, slab / rb / 32 * 32);
     dim3 g2((unsigned)s.n, (unsigned)((nrows + (int64_t)thr * rb - 1) / ((int64_t)thr * rb)));
-    if (c.real_h) {
-      if (rb == 4) k_rowpass_rb<true, 4><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else if (rb == 2) k_rowpass_rb<true, 2><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else k_rowpass_rb<true, 1><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-    } else {
-      if (rb == 4) k_rowpass_rb<false, 4><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else if (rb == 2) k_rowpass_rb<false, 2><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
-      else k_rowpass_rb<false, 1><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val);
+    // fused Lanczos dot (lanczos.cu sets dot_request): one partial per CTA
+    double *dp = nullptr;
+    if (c.dot_request) {
+      const int64_t np = (int64_t)g2.x * g2.y;
+      if (c.dot_cap < np) {
+        dev_free(c.dot_partial);
+        CB_CHECK(dev_alloc(&c.dot_partial, np));
+        c.dot_cap = np;
+      }
+      dp = c.dot_partial;
+      c.dot_npartial = np;
+      c.dot_done = true;
     }
+#define CB_ROWRB(RH_, RB_)                                                                                                   \
+  do {                                                                                                                       \
+    if (dp) k_rowpass_rb<RH_, RB_, true><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val, dp);                \
+    else k_rowpass_rb<RH_, RB_, false><<<g2, thr, 0, c.stream>>>(nrows, v, out, s.rowptr, s.col, s.val, nullptr);             \
+  } while (0)
+    if (c.real_h) {
+      if (rb == 4) CB_ROWRB(true, 4); else if (rb == 2) CB_ROWRB(true, 2); else CB_ROWRB(true, 1);
+    } else {
+      if (rb == 4) CB_ROWRB(false, 4); else if (rb == 2) CB_ROWRB(false, 2); else CB_ROWRB(false, 1);
+    }
+#undef CB_ROWRB
     c.launches++;
     return 0;
   }

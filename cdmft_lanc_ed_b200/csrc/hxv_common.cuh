@@ -1,7 +1,9 @@
 // hxv_common.cuh -- device helpers shared by the H x v translation units (hxv.cu, hxv_real.cu)
 #pragma once
 #include <algorithm>
+#include <map>
 #include <type_traits>
+#include <utility>
 
 #include "ctx.h"
 
@@ -252,10 +254,18 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
   void (*kern)(int64_t, int64_t, const T *, T *, ColResArgs, DiagArgs) =
       sc.fmt == 2 ? k_colres<T, 3> : (sc.fmt == 1 ? k_colres<T, 2> : (c.real_h ? k_colres<T, 1> : k_colres<T, 0>));
-  CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = sc.nwarps * 32;  // the streams were dealt for exactly this many warps
-  int per_sm = 1;
-  CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  // attribute + occupancy query once per (kernel, shared-memory size)
+  static std::map<std::pair<const void *, size_t>, int> configured;
+  auto key = std::make_pair((const void *)kern, smem * 4096 + (size_t)threads);
+  auto it = configured.find(key);
+  if (it == configured.end()) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
+    it = configured.emplace(key, q).first;
+  }
+  const int per_sm = it->second;
   if (per_sm < 1) return kColresNA;
   const int64_t grid = std::min<int64_t>(ncols, (int64_t)c.sm_count * per_sm);
   kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);

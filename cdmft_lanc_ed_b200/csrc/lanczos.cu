@@ -80,6 +80,13 @@ __global__ void k_reduce_final(int nparts, const double2 *__restrict__ partial, 
   block_sum2(re, im);
   if (threadIdx.x == 0) { out[0] = re; out[1] = im; }
 }
+// stage 1 of the fixed-tree sum of the row pass's per-CTA dot partials
+__global__ void __launch_bounds__(256) k_sum_partials(int64_t n, const double *__restrict__ p, double2 *__restrict__ partial) {
+  double re = 0, im = 0;
+  GRID_STRIDE(i, n) re += p[i];
+  block_sum2(re, im);
+  if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_scale(int64_t n, T *__restrict__ v, double s) {
   GRID_STRIDE(i, n) v[i] = scaled(v[i], s);
@@ -219,9 +226,21 @@ template <typename T>
 static int lanczos_step(LanczosRun<T> &L, double *alfa, double *beta) {
   Ctx &c = ctx();
   std::complex<double> z;
-  CB_CHECK(hxv_t(L.u, L.t));
+  // alpha = Re<u, H u>: the row pass reduces it on the fly when it can (single rank, generic SPARSE row pass)
+  c.dot_request = c.opt.fuse_dot != 0;
+  c.dot_done = false;
+  int rc = hxv_t(L.u, L.t);
+  c.dot_request = false;
+  CB_CHECK(rc);
   prof_begin(4);
-  CB_CHECK(dot(L.n, L.u, L.t, &z));
+  if (c.dot_done) {
+    CB_CHECK(zero_partials());
+    k_sum_partials<<<kRedBlocks, 256, 0, c.stream>>>(c.dot_npartial, c.dot_partial, (double2 *)c.red);
+    c.launches++;
+    CB_CHECK(finish_reduce(&z));
+  } else {
+    CB_CHECK(dot(L.n, L.u, L.t, &z));
+  }
   prof_end();
   const double a = z.real() / (L.beta_cur * L.beta_cur);
   CB_CHECK(zero_partials());

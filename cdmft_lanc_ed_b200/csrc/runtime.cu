@@ -235,7 +235,7 @@ int cdmft_b200_finalize(void) {
   if (c.hstatus) cdmft_b200_delete_hv_sector();
   cudaStreamSynchronize(c.stream);
   if (c.nccl_comm) { nccl.CommDestroy(c.nccl_comm); c.nccl_comm = nullptr; }
-  dev_free(c.red); dev_free(c.cross_tab);
+  dev_free(c.red); dev_free(c.cross_tab); dev_free(c.dot_partial); c.dot_cap = 0;
   dev_free(c.stage_v); dev_free(c.stage_hv); c.stage_n = 0;
   for (auto &k : c.kv) dev_free(k);
   c.kv_n = 0;
@@ -345,6 +345,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "row_rb") c.opt.row_rb = value;
   else if (k == "use_ipc") c.opt.use_ipc = value;
   else if (k == "sched") c.opt.sched = value;
+  else if (k == "fuse_dot") c.opt.fuse_dot = value;
   else if (k == "rowres_cols") c.opt.rowres_cols = value;
   else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);

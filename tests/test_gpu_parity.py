@@ -325,3 +325,33 @@ def test_real_mode_krylov_equals_complex_mode(ed, oracle_lib):
         assert abs(abs(np.vdot(res[0][4], res[1][4])) - 1) < 1e-8
         ed.delete_Hv_sector()
         orc.delete_hv_sector()
+
+
+def test_fused_dot_matches_separate_dot(ed, oracle_lib):
+    """The Lanczos alpha reduced inside the row pass (option fuse_dot, default on) equals the separate
+    dot-product sweep and the oracle, for complex vectors, real vectors (paired rows) and an odd DimUp."""
+    for mdl, (nup, ndw) in [(models.hm2x2(2), (6, 6)), (models.bhz2(1), (2, 2)), (models.hm2x2(1), (3, 4)),
+                            (models.random_model(3, 1, 1, complex_h=False, seed=5), (2, 3))]:
+        orc = oracle_lib.Oracle(mdl)
+        ed.ed_set_model(mdl)
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        n = ed.build_Hv_sector(isec, True)
+        orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+        try:
+            for real in (True, False):
+                v0 = _rand_vec(n, seed=33, real=real)
+                out = {}
+                for fuse in (1, 0):
+                    ed.set_option("fuse_dot", fuse)
+                    out[fuse] = ed.sp_lanc_tridiag(v0, 30)
+                ond, oa, ob = orc.lanc_tridiag(v0, 30)
+                for fuse in (1, 0):
+                    nd, a, b = out[fuse]
+                    assert nd == ond
+                    assert np.abs(a[:25] - oa[:25]).max() <= RTOL * np.abs(oa[:25]).max(), (mdl.name, real, fuse)
+                    assert np.abs(b[:25] - ob[:25]).max() <= RTOL * np.abs(ob[:25]).max(), (mdl.name, real, fuse)
+                assert np.abs(out[1][1][:25] - out[0][1][:25]).max() <= 1e-12 * np.abs(oa[:25]).max()
+        finally:
+            ed.set_option("fuse_dot", 1)
+            ed.delete_Hv_sector()
+            orc.delete_hv_sector()
