@@ -256,11 +256,16 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
       sc.fmt == 2 ? k_colres<T, 3> : (sc.fmt == 1 ? k_colres<T, 2> : (c.real_h ? k_colres<T, 1> : k_colres<T, 0>));
   const int threads = sc.nwarps * 32;  // the streams were dealt for exactly this many warps
   // attribute + occupancy query once per (kernel, shared-memory size)
+  static std::map<const void *, size_t> max_smem;  // the attribute is only ever raised
   static std::map<std::pair<const void *, size_t>, int> configured;
+  size_t &ms = max_smem[(const void *)kern];
+  if (smem > ms) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ms = smem;
+  }
   auto key = std::make_pair((const void *)kern, smem * 4096 + (size_t)threads);
   auto it = configured.find(key);
   if (it == configured.end()) {
-    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int q = 0;
     CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
     it = configured.emplace(key, q).first;
