@@ -504,9 +504,20 @@ __global__ void __launch_bounds__(256) k_rowpass_rb(int64_t n /*rows=DimUp*/, co
     double2 x[RB];
 #pragma unroll
     for (int r = 0; r < RB; r++) x[r] = ldg2(vi[r] + off);
+    // the coefficient is warp-uniform: purely real / purely imaginary entries (every hop of the BHZ model) take
+    // two FMAs instead of four
+    if (REALH || h.y == 0.0) {
 #pragma unroll
-    for (int r = 0; r < RB; r++) {
-      if (REALH) rfma(acc[r], h.x, x[r]); else cfma(acc[r], h, x[r]);
+      for (int r = 0; r < RB; r++) rfma(acc[r], h.x, x[r]);
+    } else if (h.x == 0.0) {
+#pragma unroll
+      for (int r = 0; r < RB; r++) {
+        acc[r].x = fma(-h.y, x[r].y, acc[r].x);
+        acc[r].y = fma(h.y, x[r].x, acc[r].y);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RB; r++) cfma(acc[r], h, x[r]);
     }
   }
   double dsum = 0.0;
@@ -1189,11 +1200,12 @@ __global__ void __launch_bounds__(256) k_nonlocal(int64_t nloc, const double2 *_
   hv[il] = o;
 }
 
-static int hxv_local_terms(const double2 *v, double2 *hv);
+static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs);
+int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg);  // hxv_real.cu
 
 int hxv_device(const double2 *v, double2 *hv) {
   Ctx &c = ctx();
-  CB_CHECK(hxv_local_terms(v, hv));
+  CB_CHECK(hxv_local_terms(v, hv, false));
   if (!c.jhflag) return 0;
   NonLocalArgs a{};
   a.map_up = c.up.map; a.map_dw = c.dw.map;
@@ -1228,10 +1240,17 @@ int hxv_device(const double2 *v, double2 *hv) {
   return 0;
 }
 
-static int hxv_local_terms(const double2 *v, double2 *hv) {
+// PAIRS (real Krylov mode on a sharded layout): v / hv hold REAL vectors.  The diag + Hup pass runs the real
+// kernels; for everything after it two adjacent up-rows of the real vector are one double2 of a "complex"
+// vector with DimUp/2 rows -- transposes, exchanges and the Hdw pass act on the other index, and a real
+// coefficient treats both halves alike, so the complex code runs unchanged on half the bytes (HBM and NVLink).
+static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs) {
   Ctx &c = ctx();
   const bool sharded = c.spmd || c.sim || c.opt.force_sharded;
   DiagArgs nodiag{};
+  if (pairs && (!sharded || (c.dimup & 1) || !c.real_h)) return fail("hxv: paired-row view needs a sharded layout, a real H and an even DimUp");
+  const int64_t DU = pairs ? c.dimup / 2 : c.dimup;  // rows of the (possibly paired) view
+  auto usplit = [&](int p) { return split_of(DU, c.p_eff, p); };
   if (!sharded) {
     // one rank: diag + up (column pass), then dw on the strided index (row pass)
     CB_CHECK(colpass(c.up, c.dimdw, v, hv, diag_args(0)));
@@ -1254,6 +1273,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     // The forward transpose only reads v: it runs on the communication stream, overlapped with the
     // diag+Hup pass on the compute stream.
     RankState &me = c.rk[0];
+    const Split me_up = usplit(me.rank);
+    (void)me_up;
     cudaStream_t main = c.stream;
     // (measured on 2 B200: overlapping it with the column pass slows both -- they share the LSU
     // pipe -- so it is sequential unless overlap == 2)
@@ -1267,8 +1288,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     prof_begin(2);
     for (int k = 0; k < P && rc == 0; k++) {
       const int p = (me.rank + k) % P;  // staggered schedule: at step k every rank targets a different GPU
-      Split pu = split_of(c.dimup, P, p);
-      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, c.peer_vt[p], c.dimdw, me.dw.off);
+      Split pu = usplit(p);
+      transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, c.peer_vt[p], c.dimdw, me.dw.off);
     }
     prof_end();
     if (rc == 0) rc = nccl_barrier();  // B: all blocks of every vt have landed
@@ -1283,14 +1304,16 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     // the transpose of v does not depend on the diag+Hup pass: run pack -> all-to-all -> unpack on the
     // communication stream while the column pass runs on the compute stream
     RankState &me = c.rk[0];
+    const Split me_up = usplit(me.rank);
+    (void)me_up;
     cudaStream_t main = c.stream;
     int64_t so = 0, ro = 0;
     prof_begin(2);  // pack on the compute stream (alone, at full speed) ...
     for (int p = 0; p < P; p++) {
-      Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
+      Split pu = usplit(p), pd = split_of(c.dimdw, P, p);
       cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];
-      cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];
-      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+      cr[p] = me_up.q * pd.q; orr[p] = ro; ro += cr[p];
+      transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
     }
     prof_end();
     CB_CUDA(cudaEventRecord(c.ev_in, main));
@@ -1303,7 +1326,7 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
       prof_begin(2);
       for (int p = 0; p < P; p++) {
         Split pd = split_of(c.dimdw, P, p);
-        copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
+        copy_block<false>(me.recvbuf + orr[p], me_up.q, pd.q, me.vt, c.dimdw, pd.off);
       }
       prof_end();
       cudaEventRecord(c.ev_comm, c.comm_stream);
@@ -1313,8 +1336,9 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   }
   for (auto &r : c.rk) {
     offs.push_back(off);
-    CB_CHECK(colpass(c.up, r.dw.q, v + off, hv + off, diag_args(r.dw.off)));
-    off += r.nloc;
+    if (pairs) CB_CHECK(colpass_real(c.up, r.dw.q, (const double *)(v + off), (double *)(hv + off), diag_args(r.dw.off)));
+    else CB_CHECK(colpass(c.up, r.dw.q, v + off, hv + off, diag_args(r.dw.off)));
+    off += pairs ? r.nloc / 2 : r.nloc;
   }
   if (!c.spmd || P == 1) {
     // device-local exchange: write straight into the destination rank's buffer
@@ -1322,15 +1346,15 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     for (size_t a = 0; a < c.rk.size(); a++)
       for (size_t b = 0; b < c.rk.size(); b++) {
         RankState &src = c.rk[a], &dst = c.rk[b];
-        transpose_block<false>(v + offs[a], c.dimup, dst.up.off, dst.up.q, src.dw.q, dst.vt, c.dimdw, src.dw.off);
+        transpose_block<false>(v + offs[a], DU, usplit(dst.rank).off, usplit(dst.rank).q, src.dw.q, dst.vt, c.dimdw, src.dw.off);
       }
     prof_end();
-    for (auto &r : c.rk) CB_CHECK(colpass(c.dw, r.up.q, r.vt, r.hvt, nodiag));
+    for (auto &r : c.rk) CB_CHECK(colpass(c.dw, usplit(r.rank).q, r.vt, r.hvt, nodiag));
     prof_begin(2);
     for (size_t a = 0; a < c.rk.size(); a++)
       for (size_t b = 0; b < c.rk.size(); b++) {
         RankState &src = c.rk[a], &dst = c.rk[b];
-        transpose_block<true>(src.hvt, c.dimdw, dst.dw.off, dst.dw.q, src.up.q, hv + offs[b], c.dimup, src.up.off);
+        transpose_block<true>(src.hvt, c.dimdw, dst.dw.off, dst.dw.q, usplit(src.rank).q, hv + offs[b], DU, usplit(src.rank).off);
       }
     prof_end();
     return 0;
@@ -1338,21 +1362,22 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   // SPMD over NCCL: pack (transposing) -> grouped send/recv -> unpack
   if (c.rk.empty()) return 0;  // rank outside the shrunk communicator
   RankState &me = c.rk[0];
+  const Split me_up = usplit(me.rank);
   if (use_ipc) {
     if (c.opt.overlap == 2 && c.comm_stream) CB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
-    CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
+    CB_CHECK(colpass(c.dw, me_up.q, me.vt, me.hvt, nodiag));
     prof_begin(2);
     for (int k = 0; k < P; k++) {  // back: my rows (up) x p's columns (dw) -> p's receive window, transposed
       const int p = (me.rank + k) % P;
       Split pd = split_of(c.dimdw, P, p);
-      transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me.up.q, c.peer_recv[p] + pd.q * me.up.off, me.up.q, 0);
+      transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me_up.q, c.peer_recv[p] + pd.q * me_up.off, me_up.q, 0);
     }
     prof_end();
     CB_CHECK(nccl_barrier());  // C: my receive window is complete
     prof_begin(2);
     for (int p = 0; p < P; p++) {
-      Split pu = split_of(c.dimup, P, p);
-      copy_block<true>(me.recvbuf + me.dw.q * pu.off, me.dw.q, pu.q, hv, c.dimup, pu.off);
+      Split pu = usplit(p);
+      copy_block<true>(me.recvbuf + me.dw.q * pu.off, me.dw.q, pu.q, hv, DU, pu.off);
     }
     prof_end();
     return 0;
@@ -1363,10 +1388,10 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   } else {
     prof_begin(2);
     for (int p = 0; p < P; p++) {
-      Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
+      Split pu = usplit(p), pd = split_of(c.dimdw, P, p);
       cs[p] = pu.q * me.dw.q; os[p] = so; so += cs[p];   // my columns, p's rows
-      cr[p] = me.up.q * pd.q; orr[p] = ro; ro += cr[p];  // my rows, p's columns
-      transpose_block<false>(v, c.dimup, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+      cr[p] = me_up.q * pd.q; orr[p] = ro; ro += cr[p];  // my rows, p's columns
+      transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
     }
     prof_end();
     prof_begin(3);
@@ -1375,18 +1400,18 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
     prof_begin(2);
     for (int p = 0; p < P; p++) {
       Split pd = split_of(c.dimdw, P, p);
-      copy_block<false>(me.recvbuf + orr[p], me.up.q, pd.q, me.vt, c.dimdw, pd.off);
+      copy_block<false>(me.recvbuf + orr[p], me_up.q, pd.q, me.vt, c.dimdw, pd.off);
     }
     prof_end();
   }
-  CB_CHECK(colpass(c.dw, me.up.q, me.vt, me.hvt, nodiag));
+  CB_CHECK(colpass(c.dw, me_up.q, me.vt, me.hvt, nodiag));
   so = ro = 0;
   prof_begin(2);
   for (int p = 0; p < P; p++) {
-    Split pu = split_of(c.dimup, P, p), pd = split_of(c.dimdw, P, p);
-    cs[p] = pd.q * me.up.q; os[p] = so; so += cs[p];   // my rows (up), p's columns (dw)
+    Split pu = usplit(p), pd = split_of(c.dimdw, P, p);
+    cs[p] = pd.q * me_up.q; os[p] = so; so += cs[p];   // my rows (up), p's columns (dw)
     cr[p] = me.dw.q * pu.q; orr[p] = ro; ro += cr[p];
-    transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me.up.q, me.sendbuf + os[p], me.up.q, 0);
+    transpose_block<false>(me.hvt, c.dimdw, pd.off, pd.q, me_up.q, me.sendbuf + os[p], me_up.q, 0);
   }
   prof_end();
   prof_begin(3);
@@ -1394,12 +1419,15 @@ static int hxv_local_terms(const double2 *v, double2 *hv) {
   prof_end();
   prof_begin(2);
   for (int p = 0; p < P; p++) {
-    Split pu = split_of(c.dimup, P, p);
-    copy_block<true>(me.recvbuf + orr[p], me.dw.q, pu.q, hv, c.dimup, pu.off);
+    Split pu = usplit(p);
+    copy_block<true>(me.recvbuf + orr[p], me.dw.q, pu.q, hv, DU, pu.off);
   }
   prof_end();
   return 0;
 }
+
+// real vectors on a sharded layout (called from hxv_real.cu): see PAIRS above
+int hxv_sharded_real(const double *v, double *hv) { return hxv_local_terms((const double2 *)v, (double2 *)hv, true); }
 
 // spH0d of the local rows
 __global__ void k_diag_only(int64_t n, int64_t ncols, double *__restrict__ out, DiagArgs dg) {

@@ -97,24 +97,35 @@ __global__ void __launch_bounds__(256) k_rowpass_r(int64_t n /*rows*/, int64_t n
   out[i + c * n] += acc0 + acc1;
 }
 
-// real-vector H x v on one rank (non-sharded); requires a real Hamiltonian and no Jx/Jp term
+// diag + Hup on a real vector: column-resident kernel when a column fits in shared memory, else the generic one
+int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  if (ncols <= 0 || s.n <= 0) return 0;
+  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  prof_begin(0);
+  const int rc = c.opt.colpass_variant == 6 ? launch_colres<double>(s, ncols, v, out, dg) : kColresNA;
+  if (rc != 0 && rc != kColresNA) { prof_end(); return rc; }
+  if (rc == kColresNA) {
+    dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((ncols + 3) / 4));
+    if (grid.y > 65535) { prof_end(); return fail("colpass_r: too many column groups"); }
+    if (direct) k_colpass_r<true, 4><<<grid, 256, 0, c.stream>>>(s.n, ncols, v, out, op_args(s), dg);
+    else k_colpass_r<false, 4><<<grid, 256, 0, c.stream>>>(s.n, ncols, v, out, op_args(s), dg);
+    c.launches++;
+  }
+  prof_end();
+  return 0;
+}
+
+int hxv_sharded_real(const double *v, double *hv);  // hxv.cu
+
+// real-vector H x v; requires a real Hamiltonian and no Jx/Jp term.  One rank: column pass + row pass.
+// Sharded layouts (SPMD, simulated ranks): the paired-row view of hxv.cu (even DimUp).
 int hxv_device_real(const double *v, double *hv) {
   Ctx &c = ctx();
-  if (!c.real_h || c.jhflag || c.spmd || c.sim || c.opt.force_sharded) return fail("hxv_device_real: not applicable");
+  if (!c.real_h || c.jhflag) return fail("hxv_device_real: not applicable");
+  if (c.spmd || c.sim || c.opt.force_sharded) return hxv_sharded_real(v, hv);
   const bool direct = c.mode == CDMFT_B200_DIRECT;
-  {
-    const SpinOp &s = c.up;
-    dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((c.dimdw + 3) / 4));
-    if (grid.y > 65535) return fail("colpass_r: too many column groups");
-    prof_begin(0);
-    const int rc = c.opt.colpass_variant == 6 ? launch_colres<double>(s, c.dimdw, v, hv, diag_args(0)) : kColresNA;
-    if (rc != 0 && rc != kColresNA) { prof_end(); return rc; }
-    if (rc == 0) {}  // column-resident kernel launched
-    else if (direct) k_colpass_r<true, 4><<<grid, 256, 0, c.stream>>>(s.n, c.dimdw, v, hv, op_args(s), diag_args(0));
-    else k_colpass_r<false, 4><<<grid, 256, 0, c.stream>>>(s.n, c.dimdw, v, hv, op_args(s), diag_args(0));
-    if (rc != 0) c.launches++;
-    prof_end();
-  }
+  CB_CHECK(colpass_real(c.up, c.dimdw, v, hv, diag_args(0)));
   if (!direct && !(c.dimup & 1) && c.opt.colpass_variant != 5) return rowpass_real_as_pairs(c.dimup, v, hv);  // 16-byte gathers (two rows per lane)
   {
     const SpinOp &s = c.dw;

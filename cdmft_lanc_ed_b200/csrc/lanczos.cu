@@ -348,7 +348,10 @@ __global__ void __launch_bounds__(256) k_apply_op(int64_t idim, int64_t idimup, 
 // real mode = real Hamiltonian, one rank, no Jx/Jp, and a start vector without imaginary part
 static bool real_mode_possible() {
   Ctx &c = ctx();
-  return c.opt.real_lanczos && c.real_h && !c.jhflag && !c.spmd && !c.sim && !c.opt.force_sharded;
+  if (!c.opt.real_lanczos || !c.real_h || c.jhflag) return false;
+  // sharded layouts use the paired-row view (hxv.cu): DimUp must be even
+  if (c.spmd || c.sim || c.opt.force_sharded) return (c.dimup & 1) == 0;
+  return true;
 }
 // sum |Im z|^2 (and optionally r = Re z)
 static int split_real(int64_t n, const double2 *z, double *r, double *im2) {
@@ -454,7 +457,7 @@ int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, d
   double2 *z0 = c.kv[0];
   if (nloc > 0)
     CB_CUDA(cudaMemcpyAsync(z0, v0, (size_t)nloc * 16, is_device_ptr(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
-  if (real_mode_possible() && nloc > 0) {
+  if (real_mode_possible()) {  // every rank takes the same branch: the reductions below are collective
     double *r = (double *)c.kv[1];  // u (real) in the first half of kv[1]
     double im2 = 1.0;
     CB_CHECK(split_real(nloc, z0, r, &im2));
@@ -492,7 +495,7 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
     if (nloc > 0) { k_fill<double2><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, 1.0 / std::sqrt((double)c.dim)); c.launches++; }
   }
   bool done = false;
-  if (real_mode_possible() && nloc > 0) {
+  if (real_mode_possible()) {  // every rank takes the same branch: the reductions below are collective
     // real mode: u, um in kv[0] (two halves), t and the real eigenvector in kv[1]
     double *gr = (double *)c.kv[1] + nloc;
     double im2 = 1.0;

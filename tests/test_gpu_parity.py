@@ -355,3 +355,42 @@ def test_fused_dot_matches_separate_dot(ed, oracle_lib):
             ed.set_option("fuse_dot", 1)
             ed.delete_Hv_sector()
             orc.delete_hv_sector()
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+def test_real_mode_krylov_on_sharded_layout(oracle_lib, P):
+    """Real H + real start vector on the Ndw-sharded layout (P simulated ranks): the Krylov drivers keep real
+    vectors and run transposes / Hdw pass on the paired-row view (two adjacent up-rows = one double2); an odd
+    DimUp falls back to complex vectors.  Coefficients and E0 against the oracle and against real_lanczos=0."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    cases = [(models.hm2x2(2), (6, 6), True), (models.hm2x2(2), (5, 7), False), (models.hm2x2(1), (4, 3), True),
+             (models.random_model(3, 1, 1, complex_h=False, seed=13), (3, 3), True)]   # DimUp = 924, 792, 70, 20 / odd: none here
+    cases.append((models.random_model(3, 1, 0, complex_h=False, seed=3), (1, 2), True))  # DimUp = 3 (odd): complex fallback
+    E.ed_init_sim(P, 0)
+    try:
+        for mdl, (nup, ndw), sparse in cases:
+            orc = oracle_lib.Oracle(mdl)
+            E.ed_set_model(mdl)
+            isec = models.get_sector(mdl.ns, nup, ndw)
+            n = E.build_Hv_sector(isec, sparse)
+            orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+            v0 = _rand_vec(n, seed=77, real=True)
+            nl = min(25, n)
+            ond, oa, ob = orc.lanc_tridiag(v0, nl)
+            oe0 = orc.lanc_eigh(300, 1e-13)[0]
+            for mode in (1, 0):
+                E.set_option("real_lanczos", mode)
+                nd, a, b = E.sp_lanc_tridiag(v0, nl)
+                k = min(nd, ond, 20)
+                assert np.abs(a[:k] - oa[:k]).max() <= RTOL * max(np.abs(oa[:k]).max(), 1e-300), (mdl.name, mode)
+                assert np.abs(b[:k] - ob[:k]).max() <= RTOL * max(np.abs(ob[:k]).max(), 1e-300), (mdl.name, mode)
+                vec = np.zeros(n, dtype=np.complex128)
+                e0, nit, _, _ = E.sp_lanc_eigh(vec, 300, 1e-13)
+                assert abs(e0 - oe0) <= RTOL * max(abs(oe0), 1e-300), (mdl.name, mode)
+                assert np.linalg.norm(orc.hxv(vec) - e0 * vec) < 1e-5
+            E.set_option("real_lanczos", 1)
+            E.delete_Hv_sector()
+            orc.delete_hv_sector()
+    finally:
+        E.set_option("real_lanczos", 1)
+        E.ed_finalize()

@@ -53,7 +53,19 @@ def main():
             time_hxv(n, iters=5, warm=0)
             kt = {k: round(E.profile_query(k)[0] / 5, 3) for k in (0, 1, 2)}
             E.set_option("profile", 0)
+            # one Krylov run (20 steps) with the per-kind timers: real vectors when H is real
+            E.set_option("profile", 1)
+            E.profile_query(0), E.profile_query(1), E.profile_query(4)
+            v0 = torch.ones(n, dtype=torch.complex128, device="cuda")
+            torch.cuda.synchronize()
+            t0 = time.time()
+            E.sp_lanc_tridiag(v0, 20)
+            tl = (time.time() - t0) / 20 * 1e3
+            kl = {k: round(E.profile_query(k)[0] / 20, 3) for k in (0, 1, 4)}
+            E.set_option("profile", 0)
+            del v0
             E.delete_Hv_sector()
+            opts = dict(opts, lanc_ms_per_iter=round(tl, 3), lanc_col=kl[0], lanc_row=kl[1], lanc_vec=kl[4])
             print(json.dumps(dict(cfg=which, sparse=sparse, **opts, n=n, build_s=round(tb, 3), ms=round(ms, 4),
                                   gbs_alg=round(32 * n / ms / 1e6, 1), col_ms=kt[0], row_ms=kt[1], tr_ms=kt[2])), flush=True)
     E.ed_finalize()

@@ -46,6 +46,9 @@ def main():
             hv = np.empty_like(vloc)
             E.spHtimesV_p(nloc, vloc, hv)
             nd, a, b = E.sp_lanc_tridiag(vloc, 30)
+            # real start vector: real Krylov vectors on the sharded layout (paired-row view) when H is real
+            vr = np.ascontiguousarray(v.real[off:off + nloc] / np.linalg.norm(v.real)).astype(np.complex128)
+            ndr, ar, br = E.sp_lanc_tridiag(vr, 30)
             # gather on rank 0 (gather_vector_MPI, ED_SETUP.f90:633-668)
             parts = [None] * world
             dist.all_gather_object(parts, hv)
@@ -56,14 +59,17 @@ def main():
                 orc.build_hv_sector(isec, edo.SPARSE_MPI if sparse else edo.DIRECT_MPI, world)
                 ref = orc.hxv(v)
                 ond, oa, ob = orc.lanc_tridiag(v, 30)
+                ondr, oar, obr = orc.lanc_tridiag((v.real / np.linalg.norm(v.real)).astype(np.complex128), 30)
                 got = np.concatenate([p for p in parts if p.size])
                 err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
                 k = min(nd, ond, 20)
                 erra = np.abs(a[:k] - oa[:k]).max() / max(np.abs(oa[:k]).max(), 1e-300)
-                good = err < 1e-10 and erra < 1e-9 and p_eff == orc.active_ranks() and nd == ond
+                kr = min(ndr, ondr, 20)
+                errr = np.abs(ar[:kr] - oar[:kr]).max() / max(np.abs(oar[:kr]).max(), 1e-300)
+                good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == orc.active_ranks() and nd == ond and ndr == ondr
                 ok &= bool(good)
                 print(f"{mdl.name} sector({nup},{ndw}) sparse={sparse} P={world} p_eff={p_eff} dim={dim} "
-                      f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} {'OK' if good else 'FAIL'}", flush=True)
+                      f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} alpha_realstart_relerr={errr:.2e} {'OK' if good else 'FAIL'}", flush=True)
                 orc.delete_hv_sector()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
