@@ -318,7 +318,8 @@ def run_ours(args):
         barrier()
         gs = {"seconds": time.perf_counter() - t0, "iterations": nit, "hxv_calls": 2 * nit, "e0": e0,
               "threshold": args.lanc_tol, "nitermax": args.lanc_niter, "start": "constant 1/sqrt(Dim)",
-              "vectors": "real (8 B) -- H and start vector real, single rank" if (mdl.is_real and world == 1) else "complex(8)"}
+              "vectors": ("real (8 B) -- H and start vector real" + ("" if world == 1 else ", sharded: paired-row view"))
+                         if (mdl.is_real and (world == 1 or E.getDim(isec)[1] % 2 == 0)) else "complex(8)"}
         del vec
 
     peaks = _load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))

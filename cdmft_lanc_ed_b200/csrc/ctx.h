@@ -23,7 +23,7 @@ struct Term {  // h(a,b) c^+_a c_b, a != b, 0-based bit positions inside one spi
 // by their number of steps and dealt 32/G to a warp task.
 struct Sched {
   int32_t G = 0, ntask = 0;
-  int32_t fmt = 0;              // word format: 0 general (table ids), 1 fast 32-bit, 2 fast 16-bit (sector.cu)
+  int32_t fmt = 0;              // word format: 0 general (table ids), 1 fast 32-bit, 2 fast 16-bit, 3 fast4 (sector.cu)
   int32_t nwarps = 0;           // warps per CTA the streams were dealt for (= launch configuration)
   int64_t nquads = 0;           // quads (4 steps) over all tasks
   int32_t *tbase = nullptr;     // [nwarps+1] first task of each warp (tasks are numbered warp-major) (device)
@@ -88,7 +88,7 @@ struct SpinOp {
   Sched sc8, sc16;
   RowRes rr;
   bool sc_fast = false;          // real H with <= 2 distinct |coefficients|: sign and class bits instead of table ids
-  double sc_mag[2] = {0.0, 0.0};
+  double sc_mag[4] = {0.0, 0.0, 0.0, 0.0};  // |coefficient| classes of the fast decodes
 };
 
 struct Split {  // first (n mod P) ranks get one more (ED_HAMILTONIAN.f90:92-105)
@@ -124,6 +124,7 @@ struct Options {
   int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
   int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
   int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
+  int64_t fast4 = 1;            // column-resident kernel: sign/class/phase decode for purely real-or-imaginary coefficients
   int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the row pass instead of a separate sweep
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass

@@ -108,7 +108,8 @@ struct ColResArgs {
   const uint4 *meta;             // [ntask*32]
   const uint32_t *words;
   const double2 *coef;  // [128] (table decode)
-  double m0, m1;        // fast decode
+  double m0, m1;        // fast decode (m0..m3 for the four-class variant)
+  double m2, m3;
 };
 
 __device__ __forceinline__ void colres_fma(double2 &acc, double h, double2 x) { rfma(acc, h, x); }
@@ -121,13 +122,23 @@ __device__ __forceinline__ double2 colres_scale(double d, double2 x) { return ma
 __device__ __forceinline__ double colres_scale(double d, double x) { return d * x; }
 
 // decode modes: 0 = coefficient table, complex values; 1 = coefficient table, real values;
-// 2 = fast 32-bit words; 3 = fast 16-bit words (formats in sector.cu, build_schedule_host)
+// 2 = fast 32-bit words; 3 = fast 16-bit words; 4 = fast4: purely real or purely imaginary coefficients of up
+// to four magnitudes (formats in sector.cu, build_schedule_host)
+__device__ __forceinline__ double2 colres_times_i(double2 x) { return make_double2(-x.y, x.x); }
+__device__ __forceinline__ double colres_times_i(double x) { return x; }  // real vectors never carry the phase bit
 __device__ __forceinline__ double colres_signed(double m, uint32_t signbit31) {
   return __hiloint2double(__double2hiint(m) ^ (int)signbit31, __double2loint(m));
 }
 template <typename T, int MODE>
-__device__ __forceinline__ void colres_step(T &acc, uint32_t w, const char *xs, const char *coef_b, double m0, double m1) {
-  if (MODE == 2) {
+__device__ __forceinline__ void colres_step(T &acc, uint32_t w, const char *xs, const char *coef_b, double m0, double m1,
+                                            double m2 = 0.0, double m3 = 0.0) {
+  if (MODE == 4) {
+    // w = (negative << 31) | byte offset | imaginary << 2 | class : h = +-m or +-i*m
+    T x = *(const T *)(xs + (w & 0x7FFFFFF8u & ~(uint32_t)(sizeof(T) - 1)));
+    const double ma = (w & 1u) ? m1 : m0, mb = (w & 1u) ? m3 : m2;
+    if (w & 4u) x = colres_times_i(x);
+    colres_fma(acc, colres_signed((w & 2u) ? mb : ma, w & 0x80000000u), x);
+  } else if (MODE == 2) {
     // w = (negative << 31) | byte offset | class : branch-free, idle lanes read a zero element
     const T x = *(const T *)(xs + (w & 0x7FFFFFF8u & ~(uint32_t)(sizeof(T) - 1)));
     colres_fma(acc, colres_signed((w & 1u) ? m1 : m0, w & 0x80000000u), x);
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t npad = (n + G - 1) / G * G;
   if (threadIdx.x == 0) mbar_init(bar, 1);
-  if (threadIdx.x < 128) coef[threadIdx.x] = MODE >= 2 ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
+  if (threadIdx.x < 128) coef[threadIdx.x] = MODE >= 2 ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];  // table decode only
   for (int64_t k = n + threadIdx.x; k < npad + G; k += blockDim.x) colres_zero(xs[k]);  // idle lanes gather these
   // this warp's stream: tasks [t0,t1) and the quads from q0 on (the same for every column)
   const int t0 = __ldg(a.tbase + warp), t1 = __ldg(a.tbase + warp + 1);
@@ -218,10 +229,10 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
           colres_step16x2<T>(acc, w.x, xs_b, a.m0, a.m1);
           colres_step16x2<T>(acc, w.y, xs_b, a.m0, a.m1);
         } else {
-          colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1);
-          colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1);
-          colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1);
-          colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1);
+          colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
         }
       }
       if (valid) oc[m.z] = acc;
@@ -251,9 +262,10 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   if (dg.enabled && dg.f_row != s.f) return kColresNA;  // the schedule carries the operator's own row diagonal
   ColResArgs a{};
   a.tbase = sc.tbase; a.qbase = sc.qbase; a.meta = (const uint4 *)sc.meta; a.words = sc.words;
-  a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
+  a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1]; a.m2 = s.sc_mag[2]; a.m3 = s.sc_mag[3];
   void (*kern)(int64_t, int64_t, const T *, T *, ColResArgs, DiagArgs) =
-      sc.fmt == 2 ? k_colres<T, 3> : (sc.fmt == 1 ? k_colres<T, 2> : (c.real_h ? k_colres<T, 1> : k_colres<T, 0>));
+      sc.fmt == 3 ? k_colres<T, 4>
+                  : (sc.fmt == 2 ? k_colres<T, 3> : (sc.fmt == 1 ? k_colres<T, 2> : (c.real_h ? k_colres<T, 1> : k_colres<T, 0>)));
   const int threads = sc.nwarps * 32;  // the streams were dealt for exactly this many warps
   // attribute + occupancy query once per (kernel, shared-memory size)
   static std::map<const void *, size_t> max_smem;  // the attribute is only ever raised

@@ -268,7 +268,7 @@ struct SchedHost {
 static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
                                 const std::vector<uint8_t> &code, int G, int fmt, bool natural, int nwarps,
                                 const double *f_row, const uint32_t *mu_row, SchedHost &out) {
-  const bool fast = fmt != 0, w16 = fmt == 2;
+  const bool fast = fmt == 1 || fmt == 2, w16 = fmt == 2, f4 = fmt == 3;
   const int64_t ngroups = (n + G - 1) / G;
   const int64_t npad = ngroups * G;  // G zero elements follow the column in shared memory: [npad, npad+G)
   const int esz = G == 8 ? 16 : 8;   // bytes per vector element
@@ -276,14 +276,16 @@ static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, c
   // fmt 0 (general): (j << 7) | coefficient id, id 0 = 0.0       four steps per uint4
   // fmt 1 (fast32):  (negative << 31) | (j * esz) | class         four steps per uint4, address one AND away
   // fmt 2 (fast16):  (negative << 15) | (class << 14) | j         two steps per uint32 (needs npad+G <= 2^14)
+  // fmt 3 (fast4):   (negative << 31) | (j * esz) | imaginary << 2 | class (2 bits)   four steps per uint4
   auto mkword = [&](int64_t j, uint32_t cd) -> uint32_t {
+    if (f4) return ((cd & 1u) << 31) | (uint32_t)(j * esz) | ((cd >> 1) & 3u) | (((cd >> 3) & 1u) << 2);
     if (w16) return ((cd & 1u) << 15) | (((cd >> 1) & 1u) << 14) | (uint32_t)j;
     if (fast) return ((cd & 1u) << 31) | (uint32_t)(j * esz) | ((cd >> 1) & 1u);
     return ((uint32_t)j << 7) | cd;
   };
   auto idle = [&](int b) -> uint32_t {
     if (w16) return (uint32_t)(npad + b);
-    return fast ? (uint32_t)((npad + b) * esz) : ((uint32_t)(npad + b) << 7);
+    return (fast || f4) ? (uint32_t)((npad + b) * esz) : ((uint32_t)(npad + b) << 7);
   };
   std::vector<std::vector<uint32_t>> steps(ngroups);  // [K_g * G] words of each group
   std::vector<int32_t> K(ngroups, 0);
@@ -716,12 +718,37 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
           code[k] = (uint8_t)((cls << 1) | (std::signbit(x) ? 1 : 0));
         }
       }
+      // second level: every coefficient purely real or purely imaginary, at most four distinct magnitudes
+      // (complex hoppings such as the BHZ model's -ts*sigma_z + i*lambda/2*sigma_x): code4 = negative | class<<1 | imaginary<<3
+      std::vector<uint8_t> code4;
+      bool fast4 = !fast;
+      {
+        std::vector<double> mags4;
+        for (int t = 1; t < op.ncoef && fast4; t++) {
+          if (table[t].x != 0.0 && table[t].y != 0.0) { fast4 = false; break; }
+          const double m = std::fabs(table[t].y != 0.0 ? table[t].y : table[t].x);
+          if (std::find(mags4.begin(), mags4.end(), m) == mags4.end()) mags4.push_back(m);
+          if (mags4.size() > 4) fast4 = false;
+        }
+        if (fast4) {
+          for (int q = 0; q < 4; q++) op.sc_mag[q] = q < (int)mags4.size() ? mags4[q] : 0.0;
+          code4.resize(op.nnz);
+          for (int64_t k = 0; k < op.nnz; k++) {
+            const double2 h = table[ids[k]];
+            const bool im = h.y != 0.0;
+            const double x = im ? h.y : h.x;
+            const int cls = (int)(std::find(mags4.begin(), mags4.end(), std::fabs(x)) - mags4.begin());
+            code4[k] = (uint8_t)((std::signbit(x) ? 1 : 0) | (cls << 1) | (im ? 8 : 0));
+          }
+        }
+      }
       // operator streams of the block-resident row pass
       if (op.n < (1 << 24)) CB_CHECK(build_rowres(op, ns, hrp, hcol, code, fast, std::max<int64_t>(8, std::min<int64_t>(1760, c.opt.rowres_cols))));
       // schedules of the column-resident kernels (only when a column can live in shared memory)
       if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 24)) {
         const bool natural = c.opt.sched == 0;
-        const int fmt = !fast ? 0 : (op.n + 32 <= (1 << 14) ? 2 : 1);
+        const int fmt = fast4 && c.opt.fast4 ? 3 : (!fast ? 0 : (op.n + 32 <= (1 << 14) ? 2 : 1));
+        if (fmt == 3) code = code4;
         // per-row part of the diagonal and the row's impurity configuration travel with the schedule
         std::vector<double> hf(op.n);
         std::vector<int32_t> hmap(op.n);

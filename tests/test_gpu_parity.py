@@ -248,6 +248,7 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     dict(rowpass_variant=4, rowres_cols=1760),                 # ... one block
     dict(colpass_variant=6, sched=1),                          # column-resident kernel, edge-coloured schedule (default)
     dict(colpass_variant=6, sched=0),                          # ... natural CSR order
+    dict(colpass_variant=6, fast4=0),                          # ... coefficient-table decode instead of sign/class/phase bits
     dict(colpass_variant=6, force_sharded=1),                  # ... on both spins (transposed layout)
     dict(colpass_variant=1, rowpass_variant=1, col_batch=1),   # generic global-gather kernels
     dict(colpass_variant=1, rowpass_variant=1, col_batch=8),
@@ -274,7 +275,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=6, sched=1, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
+    defaults = dict(colpass_variant=6, sched=1, fast4=1, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)
