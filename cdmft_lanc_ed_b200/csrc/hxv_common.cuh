@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
   const int t0 = __ldg(a.tbase + warp), t1 = __ldg(a.tbase + warp + 1);
   const int64_t q0 = __ldg(a.qbase + warp);
   const uint4 *mp = a.meta + (int64_t)t0 * 32 + lane;
-  using WQ = typename std::conditional<MODE == 3, uint2, uint4>::type;  // one quad (4 steps) of a lane
+  using WQ = typename std::conditional<MODE == 3, uint32_t, uint4>::type;  // one unit of a lane: 2 or 4 steps
   const WQ *wbase = (const WQ *)a.words + q0 * 32 + lane;
   __syncthreads();
   const uint32_t bytes = (uint32_t)(n * sizeof(T));
@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
     }
     // operator stream: nothing of it depends on the column, so the first loads fly while the column arrives
     const WQ *wp = wbase;
-    WQ wa = __ldg(wp), wb = __ldg(wp + 32);  // two quads of slack behind every stream
+    WQ wa = __ldg(wp), wb = __ldg(wp + 32);  // four units of slack behind every stream
+    WQ wc = wa, wd = wa;
+    if constexpr (MODE == 3) { wc = __ldg(wp + 64); wd = __ldg(wp + 96); }
     uint4 m = t0 < t1 ? __ldg(mp) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
     mbar_wait(bar, phase);
     phase ^= 1u;
@@ -222,13 +224,15 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
         acc = colres_scale(__hiloint2double((int)m.y, (int)m.x) + dtab[m.w & 0xFFFFu], xs[m.z]);
       for (int kq = 0; kq < nquad; kq++) {
         const WQ w = wa;
-        wa = wb;
         wp += 32;
-        wb = __ldg(wp + 32);
         if constexpr (MODE == 3) {
-          colres_step16x2<T>(acc, w.x, xs_b, a.m0, a.m1);
-          colres_step16x2<T>(acc, w.y, xs_b, a.m0, a.m1);
+          // one 4-byte load (a single 128-byte line per warp) per two steps, four loads in flight
+          wa = wb; wb = wc; wc = wd;
+          wd = __ldg(wp + 96);
+          colres_step16x2<T>(acc, w, xs_b, a.m0, a.m1);
         } else {
+          wa = wb;
+          wb = __ldg(wp + 32);
           colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
           colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
           colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);

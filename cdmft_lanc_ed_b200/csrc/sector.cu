@@ -261,8 +261,8 @@ struct SchedHost {
   int32_t ntask = 0;
   int64_t nquads = 0;
   std::vector<int32_t> tbase, qbase;  // [nwarps+1] first task / first quad of each warp's stream
-  std::vector<uint32_t> meta;         // [ntask*32] uint4 per task and lane: f_row (8 B), row (-1 = none), mu | nquad << 16
-  std::vector<uint32_t> words;        // [(nquads+2)*32] uint4 (fmt 0,1) or uint2 (fmt 2) per quad and lane
+  std::vector<uint32_t> meta;         // [ntask*32] uint4 per task and lane: f_row (8 B), row (-1 = none), mu | units << 16
+  std::vector<uint32_t> words;        // [(nquads+4)*32] per unit and lane: uint4 = 4 steps (fmt 0,1,3) or uint32 = 2 steps (fmt 2)
 };
 
 static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
@@ -378,6 +378,7 @@ static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, c
     }
     out.tbase[nwarps] = (int32_t)t;
   }
+  const int spu = w16 ? 2 : 4;  // steps per unit
   std::vector<int32_t> qoff(ntask + 1, 0);
   for (int64_t t = 0; t < ntask; t++) {
     int kt = 0;
@@ -385,12 +386,12 @@ static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, c
       const int64_t idx = sorted_of_task[t] * per + q;
       if (idx < ngroups) kt = std::max(kt, K[order[idx]]);
     }
-    qoff[t + 1] = qoff[t] + (kt + 3) / 4;  // four steps per load (uint4 of 32-bit words / uint2 of 16-bit words)
+    qoff[t + 1] = qoff[t] + (kt + spu - 1) / spu;  // one load per unit: uint4 = 4 steps of 32-bit words, uint32 = 2 steps of 16-bit words
   }
   for (int w = 0; w <= nwarps; w++) out.qbase[w] = qoff[out.tbase[w]];
   out.nquads = qoff[ntask];
-  const size_t wpq = w16 ? 2 : 4;  // 32-bit registers per lane and quad
-  out.words.assign(((size_t)out.nquads + 2) * 32 * wpq, 0u);  // two quads of slack: the prefetch runs ahead unguarded
+  const size_t wpq = w16 ? 1 : 4;  // 32-bit registers per lane and unit
+  out.words.assign(((size_t)out.nquads + 4) * 32 * wpq, 0u);  // four units of slack: the prefetch runs ahead unguarded
   for (int64_t t = 0; t < ntask; t++) {
     const int nq = qoff[t + 1] - qoff[t];
     for (int q = 0; q < per; q++) {
@@ -405,10 +406,10 @@ static void build_schedule_host(int64_t n, const std::vector<int32_t> &rowptr, c
         memcpy(m, &f, 8);
         m[2] = valid ? (uint32_t)i : 0xFFFFFFFFu;
         m[3] = (valid && mu_row ? (mu_row[i] & 0xFFFFu) : 0u) | ((uint32_t)nq << 16);
-        for (int k = 0; k < nq * 4; k++) {
+        for (int k = 0; k < nq * spu; k++) {
           const uint32_t w = (g >= 0 && k < K[g]) ? steps[g][(size_t)k * G + r] : idle(r);
-          const size_t base = (((size_t)qoff[t] + k / 4) * 32 + lane) * wpq;
-          if (w16) out.words[base + (k & 3) / 2] |= w << ((k & 1) * 16);
+          const size_t base = (((size_t)qoff[t] + k / spu) * 32 + lane) * wpq;
+          if (w16) out.words[base] |= w << ((k & 1) * 16);
           else out.words[base + (k & 3)] = w;
         }
       }
