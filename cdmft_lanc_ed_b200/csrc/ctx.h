@@ -32,6 +32,24 @@ struct Sched {
   uint32_t *words = nullptr;    // [(nquads+2)*32] uint4 / uint2 per quad and lane; formats in sector.cu
 };
 
+// Column-resident kernel for columns that do not fit in shared memory (Ns = 18: 778 KB): the column is cut into
+// row blocks = runs of states sharing their top bits (K5: four blocks of <= 12 870 rows).  A CTA owns
+// (column, block): the block's rows are staged by TMA, entries whose source lies inside the block follow the
+// block's own edge-coloured schedule (relative indices), the others (hops that change the top bits) are
+// gathered from global memory / L2.  One Sched-like stream set per block, concatenated.
+struct ColBlk {
+  int32_t nblk = 0, nwarps = 0, fmt = 0, G = 0;
+  int64_t max_rows = 0;
+  bool even_blocks = false;   // every block starts and ends on an even row (needed for 8-byte elements: 16-byte aligned copies)
+  int4 *blk = nullptr;        // [nblk] {first row, rows, first task, first unit}
+  int32_t *tbase = nullptr;   // [nblk*(nwarps+1)] first task of each warp, relative to the block's first task
+  int32_t *qbase = nullptr;   // [nblk*(nwarps+1)] first unit of each warp's stream, relative to the block's first unit
+  uint32_t *meta = nullptr;   // [ntask*32] uint4: f_row, row relative to the block (-1 none), mu | units << 16
+  uint32_t *words = nullptr;  // in-block words (formats of Sched, indices relative to the block)
+  uint2 *toff = nullptr;      // [ntask] {first off-block step, off-block steps} of each task
+  uint32_t *woff = nullptr;   // [steps*32] off-block words: sign<<31 | row<<3 | code3 (fast) or row<<7 | id; see sector.cu
+};
+
 // Operator streams of the block-resident row pass (k_rowres, hxv.cu).  Columns (states of this spin) are cut
 // into blocks sharing their top bits; a CTA owns one block x 8 rows of the other spin's index, keeps that tile
 // in shared memory and runs, per warp task of 4 columns (one per 8-lane group), the in-block entries against
@@ -86,6 +104,7 @@ struct SpinOp {
   bool pk_swizzled = false;      // built for the column pass (slot swizzled with rel&7)
   // column-resident kernels: schedules for 16-byte (sc8) and 8-byte (sc16) vector elements
   Sched sc8, sc16;
+  ColBlk cb8, cb16;
   RowRes rr;
   bool sc_fast = false;          // real H with <= 2 distinct |coefficients|: sign and class bits instead of table ids
   double sc_mag[4] = {0.0, 0.0, 0.0, 0.0};  // |coefficient| classes of the fast decodes
@@ -116,6 +135,7 @@ struct Options {
   // shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass, 4/5 = rotating-slot tiles
   int64_t colpass_variant = 6;
   int64_t sched = 1;            // 1 = conflict-free edge-coloured schedule, 0 = natural CSR order (for comparison)
+  int64_t colres_rows = 0;      // > 0: force the block-split column-resident kernel with at most this many rows per block
   int64_t rowres_cols = 570;    // max columns of a block of the block-resident row pass ((cols+1) x 128 B of shared memory)
   int64_t rowpass_variant = 1;  // 1 = generic L2-slab kernel (default, fastest measured), 4 = block-resident shared-memory row pass
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)

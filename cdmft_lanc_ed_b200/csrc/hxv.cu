@@ -811,7 +811,10 @@ static int colpass_impl(const SpinOp &s, int64_t ncols, const double2 *v, double
   // 0/2 = shared-memory tiles, 4/5 = rotating-slot tiles
   int64_t var = ctx().opt.colpass_variant;
   if (var == 6) {
-    const int rc = launch_colres<double2>(s, ncols, v, out, dg);
+    // forced block split (tests) -> block-split kernel; else whole column; else block split for big columns
+    int rc = ctx().opt.colres_rows > 0 ? launch_colblk<double2>(s, ncols, v, out, dg) : kColresNA;
+    if (rc == kColresNA) rc = launch_colres<double2>(s, ncols, v, out, dg);
+    if (rc == kColresNA) rc = launch_colblk<double2>(s, ncols, v, out, dg);
     if (rc != kColresNA) return rc;
     var = 1;  // does not apply (DIRECT mode, column larger than shared memory): generic kernel
   }

@@ -118,6 +118,7 @@ __device__ __forceinline__ void colres_cfma(double2 &acc, double2 h, double2 x) 
 __device__ __forceinline__ void colres_cfma(double &acc, double2 h, double x) { acc = fma(h.x, x, acc); }
 __device__ __forceinline__ void colres_zero(double2 &a) { a = make_double2(0.0, 0.0); }
 __device__ __forceinline__ void colres_zero(double &a) { a = 0.0; }
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 colres_scale(double d, double2 x) { return make_double2(d * x.x, d * x.y); }
 __device__ __forceinline__ double colres_scale(double d, double x) { return d * x; }
 
@@ -246,6 +247,143 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Block-split column-resident kernel (ColBlk, ctx.h): columns larger than shared memory (Ns = 18).
+// Work item = (column, row block); items of one column are adjacent, so its blocks run on neighbouring SMs at
+// the same time and the off-block gathers hit L2.  In-block entries: the block's edge-coloured schedule against
+// shared memory, exactly as in k_colres; off-block entries: lane-parallel stream, scattered 16-byte (8-byte)
+// gathers from the column in global memory.  MODE as in k_colres (16-bit words are not used here).
+// ------------------------------------------------------------------------------------
+struct ColBlkArgs {
+  const int4 *blk;
+  const int32_t *tbase, *qbase;
+  const uint4 *meta;
+  const uint32_t *words;
+  const uint2 *toff;
+  const uint32_t *woff;
+  const double2 *coef;
+  double m0, m1, m2, m3;
+  int nblk, nwarps;
+};
+
+template <int MODE>
+__device__ __forceinline__ bool colblk_on(uint32_t w) { return MODE >= 2 ? (w != 0xFFFFFFFFu) : ((w & 127u) != 0u); }
+template <typename T, int MODE>
+__device__ __forceinline__ T colblk_off_load(uint32_t w, const T *__restrict__ vc) {
+  T x;
+  colres_zero(x);
+  if (colblk_on<MODE>(w)) x = __ldg(vc + (MODE >= 2 ? ((w & 0x7FFFFFFFu) >> 3) : (w >> 7)));
+  return x;
+}
+template <typename T, int MODE>
+__device__ __forceinline__ void colblk_off_apply(T &acc, uint32_t w, T x, const char *coef_b, double m0, double m1, double m2,
+                                                 double m3) {
+  if (!colblk_on<MODE>(w)) return;
+  if (MODE >= 2) {
+    const double ma = (w & 1u) ? m1 : m0, mb = (w & 1u) ? m3 : m2;
+    if (MODE == 4 && (w & 4u)) x = colres_times_i(x);
+    colres_fma(acc, colres_signed((MODE == 4 && (w & 2u)) ? mb : ma, w & 0x80000000u), x);
+  } else if (MODE == 1) {
+    colres_fma(acc, *(const double *)(coef_b + ((w & 127u) << 4)), x);
+  } else {
+    colres_cfma(acc, *(const double2 *)(coef_b + ((w & 127u) << 4)), x);
+  }
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_colblk(int64_t n, int64_t ncols, const T *__restrict__ v, T *__restrict__ out,
+                                                     ColBlkArgs a, DiagArgs dg) {
+  constexpr int G = sizeof(T) == 16 ? 8 : 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bar = (uint64_t *)smem_raw;
+  double2 *coef = (double2 *)(smem_raw + 128);
+  double *dtab = (double *)(smem_raw + 128 + 2048);
+  const int ndt = dg.enabled ? (1 << dg.nimp) : 0;
+  T *xs = (T *)(smem_raw + 128 + 2048 + (((size_t)ndt * 8 + 127) & ~(size_t)127));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  if (threadIdx.x < 128) coef[threadIdx.x] = MODE >= 2 ? make_double2(0.0, 0.0) : a.coef[threadIdx.x];
+  __syncthreads();
+  const char *xs_b = (const char *)xs;
+  const char *coef_b = (const char *)coef;
+  uint32_t phase = 0;
+  const int64_t nitems = ncols * a.nblk;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t c = item / a.nblk;
+    const int b = (int)(item - c * a.nblk);
+    const int4 bd = __ldg(a.blk + b);
+    const int g0 = bd.x, ng = bd.y;
+    const int npad = (ng + G - 1) / G * G;
+    const T *vc = v + c * n;
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)ng * (uint32_t)sizeof(T);
+      mbar_expect_tx(bar, bytes);
+      const char *src = (const char *)(vc + g0);
+      for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s((char *)xs + off, src + off, min(32768u, bytes - off), bar);
+    }
+    for (int k = ng + threadIdx.x; k < npad + G; k += blockDim.x) colres_zero(xs[k]);  // idle lanes gather these
+    for (int mu = threadIdx.x; mu < ndt; mu += blockDim.x) {
+      const int64_t cg = dg.coloff + c;
+      double val = __ldg(dg.f_col + cg);
+      uint32_t md = (uint32_t)__ldg(dg.map_col + cg) & ((1u << dg.nimp) - 1u);
+      while (md) {
+        const int bb = __ffs(md) - 1;
+        md &= md - 1;
+        val += __ldg(dg.cross_tab + ((int64_t)bb << dg.nimp) + mu);
+      }
+      dtab[mu] = val;
+    }
+    const int t0 = bd.z + __ldg(a.tbase + b * (a.nwarps + 1) + warp), t1 = bd.z + __ldg(a.tbase + b * (a.nwarps + 1) + warp + 1);
+    const uint4 *wp = (const uint4 *)a.words + ((int64_t)bd.w + __ldg(a.qbase + b * (a.nwarps + 1) + warp)) * 32 + lane;
+    const uint4 *mp = a.meta + (int64_t)t0 * 32 + lane;
+    uint4 wa = __ldg(wp), wb = __ldg(wp + 32);
+    uint4 m = t0 < t1 ? __ldg(mp) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncthreads();
+    T *oc = out + c * n + g0;
+    for (int t = t0; t < t1; t++) {
+      uint4 mnext = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+      if (t + 1 < t1) mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
+      const uint2 to = __ldg(a.toff + t);
+      const int nquad = (int)(m.w >> 16);
+      const bool valid = m.z != 0xFFFFFFFFu;
+      T acc;
+      colres_zero(acc);
+      if (dg.enabled && valid)
+        acc = colres_scale(__hiloint2double((int)m.y, (int)m.x) + dtab[m.w & 0xFFFFu], xs[m.z]);
+      {  // off-block sources (hops that change the top bits): scattered gathers from the column in global memory / L2
+        const uint32_t *wo = a.woff + (int64_t)to.x * 32 + lane;
+        const int noff = (int)to.y;
+        int k = 0;
+        for (; k + 2 <= noff; k += 2) {
+          const uint32_t w0 = __ldg(wo + k * 32), w1 = __ldg(wo + k * 32 + 32);
+          const T x0 = colblk_off_load<T, MODE>(w0, vc), x1 = colblk_off_load<T, MODE>(w1, vc);
+          colblk_off_apply<T, MODE>(acc, w0, x0, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colblk_off_apply<T, MODE>(acc, w1, x1, coef_b, a.m0, a.m1, a.m2, a.m3);
+        }
+        if (k < noff) {
+          const uint32_t w0 = __ldg(wo + k * 32);
+          colblk_off_apply<T, MODE>(acc, w0, colblk_off_load<T, MODE>(w0, vc), coef_b, a.m0, a.m1, a.m2, a.m3);
+        }
+      }
+      for (int kq = 0; kq < nquad; kq++) {
+        const uint4 w = wa;
+        wp += 32;
+        wa = wb;
+        wb = __ldg(wp + 32);
+        colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+        colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+        colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+        colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+      }
+      if (valid) oc[m.z] = acc;
+      m = mnext;
+    }
+    __syncthreads();  // every gather of this block is done before the next bulk copy lands
+  }
+}
+
 // shared memory the kernel needs for a column of n elements of elem bytes
 inline size_t colres_smem(int64_t n, int elem, int nimp_diag) {
   const size_t ndt = nimp_diag >= 0 ? ((size_t)1 << nimp_diag) : 0;
@@ -294,5 +432,34 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   return 0;
 }
 
+
+template <typename T>
+inline int launch_colblk(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const ColBlk &cb = sizeof(T) == 16 ? s.cb8 : s.cb16;
+  if (c.mode != CDMFT_B200_SPARSE || !cb.words || cb.nblk <= 0) return kColresNA;
+  if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h || !cb.even_blocks)) return kColresNA;  // 16-byte aligned bulk copies
+  if (dg.enabled && dg.f_row != s.f) return kColresNA;
+  const size_t smem = colres_smem(cb.max_rows, (int)sizeof(T), dg.enabled ? dg.nimp : -1);
+  if (smem > 232448) return kColresNA;
+  ColBlkArgs a{};
+  a.blk = cb.blk; a.tbase = cb.tbase; a.qbase = cb.qbase; a.meta = (const uint4 *)cb.meta; a.words = cb.words;
+  a.toff = cb.toff; a.woff = cb.woff; a.coef = s.coef;
+  a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1]; a.m2 = s.sc_mag[2]; a.m3 = s.sc_mag[3];
+  a.nblk = cb.nblk; a.nwarps = cb.nwarps;
+  void (*kern)(int64_t, int64_t, const T *, T *, ColBlkArgs, DiagArgs) =
+      cb.fmt == 3 ? k_colblk<T, 4> : (cb.fmt == 1 ? k_colblk<T, 2> : (c.real_h ? k_colblk<T, 1> : k_colblk<T, 0>));
+  static std::map<const void *, size_t> max_smem;
+  size_t &ms = max_smem[(const void *)kern];
+  if (smem > ms) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ms = smem;
+  }
+  const int threads = cb.nwarps * 32;
+  const int64_t grid = std::min<int64_t>(ncols * cb.nblk, (int64_t)c.sm_count);
+  kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);
+  c.launches++;
+  return 0;
+}
 
 }  // namespace cb

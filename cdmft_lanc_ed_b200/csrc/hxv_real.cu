@@ -103,7 +103,12 @@ int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, c
   if (ncols <= 0 || s.n <= 0) return 0;
   const bool direct = c.mode == CDMFT_B200_DIRECT;
   prof_begin(0);
-  const int rc = c.opt.colpass_variant == 6 ? launch_colres<double>(s, ncols, v, out, dg) : kColresNA;
+  int rc = kColresNA;
+  if (c.opt.colpass_variant == 6) {
+    if (c.opt.colres_rows > 0) rc = launch_colblk<double>(s, ncols, v, out, dg);
+    if (rc == kColresNA) rc = launch_colres<double>(s, ncols, v, out, dg);
+    if (rc == kColresNA) rc = launch_colblk<double>(s, ncols, v, out, dg);
+  }
   if (rc != 0 && rc != kColresNA) { prof_end(); return rc; }
   if (rc == kColresNA) {
     dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((ncols + 3) / 4));

@@ -347,6 +347,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "sched") c.opt.sched = value;
   else if (k == "fuse_dot") c.opt.fuse_dot = value;
   else if (k == "fast4") c.opt.fast4 = value;
+  else if (k == "colres_rows") c.opt.colres_rows = value;
   else if (k == "rowres_cols") c.opt.rowres_cols = value;
   else if (k == "profile") c.profile = value != 0;
   else return fail("set_option: unknown key %s", key);

@@ -531,6 +531,132 @@ static int build_rowres(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// Block-split schedules (ColBlk in ctx.h) for columns larger than shared memory: one build_schedule_host per
+// row block on the in-block part of the CSR (relative indices) plus, per warp task, the off-block entries of
+// its 32 rows as a lane-parallel stream.  code3 of an off-block fast word: class (2 bits) | imaginary << 2.
+// ------------------------------------------------------------------------------------
+static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
+                        const std::vector<uint8_t> &code, int G, int fmt, bool natural, int64_t cap_rows,
+                        const double *f_row, const uint32_t *mu_row) {
+  Ctx &c = ctx();
+  int t = 0;
+  for (; t <= ns; t++) {
+    int64_t mx = 0;
+    for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, op.npart - k));
+    if (mx <= cap_rows) break;
+  }
+  std::vector<int4> blk;
+  std::vector<int32_t> tbase, qbase;
+  std::vector<uint32_t> meta, words, woff;
+  std::vector<uint2> toff;
+  const int nwarps = 32;
+  const bool fastw = fmt == 1 || fmt == 3;  // fmt 2 (16-bit) is not used here
+  const uint32_t NONE = fastw ? 0xFFFFFFFFu : 0u;
+  std::vector<int32_t> bstart;  // first row of every block + the end
+  {
+    int64_t st = 0;
+    for (uint32_t P = 0; P < (1u << t); P++) {
+      const int64_t ng = binom64(ns - t, op.npart - __builtin_popcount(P));
+      if (ng <= 0) continue;
+      bstart.push_back((int32_t)st);
+      st += ng;
+    }
+    bstart.push_back((int32_t)st);
+  }
+  int64_t start = 0, mxrows = 0, task0 = 0, unit0 = 0;
+  for (uint32_t P = 0; P < (1u << t); P++) {
+    const int64_t ng = binom64(ns - t, op.npart - __builtin_popcount(P));
+    if (ng <= 0) continue;
+    const int64_t g0 = start;
+    start += ng;
+    mxrows = std::max(mxrows, ng);
+    // in-block sub-matrix with relative indices
+    std::vector<int32_t> rp(ng + 1, 0), cl;
+    std::vector<uint8_t> cd;
+    for (int64_t i = 0; i < ng; i++) {
+      for (int32_t p = rowptr[g0 + i]; p < rowptr[g0 + i + 1]; p++)
+        if (col[p] >= g0 && col[p] < g0 + ng) { cl.push_back((int32_t)(col[p] - g0)); cd.push_back(code[p]); }
+      rp[i + 1] = (int32_t)cl.size();
+    }
+    SchedHost sh;
+    build_schedule_host(ng, rp, cl, cd, G, fmt, natural, nwarps, f_row ? f_row + g0 : nullptr, mu_row ? mu_row + g0 : nullptr, sh);
+    blk.push_back(make_int4((int)g0, (int)ng, (int)task0, (int)unit0));
+    tbase.insert(tbase.end(), sh.tbase.begin(), sh.tbase.end());
+    qbase.insert(qbase.end(), sh.qbase.begin(), sh.qbase.end());
+    meta.insert(meta.end(), sh.meta.begin(), sh.meta.end());
+    words.insert(words.end(), sh.words.begin(), sh.words.end());
+    // off-block streams, lane-parallel per task.  Steps are aligned by SOURCE BLOCK: all lanes of a step gather
+    // from the same block, entries in ascending order, so that neighbouring rows taking the same hop read
+    // neighbouring sources (a hop between two top bits keeps the in-block index: perfectly coalesced).
+    auto block_of = [&](int32_t j) -> int {
+      int lo = 0, hi = (int)bstart.size() - 2;
+      while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (bstart[mid] <= j) lo = mid; else hi = mid - 1; }
+      return lo;
+    };
+    const int nbtot = (int)bstart.size() - 1;
+    std::vector<int> cnt((size_t)32 * nbtot), base(nbtot);
+    for (int32_t tk = 0; tk < sh.ntask; tk++) {
+      std::fill(cnt.begin(), cnt.end(), 0);
+      for (int lane = 0; lane < 32; lane++) {
+        const uint32_t rel = sh.meta[((size_t)tk * 32 + lane) * 4 + 2];
+        if (rel == 0xFFFFFFFFu) continue;
+        for (int32_t p = rowptr[g0 + rel]; p < rowptr[g0 + rel + 1]; p++)
+          if (!(col[p] >= g0 && col[p] < g0 + ng)) cnt[(size_t)lane * nbtot + block_of(col[p])]++;
+      }
+      int noff = 0;
+      for (int bb = 0; bb < nbtot; bb++) {
+        int mxc = 0;
+        for (int lane = 0; lane < 32; lane++) mxc = std::max(mxc, cnt[(size_t)lane * nbtot + bb]);
+        base[bb] = noff;
+        noff += mxc;
+      }
+      const size_t ob = woff.size() / 32;
+      toff.push_back(make_uint2((uint32_t)ob, (uint32_t)noff));
+      woff.resize(woff.size() + (size_t)noff * 32, NONE);
+      for (int lane = 0; lane < 32; lane++) {
+        const uint32_t rel = sh.meta[((size_t)tk * 32 + lane) * 4 + 2];
+        if (rel == 0xFFFFFFFFu) continue;
+        std::vector<int> fill(nbtot, 0);
+        for (int32_t p = rowptr[g0 + rel]; p < rowptr[g0 + rel + 1]; p++) {
+          if (col[p] >= g0 && col[p] < g0 + ng) continue;
+          const int bb = block_of(col[p]);
+          const uint32_t cdp = code[p];
+          uint32_t w;
+          if (fmt == 3) w = ((cdp & 1u) << 31) | ((uint32_t)col[p] << 3) | ((cdp >> 1) & 3u) | (((cdp >> 3) & 1u) << 2);
+          else if (fmt == 1) w = ((cdp & 1u) << 31) | ((uint32_t)col[p] << 3) | ((cdp >> 1) & 1u);
+          else w = ((uint32_t)col[p] << 7) | cdp;
+          woff[(ob + base[bb] + fill[bb]) * 32 + lane] = w;
+          fill[bb]++;
+        }
+      }
+    }
+    task0 += sh.ntask;
+    unit0 += (int64_t)(sh.words.size() / (32 * 4));  // fmt 0/1/3: one uint4 per unit and lane (slack included)
+  }
+  if (start != op.n) return fail("internal: column blocks do not cover the sector");
+  woff.resize(woff.size() + 64, NONE);
+  cb.nblk = (int32_t)blk.size(); cb.nwarps = nwarps; cb.fmt = fmt; cb.G = G; cb.max_rows = mxrows;
+  cb.even_blocks = true;
+  for (auto &q : blk) cb.even_blocks = cb.even_blocks && !(q.x & 1) && !(q.y & 1);
+  CB_CHECK(dev_alloc(&cb.blk, (int64_t)blk.size()));
+  CB_CHECK(dev_alloc(&cb.tbase, (int64_t)tbase.size()));
+  CB_CHECK(dev_alloc(&cb.qbase, (int64_t)qbase.size()));
+  CB_CHECK(dev_alloc(&cb.meta, (int64_t)meta.size()));
+  CB_CHECK(dev_alloc(&cb.words, (int64_t)words.size()));
+  CB_CHECK(dev_alloc(&cb.toff, (int64_t)toff.size()));
+  CB_CHECK(dev_alloc(&cb.woff, (int64_t)woff.size()));
+  CB_CUDA(cudaMemcpyAsync(cb.blk, blk.data(), blk.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.tbase, tbase.data(), tbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.qbase, qbase.data(), qbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.words, words.data(), words.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.toff, toff.data(), toff.size() * sizeof(uint2), cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaMemcpyAsync(cb.woff, woff.data(), woff.size() * 4, cudaMemcpyHostToDevice, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
                   double const_add, bool want_csr, bool pack_swizzled) {
   Ctx &c = ctx();
@@ -769,6 +895,35 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
           CB_CHECK(upload_schedule(op.sc16, sh));
         }
       }
+      // block-split schedules: columns larger than shared memory (or forced small blocks for the tests)
+      {
+        const int64_t forced = c.opt.colres_rows;
+        const int fmtb = fast4 && c.opt.fast4 ? 3 : (fast ? 1 : 0);
+        const std::vector<uint8_t> &codeb = fmtb == 3 ? code4 : (fast ? code : ids);
+        std::vector<double> hf;
+        std::vector<uint32_t> hmu;
+        auto need_rowdata = [&]() -> int {
+          if (!hf.empty()) return 0;
+          hf.resize(op.n);
+          std::vector<int32_t> hmap(op.n);
+          hmu.resize(op.n);
+          CB_CUDA(cudaMemcpy(hf.data(), op.f, op.n * 8, cudaMemcpyDeviceToHost));
+          CB_CUDA(cudaMemcpy(hmap.data(), op.map, op.n * 4, cudaMemcpyDeviceToHost));
+          for (int64_t i = 0; i < op.n; i++) hmu[i] = (uint32_t)hmap[i] & ((1u << c.nimp) - 1u);
+          return 0;
+        };
+        const int64_t room = 232448 - 128 - 2048 - (((int64_t)8 << c.nimp) + 127) / 128 * 128;
+        if (!hrp.empty() && (forced > 0 || (int64_t)(op.n + 32) * 16 > room)) {
+          CB_CHECK(need_rowdata());
+          const int64_t cap = forced > 0 ? std::max<int64_t>(8, forced) : room / 16 - 32;
+          CB_CHECK(build_colblk(op, op.cb8, ns, hrp, hcol, codeb, 8, fmtb, c.opt.sched == 0, cap, hf.data(), hmu.data()));
+        }
+        if (!hrp.empty() && op.real_h && (forced > 0 || (int64_t)(op.n + 32) * 8 > room)) {
+          CB_CHECK(need_rowdata());
+          const int64_t cap = forced > 0 ? std::max<int64_t>(16, forced) : room / 8 - 32;
+          CB_CHECK(build_colblk(op, op.cb16, ns, hrp, hcol, codeb, 16, fmtb, c.opt.sched == 0, cap, hf.data(), hmu.data()));
+        }
+      }
       cudaFree(d_ids);
       cudaFree(d_rounds);
     }
@@ -785,6 +940,9 @@ void free_spin_op(SpinOp &op) {
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
   dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
   dev_free(op.rr.blocks); dev_free(op.rr.tbase); dev_free(op.rr.task); dev_free(op.rr.task_col); dev_free(op.rr.win); dev_free(op.rr.woff);
+  for (ColBlk *cb : {&op.cb8, &op.cb16}) {
+    dev_free(cb->blk); dev_free(cb->tbase); dev_free(cb->qbase); dev_free(cb->meta); dev_free(cb->words); dev_free(cb->toff); dev_free(cb->woff);
+  }
   for (Sched *sc : {&op.sc8, &op.sc16}) { dev_free(sc->tbase); dev_free(sc->qbase); dev_free(sc->meta); dev_free(sc->words); }
   op = SpinOp();
 }

@@ -248,6 +248,10 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     dict(rowpass_variant=4, rowres_cols=1760),                 # ... one block
     dict(colpass_variant=6, sched=1),                          # column-resident kernel, edge-coloured schedule (default)
     dict(colpass_variant=6, sched=0),                          # ... natural CSR order
+    dict(colpass_variant=6, colres_rows=40),                   # block-split column-resident kernel (Ns=18 path), forced small blocks
+    dict(colpass_variant=6, colres_rows=9, sched=0),
+    dict(colpass_variant=6, colres_rows=130, force_sharded=1),
+    dict(colpass_variant=6, colres_rows=40, fast4=0),
     dict(colpass_variant=6, fast4=0),                          # ... coefficient-table decode instead of sign/class/phase bits
     dict(colpass_variant=6, force_sharded=1),                  # ... on both spins (transposed layout)
     dict(colpass_variant=1, rowpass_variant=1, col_batch=1),   # generic global-gather kernels
@@ -275,7 +279,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=6, sched=1, fast4=1, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
+    defaults = dict(colpass_variant=6, sched=1, fast4=1, colres_rows=0, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)
@@ -395,3 +399,31 @@ def test_real_mode_krylov_on_sharded_layout(oracle_lib, P):
     finally:
         E.set_option("real_lanczos", 1)
         E.ed_finalize()
+
+
+@pytest.mark.parametrize("rows", [12, 64, 300])
+def test_block_split_column_kernel_krylov(ed, oracle_lib, rows):
+    """The block-split column-resident kernel (columns larger than shared memory, Ns=18) forced onto small
+    sectors through colres_rows: H x v and the Krylov drivers (complex and real vectors) against the oracle."""
+    ed.set_option("colres_rows", rows)
+    try:
+        for mdl, (nup, ndw) in [(models.hm2x2(2), (6, 6)), (models.hm2x2(2), (4, 7)), (models.bhz2(1), (3, 3)),
+                                (models.random_model(2, 2, 1, seed=4), (4, 3))]:
+            orc = oracle_lib.Oracle(mdl)
+            ed.ed_set_model(mdl)
+            isec = models.get_sector(mdl.ns, nup, ndw)
+            n = ed.build_Hv_sector(isec, True)
+            orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+            v = _rand_vec(n, seed=rows + isec)
+            assert _relerr(ed.hxv(v), orc.hxv(v)) < RTOL, (mdl.name, rows)
+            for real in (True, False):
+                v0 = _rand_vec(n, seed=5, real=real)
+                nd, a, b = ed.sp_lanc_tridiag(v0, 25)
+                ond, oa, ob = orc.lanc_tridiag(v0, 25)
+                assert nd == ond
+                assert np.abs(a[:20] - oa[:20]).max() <= RTOL * np.abs(oa[:20]).max(), (mdl.name, rows, real)
+                assert np.abs(b[:20] - ob[:20]).max() <= RTOL * np.abs(ob[:20]).max(), (mdl.name, rows, real)
+            ed.delete_Hv_sector()
+            orc.delete_hv_sector()
+    finally:
+        ed.set_option("colres_rows", 0)
