@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_active_ranks", "cdmft_b200_hxv", "cdmft_b200_hxv64", "cdmft_b200_get_sector_map",
     "cdmft_b200_get_csr_nnz", "cdmft_b200_get_csr", "cdmft_b200_get_diag", "cdmft_b200_get_sparse_map",
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
-    "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host",
+    "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
 ]
 
 
@@ -406,3 +406,57 @@ def add_to_lanczos_gf_normal(vnorm2, Ei, alanc, blanc, isign, zeta, wm, g):
                                                      C.c_double(zeta), C.c_int32(wm.size), _ptr(wm), _ptr(g), _ptr(poles),
                                                      _ptr(weights)))
     return poles, weights
+
+
+# --------------------------------------------------------------------------------------
+# local observables (ED_OBSERVABLES.f90:94-236)
+# --------------------------------------------------------------------------------------
+def imp_weights(vec, nimp: int) -> np.ndarray:
+    """W[mu, md] = sum over bath configurations of |vec|^2 for impurity bits (mu, md); vec lives in the active sector."""
+    n = int(vec.shape[0]) if hasattr(vec, "shape") else len(vec)
+    w = np.zeros((1 << nimp) * (1 << nimp))
+    _chk(load_library().cdmft_b200_imp_weights(C.c_int64(n), _ptr(vec), _ptr(w)))
+    return w.reshape(1 << nimp, 1 << nimp).T.copy()  # [mu, md]
+
+
+def observables_from_weights(W: np.ndarray, nlat: int, norb: int, peso: float = 1.0) -> dict:
+    """The reference's master loop (ED_OBSERVABLES.f90:120-192) evaluated on the impurity-configuration weights:
+    gs_weight = peso*W[mu, md], nup/ndw = bits imp_state_index(ilat,iorb)-1 of mu/md.  Fortran-ordered arrays."""
+    nimp = nlat * norb
+    nmu = 1 << nimp
+    out = {k: np.zeros((nlat, norb), order="F") for k in ("dens_up", "dens_dw", "docc", "magz")}
+    out["s2tot"] = np.zeros(nlat)
+    out["sz2"] = np.zeros((nlat, nlat, norb, norb), order="F")
+    out["n2"] = np.zeros((nlat, nlat, norb, norb), order="F")
+    bits = np.array([[(m >> p) & 1 for p in range(nimp)] for m in range(nmu)], dtype=float)  # [config, pos]
+    pos = lambda il, io: io + il * norb  # imp_state_index - 1
+    for mu in range(nmu):
+        for md in range(nmu):
+            w = peso * W[mu, md]
+            if w == 0.0:
+                continue
+            nu = np.array([[bits[mu, pos(il, io)] for io in range(norb)] for il in range(nlat)])
+            nd = np.array([[bits[md, pos(il, io)] for io in range(norb)] for il in range(nlat)])
+            sz, nt = (nu - nd) / 2.0, nu + nd
+            out["dens_up"] += nu * w
+            out["dens_dw"] += nd * w
+            out["docc"] += nu * nd * w
+            out["magz"] += (nu - nd) * w
+            out["s2tot"] += sz.sum(axis=1) ** 2 * w
+            for il in range(nlat):
+                for io in range(norb):
+                    out["sz2"][il, il, io, io] += sz[il, io] ** 2 * w
+                    out["n2"][il, il, io, io] += nt[il, io] ** 2 * w
+                    for jl in range(nlat):
+                        for jo in range(io + 1, norb):
+                            out["sz2"][il, jl, io, jo] += sz[il, io] * sz[jl, jo] * w
+                            out["sz2"][il, jl, jo, io] += sz[il, jo] * sz[jl, io] * w
+                            out["n2"][il, jl, io, jo] += nt[il, io] * nt[jl, jo] * w
+                            out["n2"][il, jl, jo, io] += nt[il, jo] * nt[jl, io] * w
+    out["dens"] = out["dens_up"] + out["dens_dw"]
+    return out
+
+
+def lanc_observables(vec, nlat: int, norb: int, peso: float = 1.0) -> dict:
+    """lanc_observables for one eigenstate of the active sector (weights on the device, formulas on the host)."""
+    return observables_from_weights(imp_weights(vec, nlat * norb), nlat, norb, peso)

@@ -105,6 +105,13 @@ MODULE ED_HAMILTONIAN_B200
        integer(c_int32_t) :: ndone
        integer(c_int) :: rc
      end function c_lanc_tridiag
+     function c_imp_weights(nloc, vec, w) bind(C, name="cdmft_b200_imp_weights") result(rc)
+       import :: c_int, c_int64_t, c_double, c_double_complex
+       integer(c_int64_t), value :: nloc
+       complex(c_double_complex) :: vec(*)
+       real(c_double) :: w(*)
+       integer(c_int) :: rc
+     end function c_imp_weights
   end interface
 
   ! contiguous copies handed to C (must outlive set_model only: the library copies them)
@@ -237,5 +244,16 @@ contains
     call check(c_lanc_tridiag(int(size(vin), c_int64_t), vin, int(size(alanc), c_int32_t), thr, alanc, blanc, ndone), &
          "sp_lanc_tridiag")
   end subroutine b200_lanc_tridiag
+
+  !> replaces the master-only O(Dim) loop of lanc_observables (ED_OBSERVABLES.f90:120-192): the device reduces
+  !> gs_weight = |state_cvec|^2 onto the impurity configurations (mu,md) of the up / dw Fock states; the caller
+  !> then runs the reference's own accumulation lines over the 4**Nimp table instead of over Dim states:
+  !>   do md=0,2**Nimp-1; do mu=0,2**Nimp-1; gs_weight=peso*W(mu,md); IbUp=Bdecomp(mu,Nimp); IbDw=Bdecomp(md,Nimp); ...
+  !> vec = the local shard of an eigenvector of the ACTIVE sector (build_Hv_sector(isector) first).
+  subroutine b200_imp_weights(vec, W)
+    complex(8), dimension(:) :: vec
+    real(8), dimension(0:,0:) :: W   ! (0:2**Nimp-1, 0:2**Nimp-1) = (mu, md)
+    call check(c_imp_weights(int(size(vec), c_int64_t), vec, W), "lanc_observables")
+  end subroutine b200_imp_weights
 
 END MODULE ED_HAMILTONIAN_B200

@@ -168,6 +168,14 @@ int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlan
                                  const double *blanc, int32_t isign, double zeta, int32_t lmats,
                                  const double *wm, double *g, double *poles, double *weights);
 
+/* ---- local observables (ED_OBSERVABLES.f90:94-236, lanc_observables) --------------------------- */
+/* w[mu + md*2^Nimp] = sum over all basis states whose up / dw Fock states have the impurity bits mu / md of
+ * |vec|^2 (4^Nimp doubles, host).  Every observable of the reference's master loop (:120-192: dens, dens_up,
+ * dens_dw, docc, magz, s2tot, sz2, n2) is a weighted sum over this table -- the host layer evaluates the
+ * reference's formulas on it.  vec = local shard (host or device) of a vector of the ACTIVE sector; with
+ * sharded vectors the tables are all-reduced so every rank receives the full one.  Nimp <= 8. */
+int cdmft_b200_imp_weights(int64_t nloc, const void *vec, double *w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1082,6 +1082,75 @@ int32_t edo_add_to_lanczos_gf(edo_c64 vnorm2, double ei, int32_t nlanc, const do
   return 0;
 }
 
+/* ---- lanc_observables: local observables of one eigenstate --------------------------------------
+ * ED_OBSERVABLES.f90:94-236 (the master-only loop :120-192): for every basis state i of the sector
+ * gs_weight = peso*|vec(i)|^2, impurity occupations from Bdecomp of the up / dw Fock states
+ * (imp_state_index(ilat,iorb) = iorb + (ilat-1)*Norb), then
+ *   dens_up, dens_dw, docc = <n_up n_dw>, magz = <n_up - n_dw>            [Nlat,Norb]
+ *   s2tot(ilat) = <(sum_orb sz(ilat,orb))^2>                                 [Nlat]
+ *   sz2, n2 (ilat,jlat,iorb,jorb): the diagonal (ilat,ilat,iorb,iorb) and, for every jlat and jorb > iorb,
+ *   the (iorb,jorb) and (jorb,iorb) pairs exactly as the reference loops :172-186 fill them (other
+ *   entries stay zero).  Arrays are Fortran-ordered; all outputs are ACCUMULATED (+=) like the
+ *   reference's sum over the eigenstates of state_list. */
+int32_t edo_lanc_observables(int32_t ns, int32_t nlat, int32_t norb, int32_t isector, const edo_c64 *vec, double peso,
+                             double *dens_up, double *dens_dw, double *docc, double *magz, double *s2tot, double *sz2,
+                             double *n2) {
+  int32_t nup_s, ndw_s;
+  edo_get_nup_ndw(ns, isector, &nup_s, &ndw_s);
+  int64_t dimup, dimdw;
+  const int64_t dim = edo_get_dim(ns, isector, &dimup, &dimdw);
+  int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimup), *mapd = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimdw);
+  if (!mapu || !mapd) { free(mapu); free(mapd); FAIL("edo_lanc_observables: out of memory"); }
+  edo_build_sector_map(ns, nup_s, mapu);
+  edo_build_sector_map(ns, ndw_s, mapd);
+  const int nimp = nlat * norb;
+  double nu[64], nd[64], sz[64], nt[64];
+  if (nimp > 64) { free(mapu); free(mapd); FAIL("edo_lanc_observables: Nimp > 64"); }
+#define IX2(il, io) ((il) + nlat * (io))                                         /* (ilat,iorb), 0-based */
+#define IX4(il, jl, io, jo) ((il) + nlat * ((jl) + nlat * ((io) + norb * (jo)))) /* (ilat,jlat,iorb,jorb) */
+  for (int64_t i = 0; i < dim; i++) {
+    const int64_t iup = i % dimup, idw = i / dimup; /* state2indices, ED_SETUP.f90:547-560 */
+    const uint32_t mup = (uint32_t)mapu[iup], mdw = (uint32_t)mapd[idw];
+    const double w = peso * (creal(vec[i]) * creal(vec[i]) + cimag(vec[i]) * cimag(vec[i]));
+    for (int il = 0; il < nlat; il++)
+      for (int io = 0; io < norb; io++) {
+        const int pos = io + il * norb; /* imp_state_index - 1 */
+        nu[IX2(il, io)] = (double)((mup >> pos) & 1u);
+        nd[IX2(il, io)] = (double)((mdw >> pos) & 1u);
+        sz[IX2(il, io)] = (nu[IX2(il, io)] - nd[IX2(il, io)]) / 2.0;
+        nt[IX2(il, io)] = nu[IX2(il, io)] + nd[IX2(il, io)];
+      }
+    for (int il = 0; il < nlat; il++) {
+      double ssum = 0.0;
+      for (int io = 0; io < norb; io++) {
+        dens_up[IX2(il, io)] += nu[IX2(il, io)] * w;
+        dens_dw[IX2(il, io)] += nd[IX2(il, io)] * w;
+        docc[IX2(il, io)] += nu[IX2(il, io)] * nd[IX2(il, io)] * w;
+        magz[IX2(il, io)] += (nu[IX2(il, io)] - nd[IX2(il, io)]) * w;
+        ssum += sz[IX2(il, io)];
+      }
+      s2tot[il] += ssum * ssum * w;
+    }
+    for (int il = 0; il < nlat; il++)
+      for (int io = 0; io < norb; io++) {
+        sz2[IX4(il, il, io, io)] += sz[IX2(il, io)] * sz[IX2(il, io)] * w;
+        n2[IX4(il, il, io, io)] += nt[IX2(il, io)] * nt[IX2(il, io)] * w;
+        for (int jl = 0; jl < nlat; jl++)
+          for (int jo = io + 1; jo < norb; jo++) {
+            sz2[IX4(il, jl, io, jo)] += sz[IX2(il, io)] * sz[IX2(jl, jo)] * w;
+            sz2[IX4(il, jl, jo, io)] += sz[IX2(il, jo)] * sz[IX2(jl, io)] * w;
+            n2[IX4(il, jl, io, jo)] += nt[IX2(il, io)] * nt[IX2(jl, jo)] * w;
+            n2[IX4(il, jl, jo, io)] += nt[IX2(il, jo)] * nt[IX2(jl, io)] * w;
+          }
+      }
+  }
+#undef IX2
+#undef IX4
+  free(mapu);
+  free(mapd);
+  return 0;
+}
+
 int32_t edo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

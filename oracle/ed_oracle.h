@@ -137,6 +137,10 @@ int32_t edo_tridiag_eigh(int32_t n, double *d, double *e /* e[1..n-1] used, e[0]
 /* ---- Green's function pieces (ED_GF_NORMAL.f90:123-306, 531-903, 915-975) ---- */
 /* vvinit = sum_k coef[k] * op_k |state>, op = c (iop=-1) or cdg (iop=+1) on orbital pos (1-based),
  * spin 1=up 2=dw. state lives in isector, result in jsector (caller sizes it, zero-filled here). */
+/* lanc_observables master loop (ED_OBSERVABLES.f90:120-192); Fortran-ordered outputs, accumulated (+=) */
+int32_t edo_lanc_observables(int32_t ns, int32_t nlat, int32_t norb, int32_t isector, const edo_c64 *vec, double peso,
+                             double *dens_up, double *dens_dw, double *docc, double *magz, double *s2tot, double *sz2,
+                             double *n2);
 int32_t edo_apply_op(int32_t ns, int32_t isector, int32_t iop, int32_t ispin, int32_t nops,
                      const int32_t *pos, const edo_c64 *coef, const edo_c64 *state, edo_c64 *out,
                      int32_t *jsector_out);

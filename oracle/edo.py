@@ -160,6 +160,21 @@ def apply_op(ns, isector, iop, ispin, pos, coef, state):
     return js.value, out
 
 
+def lanc_observables(ns, nlat, norb, isector, vec, peso=1.0):
+    """Local observables of one eigenstate, ED_OBSERVABLES.f90:120-192.  Returns a dict of Fortran-ordered arrays."""
+    L = lib()
+    vec = np.ascontiguousarray(vec, dtype=np.complex128)
+    out = {k: np.zeros((nlat, norb), order="F") for k in ("dens_up", "dens_dw", "docc", "magz")}
+    out["s2tot"] = np.zeros(nlat)
+    out["sz2"] = np.zeros((nlat, nlat, norb, norb), order="F")
+    out["n2"] = np.zeros((nlat, nlat, norb, norb), order="F")
+    _chk(L.edo_lanc_observables(C.c_int32(ns), C.c_int32(nlat), C.c_int32(norb), C.c_int32(isector), _p(vec), C.c_double(peso),
+                                _p(out["dens_up"]), _p(out["dens_dw"]), _p(out["docc"]), _p(out["magz"]), _p(out["s2tot"]),
+                                _p(out["sz2"]), _p(out["n2"])))
+    out["dens"] = out["dens_up"] + out["dens_dw"]
+    return out
+
+
 # ---- context ---------------------------------------------------------------
 class Oracle:
     """Owns one edo_ctx for a cdmft_lanc_ed_b200.models.Model."""
