@@ -150,3 +150,43 @@ def test_golden_fixtures(oracle_lib):
         v = g[key + "_v"]
         assert np.abs(orc.hxv(v) - g[key + "_hv"]).max() < 1e-13
         orc.delete_hv_sector()
+
+
+def test_observables_oracle_against_jordan_wigner_operators(oracle_lib):
+    """Pins the oracle's lanc_observables restatement (ED_OBSERVABLES.f90:120-192) with operators built
+    independently in the full Fock space: <n_up>, <n_dw>, <n_up n_dw>, <(sum_orb Sz)^2>, <n_a n_b> from dense
+    Jordan-Wigner number operators acting on the sector vector embedded in the 4^Ns-dimensional space."""
+    from oracle import jw_ed as jw
+    from cdmft_lanc_ed_b200 import models
+    for mdl, (nup, ndw) in [(models.random_model(2, 1, 1, seed=2), (2, 1)), (models.random_model(2, 2, 0, seed=5), (2, 1)),
+                            (models.random_model(1, 2, 1, seed=9, kanamori=True), (2, 2))]:
+        ns, nlat, norb = mdl.ns, mdl.nlat, mdl.norb
+        isec = models.get_sector(ns, nup, ndw)
+        idx = jw.sector_indices(ns, nup, ndw)
+        rng = np.random.default_rng(17)
+        vec = rng.normal(size=len(idx)) + 1j * rng.normal(size=len(idx))
+        vec /= np.linalg.norm(vec)
+        full = np.zeros(1 << (2 * ns), dtype=np.complex128)
+        full[idx] = vec
+        c = jw._ops(2 * ns)
+        num = [op.T.conj() @ op for op in c]  # n_p = c_p^+ c_p; spin-up orbitals 0..Ns-1, spin-down Ns..2Ns-1
+        ev = lambda A: np.vdot(full, A @ full).real
+        ref = oracle_lib.lanc_observables(ns, nlat, norb, isec, vec)
+        for il in range(nlat):
+            sz_site = 0
+            for io in range(norb):
+                p = io + il * norb
+                assert abs(ref["dens_up"][il, io] - ev(num[p])) < 1e-12
+                assert abs(ref["dens_dw"][il, io] - ev(num[ns + p])) < 1e-12
+                assert abs(ref["docc"][il, io] - ev(num[p] @ num[ns + p])) < 1e-12
+                assert abs(ref["magz"][il, io] - ev(num[p] - num[ns + p])) < 1e-12
+                nt = num[p] + num[ns + p]
+                assert abs(ref["n2"][il, il, io, io] - ev(nt @ nt)) < 1e-12
+                sz_site = sz_site + (num[p] - num[ns + p]) / 2.0
+                for jl in range(nlat):
+                    for jo in range(io + 1, norb):
+                        q = jo + jl * norb
+                        assert abs(ref["n2"][il, jl, io, jo] - ev(nt @ (num[q] + num[ns + q]))) < 1e-12
+                        szi, szj = (num[p] - num[ns + p]) / 2.0, (num[q] - num[ns + q]) / 2.0
+                        assert abs(ref["sz2"][il, jl, io, jo] - ev(szi @ szj)) < 1e-12
+            assert abs(ref["s2tot"][il] - ev(sz_site @ sz_site)) < 1e-12
