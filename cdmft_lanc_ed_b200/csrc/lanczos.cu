@@ -524,8 +524,11 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   CB_REQUIRE_INIT();
   Ctx &c = ctx();
   if (!c.have_model) return fail("apply_op: no model set");
-  if (c.spmd) return fail("apply_op: single-rank only (gather the state first, ED_EIGENSPACE.f90:499-569)");
   if (ispin != 1 && ispin != 2) return fail("apply_op: ispin must be 1 or 2");
+  // SPMD: the vector is sharded along Ndw, so a spin-UP operator maps every column onto the same column of the
+  // target sector (same DimDw, same split): each rank transforms its own shard, no communication.  Spin-down
+  // operators change the column split; the reference gathers on the master for those (ED_EIGENSPACE.f90:499-569).
+  if (c.spmd && ispin != 1) return fail("apply_op: spin-down operators on a sharded vector are not supported (gather the state first)");
   const int ns = c.ns;
   int nup = (isector - 1) / (ns + 1), ndw = (isector - 1) % (ns + 1);
   int jnup = nup + (ispin == 1 ? (iop > 0 ? 1 : -1) : 0), jndw = ndw + (ispin == 2 ? (iop > 0 ? 1 : -1) : 0);
@@ -534,6 +537,12 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   int64_t idimup, idimdw, idim, jdimup, jdimdw, jdim;
   CB_CHECK(cdmft_b200_get_sector_dims(isector, &idimup, &idimdw, &idim));
   CB_CHECK(cdmft_b200_get_sector_dims(1 + jnup * (ns + 1) + jndw, &jdimup, &jdimdw, &jdim));
+  if (c.spmd) {  // local shard: this rank's columns (ED_HAMILTONIAN.f90:92-105 with P_eff = min(P, DimDw))
+    const int peff = (int)std::min<int64_t>(c.nranks, idimdw);
+    const int64_t q = c.rank < peff ? split_of(idimdw, peff, c.rank).q : 0;
+    idim = idimup * q;
+    jdim = jdimup * q;
+  }
   SpinOp src, dst;
   std::vector<Term> none;
   std::vector<double> e0(ns, 0.0);
@@ -546,6 +555,7 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   CB_CUDA(cudaMemsetAsync(d_out, 0, jdim * 16, c.stream));
   for (int k = 0; k < nops; k++) {
     if (pos[k] < 1 || pos[k] > ns) return fail("apply_op: pos out of range");
+    if (idim == 0) continue;
     k_apply_op<<<(unsigned)((idim + 255) / 256), 256, 0, c.stream>>>(idim, idimup, jdimup, ispin, iop, pos[k] - 1, src.map,
                                                                       dst.lin_lo, dst.lin_hi, ns / 2,
                                                                       make_double2(coef[2 * k], coef[2 * k + 1]), d_state, d_out);

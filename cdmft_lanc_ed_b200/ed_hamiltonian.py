@@ -382,7 +382,8 @@ def apply_op(isector: int, iop: int, ispin: int, pos, coef, state: np.ndarray):
     if min(jn) < 0 or max(jn) > ns:
         return 0, None
     jsec = get_Sector(jn[0], jn[1], ns)
-    jdim = getDim(jsec)[0]
+    # SPMD: spin-up operators act shard by shard (same Ndw split in both sectors); the result is this rank's shard
+    jdim = vecDim_Hv_sector(jsec) if _state["mode"] == "spmd" else getDim(jsec)[0]
     pos = np.ascontiguousarray(pos, dtype=np.int32)
     coef = np.ascontiguousarray(coef, dtype=np.complex128)
     state = np.ascontiguousarray(state, dtype=np.complex128)

@@ -49,6 +49,10 @@ def main():
             # real start vector: real Krylov vectors on the sharded layout (paired-row view) when H is real
             vr = np.ascontiguousarray(v.real[off:off + nloc] / np.linalg.norm(v.real)).astype(np.complex128)
             ndr, ar, br = E.sp_lanc_tridiag(vr, 30)
+            # c^+_{1,up} on the sharded vector (start vector of a GF channel, ED_GF_NORMAL.f90:180-194): shard-local
+            jsec, cv = E.apply_op(isec, +1, 1, [1], [1.0 + 0.0j], vloc)
+            cparts = [None] * world
+            dist.all_gather_object(cparts, cv if jsec else np.zeros(0, dtype=np.complex128))
             # gather on rank 0 (gather_vector_MPI, ED_SETUP.f90:633-668)
             parts = [None] * world
             dist.all_gather_object(parts, hv)
@@ -66,10 +70,13 @@ def main():
                 erra = np.abs(a[:k] - oa[:k]).max() / max(np.abs(oa[:k]).max(), 1e-300)
                 kr = min(ndr, ondr, 20)
                 errr = np.abs(ar[:kr] - oar[:kr]).max() / max(np.abs(oar[:kr]).max(), 1e-300)
-                good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == orc.active_ranks() and nd == ond and ndr == ondr
+                ojsec, ocv = edo.apply_op(ns, isec, +1, 1, [1], [1.0 + 0.0j], v)
+                gotc = np.concatenate([p for p in cparts if p is not None and p.size] or [np.zeros(0, dtype=np.complex128)])
+                okc = (ojsec == jsec) and (ojsec == 0 or (gotc.size == ocv.size and np.abs(gotc - ocv).max() < 1e-14))
+                good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == orc.active_ranks() and nd == ond and ndr == ondr and okc
                 ok &= bool(good)
                 print(f"{mdl.name} sector({nup},{ndw}) sparse={sparse} P={world} p_eff={p_eff} dim={dim} "
-                      f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} alpha_realstart_relerr={errr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+                      f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} alpha_realstart_relerr={errr:.2e} apply_op={'ok' if okc else 'BAD'} {'OK' if good else 'FAIL'}", flush=True)
                 orc.delete_hv_sector()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
