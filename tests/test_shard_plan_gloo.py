@@ -80,3 +80,66 @@ def test_vecdim_and_shrink_match_oracle(oracle_lib):
                 assert n == 0
             tot += n
         assert tot == dimup * dimdw
+
+
+def _exchange(send, rc, rank, world):
+    send_t = [torch.from_numpy(np.ascontiguousarray(b).view(np.float64).copy()) for b in send]
+    recv_t = [torch.empty(2 * n, dtype=torch.float64) for n in rc]
+    reqs = []
+    for p in range(world):
+        if p == rank:
+            recv_t[p].copy_(send_t[p])
+        else:
+            reqs.append(dist.isend(send_t[p], p))
+            reqs.append(dist.irecv(recv_t[p], p))
+    for r_ in reqs:
+        r_.wait()
+    return [t.numpy().view(np.complex128) for t in recv_t]
+
+
+def _worker_pairs(rank, world, port, nrow, ncol, q):
+    """Real Krylov vectors on the sharded layout (csrc/hxv.cu, hxv_local_terms(..., pairs)): two adjacent up-rows of
+    the REAL shard are one complex element, the distributed transposes and the Hdw pass (a real matrix acting on the
+    dw index) run on that view with nrow/2 rows, and the result read back as reals equals the real computation."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        A = rng.normal(size=(nrow, ncol))            # real vector v(iup, idw)
+        M = rng.normal(size=(ncol, ncol))            # real Hdw acting on the dw index
+        qcol, coff = sp.split_of(ncol, world, rank)
+        a_real = np.asfortranarray(A[:, coff:coff + qcol]).ravel(order="F")   # this rank's real shard
+        a_pair = a_real.view(np.complex128)                                    # (nrow/2) x qcol "complex" shard
+        du = nrow // 2
+        # forward transpose of the pair view: vt(idw, pair) for my pairs
+        sc, so, rc, ro = sp.transpose_plan(du, ncol, world, rank)
+        blocks = _exchange(sp.pack_for_transpose(a_pair, du, ncol, world, rank), rc, rank, world)
+        vt = sp.unpack_from_transpose(blocks, du, ncol, world, rank)           # column-major vt(ncol, qpair)
+        qpair, poff = sp.split_of(du, world, rank)
+        VT = vt.reshape(qpair, ncol).T                                         # [idw, pair]
+        HVT = M @ VT                                                           # Hdw pass: real matrix on complex pairs
+        hvt = np.asfortranarray(HVT).ravel(order="F")
+        # backward transpose: hvt(ncol, qpair) -> hv(pair, my columns)
+        sc2, so2, rc2, ro2 = sp.transpose_plan(ncol, du, world, rank)
+        blocks2 = _exchange(sp.pack_for_transpose(hvt, ncol, du, world, rank), rc2, rank, world)
+        hv_pair = sp.unpack_from_transpose(blocks2, ncol, du, world, rank)     # column-major (du, qcol)
+        hv_real = np.ascontiguousarray(hv_pair).view(np.float64)               # back to reals: (nrow, qcol)
+        expect = np.asfortranarray((A @ M.T)[:, coff:coff + qcol]).ravel(order="F")
+        q.put((rank, bool(np.allclose(hv_real, expect, rtol=0, atol=1e-12)), float(np.abs(hv_real - expect).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nrow,ncol", [(2, 8, 5), (2, 70, 56), (3, 20, 7)])
+def test_paired_row_view_of_real_vectors_gloo(world, nrow, ncol):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world * 10 + nrow % 7
+    procs = [ctx.Process(target=_worker_pairs, args=(r, world, port, nrow, ncol, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
