@@ -373,6 +373,33 @@ def sp_lanc_eigh(vect, nitermax: int = 512, threshold: float = 1e-18, ncheck: in
 # --------------------------------------------------------------------------------------
 # Green's function helpers (ED_GF_NORMAL.f90)
 # --------------------------------------------------------------------------------------
+def sp_eigh(neigen: int, nblock: int | None = None, nitermax: int = 512, tol: float = 1e-18, matvec=None, n: int | None = None,
+            v0=None):
+    """SciFortran `sp_eigh(MatVec, eig_values, eig_basis, Nblock, Nitermax, tol)` -- the reference's default
+    LANC_METHOD (ED_DIAG.f90:94-97,150-170): (P)ARPACK in reverse communication, which='SA', ncv = Nblock, the
+    mat-vec being the procedure pointer.  Here ARPACK stays on the host exactly as in the reference (scipy's eigsh IS
+    ARPACK's znaupd/zneupd) and every mat-vec goes through spHtimesV_p on the device: the drop-in a Fortran caller
+    gets by only re-binding the pointer.  Returns (eig_values ascending [neigen], eig_basis [n, neigen]).
+    `matvec`/`n` default to the active sector's hxv / Nloc (single rank; tests pass the oracle's mat-vec)."""
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    if matvec is None:
+        if spHtimesV_p is None:
+            raise EdB200Error("sp_eigh: Hsector NOT set (call build_Hv_sector)")
+        if _state["mode"] == "spmd":
+            raise EdB200Error("sp_eigh: host ARPACK drives a single rank (P-ARPACK is not mirrored)")
+        matvec, n = hxv, _sector["nloc"]
+    if neigen >= n:
+        raise EdB200Error("sp_eigh: Neigen must be < Dim (the reference diagonalises such sectors densely, ED_DIAG.f90:104-106)")
+    # Nblock = min(dim, lanc_ncv_factor*max(Neigen, lanc_nstates_sector) + lanc_ncv_add), defaults 10, 2, 0 (ED_INPUT_VARS.f90:171-175)
+    ncv = min(n, nblock if nblock else 10 * max(neigen, 2))
+    ncv = max(ncv, min(n, neigen + 2))
+    op = LinearOperator((n, n), matvec=lambda x: matvec(np.ascontiguousarray(x, dtype=np.complex128)), dtype=np.complex128)
+    w, z = eigsh(op, k=neigen, which="SA", ncv=ncv, maxiter=nitermax * max(1, n // max(ncv, 1)) if nitermax else None,
+                 tol=0.0 if tol < 1e-15 else tol, v0=v0)
+    order = np.argsort(w)
+    return w[order], z[:, order]
+
+
 def apply_op(isector: int, iop: int, ispin: int, pos, coef, state: np.ndarray):
     """(sum_k coef[k] op_{pos[k]}) |state>; returns (jsector, vector) or (0, None)."""
     ns = get_Ns()

@@ -470,3 +470,20 @@ def test_local_observables_on_sharded_layout(oracle_lib, P):
             E.delete_Hv_sector()
     finally:
         E.ed_finalize()
+
+
+def test_sp_eigh_arpack_with_device_matvec(ed, oracle_lib):
+    """The reference's default LANC_METHOD (ARPACK around the procedure pointer, ED_DIAG.f90:150-170): host ARPACK,
+    every mat-vec on the device through spHtimesV_p; several eigenpairs against the dense spectrum of the oracle's Hmat."""
+    for mdl, (nup, ndw), neigen in [(models.hm2x2(1), (4, 4), 3), (models.bhz2(1), (3, 3), 4)]:
+        orc = oracle_lib.Oracle(mdl)
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
+        ed.ed_set_model(mdl)
+        n = ed.build_Hv_sector(isec, True)
+        w, z = ed.sp_eigh(neigen)
+        assert z.shape == (n, neigen)
+        assert np.abs(w - ref[:neigen]).max() < RTOL * max(1.0, np.abs(ref[:neigen]).max())
+        for k in range(neigen):
+            assert np.linalg.norm(ed.hxv(np.ascontiguousarray(z[:, k])) - w[k] * z[:, k]) < 1e-8
+        ed.delete_Hv_sector()
