@@ -20,6 +20,7 @@ MODULE ED_HAMILTONIAN_B200
   public :: build_Hv_sector, delete_Hv_sector, vecDim_Hv_sector
   public :: b200_HxV
   public :: b200_lanc_eigh, b200_lanc_tridiag
+  public :: b200_imp_weights, b200_lanc_observables
 
   type, bind(C) :: cdmft_b200_model
      integer(c_int32_t) :: nlat, norb, nspin, nbath
@@ -255,5 +256,64 @@ contains
     real(8), dimension(0:,0:) :: W   ! (0:2**Nimp-1, 0:2**Nimp-1) = (mu, md)
     call check(c_imp_weights(int(size(vec), c_int64_t), vec, W), "lanc_observables")
   end subroutine b200_imp_weights
+
+  !> The body of the state loop of lanc_observables (ED_OBSERVABLES.f90:120-192) for ONE eigenvector of the active
+  !> sector, with the O(Dim) part on the device: the accumulation lines below are the reference's (:155-186), run
+  !> over the (mu,md) impurity configurations with gs_weight = peso*W(mu,md) instead of over every basis state.
+  !> All arguments are accumulated (+=) like the reference's sum over state_list.
+  subroutine b200_lanc_observables(vec, peso, dens, dens_up, dens_dw, docc, magz, s2tot, sz2, n2)
+    complex(8), dimension(:)                :: vec
+    real(8)                                 :: peso
+    real(8), dimension(Nlat,Norb)           :: dens, dens_up, dens_dw, docc, magz
+    real(8), dimension(Nlat)                :: s2tot
+    real(8), dimension(Nlat,Nlat,Norb,Norb) :: sz2, n2
+    real(8), dimension(Nlat,Norb)           :: nup, ndw, sz, nt
+    real(8), allocatable                    :: W(:,:)
+    real(8)                                 :: gs_weight
+    integer                                 :: mu, md, ilat, jlat, iorb, jorb, nimp, pos
+    nimp = Nlat*Norb
+    allocate(W(0:2**nimp-1, 0:2**nimp-1))
+    call b200_imp_weights(vec, W)
+    do md = 0, 2**nimp-1
+       do mu = 0, 2**nimp-1
+          gs_weight = peso*W(mu,md)
+          if (gs_weight == 0d0) cycle
+          do ilat = 1, Nlat
+             do iorb = 1, Norb
+                pos = iorb + (ilat-1)*Norb - 1          ! imp_state_index(ilat,iorb) - 1 (ED_SETUP.f90:563-568)
+                nup(ilat,iorb) = merge(1d0, 0d0, btest(mu, pos))
+                ndw(ilat,iorb) = merge(1d0, 0d0, btest(md, pos))
+                sz(ilat,iorb)  = (nup(ilat,iorb) - ndw(ilat,iorb))/2d0
+                nt(ilat,iorb)  =  nup(ilat,iorb) + ndw(ilat,iorb)
+             end do
+          end do
+          do ilat = 1, Nlat
+             do iorb = 1, Norb
+                dens(ilat,iorb)    = dens(ilat,iorb)    + nt(ilat,iorb)*gs_weight
+                dens_up(ilat,iorb) = dens_up(ilat,iorb) + nup(ilat,iorb)*gs_weight
+                dens_dw(ilat,iorb) = dens_dw(ilat,iorb) + ndw(ilat,iorb)*gs_weight
+                docc(ilat,iorb)    = docc(ilat,iorb)    + nup(ilat,iorb)*ndw(ilat,iorb)*gs_weight
+                magz(ilat,iorb)    = magz(ilat,iorb)    + (nup(ilat,iorb)-ndw(ilat,iorb))*gs_weight
+             end do
+             s2tot(ilat) = s2tot(ilat) + (sum(sz(ilat,:)))**2*gs_weight
+          end do
+          do ilat = 1, Nlat
+             do iorb = 1, Norb
+                sz2(ilat,ilat,iorb,iorb) = sz2(ilat,ilat,iorb,iorb) + (sz(ilat,iorb)*sz(ilat,iorb))*gs_weight
+                n2(ilat,ilat,iorb,iorb)  = n2(ilat,ilat,iorb,iorb)  + (nt(ilat,iorb)*nt(ilat,iorb))*gs_weight
+                do jlat = 1, Nlat
+                   do jorb = iorb+1, Norb
+                      sz2(ilat,jlat,iorb,jorb) = sz2(ilat,jlat,iorb,jorb) + (sz(ilat,iorb)*sz(jlat,jorb))*gs_weight
+                      sz2(ilat,jlat,jorb,iorb) = sz2(ilat,jlat,jorb,iorb) + (sz(ilat,jorb)*sz(jlat,iorb))*gs_weight
+                      n2(ilat,jlat,iorb,jorb)  = n2(ilat,jlat,iorb,jorb)  + (nt(ilat,iorb)*nt(jlat,jorb))*gs_weight
+                      n2(ilat,jlat,jorb,iorb)  = n2(ilat,jlat,jorb,iorb)  + (nt(ilat,jorb)*nt(jlat,iorb))*gs_weight
+                   end do
+                end do
+             end do
+          end do
+       end do
+    end do
+    deallocate(W)
+  end subroutine b200_lanc_observables
 
 END MODULE ED_HAMILTONIAN_B200
