@@ -536,9 +536,18 @@ static int build_rowres(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, 
 // row block on the in-block part of the CSR (relative indices) plus, per warp task, the off-block entries of
 // its 32 rows as a lane-parallel stream.  code3 of an off-block fast word: class (2 bits) | imaginary << 2.
 // ------------------------------------------------------------------------------------
+struct ColBlkHost {  // host image of ColBlk (what build_colblk uploads); filled instead of uploading for the CPU tests
+  std::vector<int4> blk;
+  std::vector<int32_t> tbase, qbase;
+  std::vector<uint32_t> meta, words, woff;
+  std::vector<uint2> toff;
+  int nwarps = 0;
+  int64_t max_rows = 0;
+};
+
 static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
                         const std::vector<uint8_t> &code, int G, int fmt, bool natural, int64_t cap_rows,
-                        const double *f_row, const uint32_t *mu_row) {
+                        const double *f_row, const uint32_t *mu_row, ColBlkHost *host_out = nullptr) {
   Ctx &c = ctx();
   int t = 0;
   for (; t <= ns; t++) {
@@ -636,6 +645,11 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
   }
   if (start != op.n) return fail("internal: column blocks do not cover the sector");
   woff.resize(woff.size() + 64, NONE);
+  if (host_out) {  // CPU inspection (cdmft_b200_colblk_host): no device involved
+    host_out->blk = blk; host_out->tbase = tbase; host_out->qbase = qbase; host_out->meta = meta; host_out->words = words;
+    host_out->woff = woff; host_out->toff = toff; host_out->nwarps = nwarps; host_out->max_rows = mxrows;
+    return 0;
+  }
   cb.nblk = (int32_t)blk.size(); cb.nwarps = nwarps; cb.fmt = fmt; cb.G = G; cb.max_rows = mxrows;
   cb.even_blocks = true;
   for (auto &q : blk) cb.even_blocks = cb.even_blocks && !(q.x & 1) && !(q.y & 1);
@@ -990,6 +1004,36 @@ int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *co
     std::copy(sh.qbase.begin(), sh.qbase.end(), qbase);
     std::copy(sh.meta.begin(), sh.meta.end(), meta);
     std::copy(sh.words.begin(), sh.words.begin() + (size_t)sh.nquads * 32 * 4, words);
+  }
+  return 0;
+}
+
+int cdmft_b200_colblk_host(int32_t ns, int32_t npart, const int32_t *rowptr, const int32_t *col, const uint8_t *code, int32_t g,
+                            int32_t natural, int64_t cap_rows, int64_t *sizes, int32_t *blk, int32_t *tbase, int32_t *qbase,
+                            uint32_t *meta, uint32_t *words, uint32_t *toff, uint32_t *woff) {
+  if (g != 8 && g != 16) return fail("colblk_host: g must be 8 or 16");
+  if (ns < 1 || ns > 30 || npart < 0 || npart > ns) return fail("colblk_host: bad ns / npart");
+  const int64_t n = binom64(ns, npart);
+  if (n <= 0 || n >= (1 << 24)) return fail("colblk_host: sector too large");
+  SpinOp op;
+  op.n = n;
+  op.npart = npart;
+  ColBlk dummy;
+  ColBlkHost h;
+  std::vector<int32_t> rp(rowptr, rowptr + n + 1), cl(col, col + rowptr[n]);
+  std::vector<uint8_t> cd(code, code + rowptr[n]);
+  CB_CHECK(build_colblk(op, dummy, ns, rp, cl, cd, g, 0, natural != 0, std::max<int64_t>(g, cap_rows), nullptr, nullptr, &h));
+  sizes[0] = (int64_t)h.blk.size(); sizes[1] = (int64_t)h.tbase.size(); sizes[2] = (int64_t)h.meta.size();
+  sizes[3] = (int64_t)h.words.size(); sizes[4] = (int64_t)h.toff.size(); sizes[5] = (int64_t)h.woff.size();
+  sizes[6] = h.nwarps; sizes[7] = h.max_rows;
+  if (blk) {
+    memcpy(blk, h.blk.data(), h.blk.size() * sizeof(int4));
+    std::copy(h.tbase.begin(), h.tbase.end(), tbase);
+    std::copy(h.qbase.begin(), h.qbase.end(), qbase);
+    std::copy(h.meta.begin(), h.meta.end(), meta);
+    std::copy(h.words.begin(), h.words.end(), words);
+    memcpy(toff, h.toff.data(), h.toff.size() * sizeof(uint2));
+    std::copy(h.woff.begin(), h.woff.end(), woff);
   }
   return 0;
 }

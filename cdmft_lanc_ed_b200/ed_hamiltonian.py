@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_get_csr_nnz", "cdmft_b200_get_csr", "cdmft_b200_get_diag", "cdmft_b200_get_sparse_map",
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
     "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
+    "cdmft_b200_colblk_host",
 ]
 
 
@@ -304,6 +305,42 @@ def schedule_host(rowptr, col, code, g: int = 8, natural: bool = False, nwarps: 
             q += nq
         assert q == qbase[w + 1]
         out.append(tasks)
+    return out
+
+
+def colblk_host(ns: int, npart: int, rowptr, col, code, g: int = 8, natural: bool = False, cap_rows: int = 64):
+    """Block-split schedules of the column-resident kernel for big columns (host only).  Returns a list of blocks:
+    dict(g0, ng, tasks=[(rows[32] relative to the block (-1 none), words[nsteps, 32], off[noff, 32])])."""
+    L = load_library()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    code = np.ascontiguousarray(code, dtype=np.uint8)
+    sizes = np.zeros(8, np.int64)
+    args = (C.c_int32(ns), C.c_int32(npart), _ptr(rowptr), _ptr(col), _ptr(code), C.c_int32(g), C.c_int32(1 if natural else 0),
+            C.c_int64(cap_rows), _ptr(sizes))
+    _chk(L.cdmft_b200_colblk_host(*args, None, None, None, None, None, None, None))
+    nblk, ntq, nmeta, nwords, ntask, nwoff, nwarps, _ = [int(x) for x in sizes]
+    blk = np.zeros(nblk * 4, np.int32)
+    tbase, qbase = np.zeros(ntq, np.int32), np.zeros(ntq, np.int32)
+    meta, words = np.zeros(nmeta, np.uint32), np.zeros(nwords, np.uint32)
+    toff, woff = np.zeros(ntask * 2, np.uint32), np.zeros(nwoff, np.uint32)
+    _chk(L.cdmft_b200_colblk_host(*args, _ptr(blk), _ptr(tbase), _ptr(qbase), _ptr(meta), _ptr(words), _ptr(toff), _ptr(woff)))
+    blk, meta, words = blk.reshape(-1, 4), meta.reshape(-1, 32, 4), words.reshape(-1, 32, 4)
+    toff, woff = toff.reshape(-1, 2), woff.reshape(-1, 32)
+    out = []
+    for b in range(nblk):
+        g0, ng, task0, unit0 = [int(x) for x in blk[b]]
+        tasks = []
+        for w in range(nwarps):
+            q = unit0 + int(qbase[b * (nwarps + 1) + w])
+            for t in range(task0 + tbase[b * (nwarps + 1) + w], task0 + tbase[b * (nwarps + 1) + w + 1]):
+                nq = int(meta[t, 0, 3] >> 16)
+                rows = meta[t, :, 2].astype(np.int64)
+                rows[rows == 0xFFFFFFFF] = -1
+                ob, no = int(toff[t, 0]), int(toff[t, 1])
+                tasks.append((rows, words[q:q + nq].transpose(0, 2, 1).reshape(nq * 4, 32), woff[ob:ob + no]))
+                q += nq
+        out.append(dict(g0=g0, ng=ng, tasks=tasks))
     return out
 
 

@@ -142,6 +142,19 @@ int cdmft_b200_schedule_host(int64_t n, const int32_t *rowptr, const int32_t *co
                              int32_t g, int32_t natural, int32_t nwarps, int32_t *ntask, int64_t *nquads,
                              int32_t *tbase, int32_t *qbase, uint32_t *meta, uint32_t *words);
 
+/* Host-only: the block-split schedules of k_colblk (columns larger than shared memory, Ns = 18)
+ * for the CSR pattern of a one-spin operator on the sector of `npart` particles in `ns` orbitals (n = C(ns,npart) rows,
+ * 0-based ascending columns).  Blocks = runs of states sharing their top bits with at most cap_rows rows.
+ * sizes[8] = {nblk, len(tbase) = len(qbase) = nblk*(nwarps+1), len(meta), len(words), ntask, len(woff), nwarps, max rows};
+ * blk[nblk*4] = {first row, rows, first task, first unit}; tbase / qbase relative to the block; meta (uint4 per task and
+ * lane: row relative to the block in word 2, units << 16 in word 3); words: uint4 per unit and lane,
+ * (source row relative to the block << 7) | code, idle lanes on the zero elements behind the block; toff[ntask*2] =
+ * {first off-block step, steps}; woff[step*32 + lane] = (source row << 7) | code, 0 = none.  Arrays may be NULL to
+ * query the sizes.  Used by the CPU tests. */
+int cdmft_b200_colblk_host(int32_t ns, int32_t npart, const int32_t *rowptr, const int32_t *col, const uint8_t *code,
+                           int32_t g, int32_t natural, int64_t cap_rows, int64_t *sizes, int32_t *blk, int32_t *tbase,
+                           int32_t *qbase, uint32_t *meta, uint32_t *words, uint32_t *toff, uint32_t *woff);
+
 /* ---- fused device-resident Krylov drivers (SciFortran SF_SP_LINALG semantics) --------- */
 /* sp_lanc_tridiag(MatVec,vin,alanc,blanc): v0 = local shard of the start vector (host or
  * device; not modified), alanc/blanc host arrays of size nitermax (blanc[0] = 0);
