@@ -487,3 +487,37 @@ def test_sp_eigh_arpack_with_device_matvec(ed, oracle_lib):
         for k in range(neigen):
             assert np.linalg.norm(ed.hxv(np.ascontiguousarray(z[:, k])) - w[k] * z[:, k]) < 1e-8
         ed.delete_Hv_sector()
+
+
+def test_cuda_path_against_committed_golden_fixtures(ed):
+    """tests/golden/golden_small.npz (oracle outputs checked against the Jordan-Wigner ED when they were generated,
+    tests/golden/make_golden.py): Fock maps and CSR patterns bit-exact, diagonal, H x v and the Lanczos
+    coefficients of the CUDA path within the north-star tolerance -- no oracle code runs in this test."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz"))
+    meta = json.loads(str(g["meta"]))
+    for case in meta["cases"]:
+        mdl = getattr(models, case["builder"])(*case["args"])
+        key, isec = case["key"], case["isector"]
+        ed.ed_set_model(mdl)
+        for sparse in (True, False):
+            n = ed.build_Hv_sector(isec, sparse)
+            assert np.array_equal(ed.get_sector_map(1), g[key + "_map_up"])
+            assert np.array_equal(ed.get_sector_map(2), g[key + "_map_dw"])
+            if sparse:
+                for which, nm in ((1, "up"), (2, "dw")):
+                    rp, col, val = ed.get_csr(which)
+                    assert np.array_equal(rp, g[f"{key}_{nm}_rowptr"]) and np.array_equal(col, g[f"{key}_{nm}_col"])
+                    assert np.abs(val - g[f"{key}_{nm}_val"]).max() < 1e-15
+                gd = g[key + "_diag"]
+                assert np.abs(ed.get_diag() - gd).max() <= 1e-13 * max(1.0, np.abs(gd).max())
+            v, hv = g[key + "_v"], g[key + "_hv"]
+            assert n == v.size
+            assert _relerr(ed.hxv(v), hv) < RTOL
+            nd, a, b = ed.sp_lanc_tridiag(v, 30)
+            ga, gb = g[key + "_alanc"], g[key + "_blanc"]
+            k = min(nd, 20)
+            assert np.abs(a[:k] - ga[:k]).max() <= RTOL * np.abs(ga[:k]).max()
+            assert np.abs(b[:k] - gb[:k]).max() <= RTOL * max(np.abs(gb[:k]).max(), 1e-300)
+            ed.delete_Hv_sector()
