@@ -50,19 +50,20 @@ struct ColBlk {
   uint32_t *woff = nullptr;   // [steps*32] off-block words: sign<<31 | row<<3 | code3 (fast) or row<<7 | id; see sector.cu
 };
 
-// Operator streams of the block-resident row pass (k_rowres, hxv.cu).  Columns (states of this spin) are cut
-// into blocks sharing their top bits; a CTA owns one block x 8 rows of the other spin's index, keeps that tile
-// in shared memory and runs, per warp task of 4 columns (one per 8-lane group), the in-block entries against
-// the tile and the off-block entries (hops that change the top bits) against global memory / L2.
+// Operator streams of the tile-resident row pass (k_rowtile, rowtile.cu).  Columns (states of this spin) are cut
+// into blocks = runs of states sharing their leading bits; a work item is one block x 8 rows of the other spin's
+// index, kept in shared memory; per warp task of 4 columns (one per 8-lane group) the in-block entries run against
+// the tile and the off-block entries (hops that change the leading bits) against global memory / L2.
 struct RowRes {
   int32_t nblocks = 0, max_block = 0, ntask = 0;
-  int32_t fmt = 0;              // 0 = coefficient-table ids, 1 = fast (sign / class bits)
+  int32_t fmt = 0;              // 0 = coefficient-table ids, 1 = sign / class / phase bits
+  double in_frac = 0.0;         // share of the entries whose source lies inside the block
   int2 *blocks = nullptr;       // [nblocks] (first column, columns)
   int32_t *tbase = nullptr;     // [nblocks+1] first task of each block
   uint4 *task = nullptr;        // [ntask] {first in-block quad, in-block quads, first off-block step, off-block steps}
   int32_t *task_col = nullptr;  // [ntask*4] column (relative to the block) of each lane group, -1 = none
-  uint32_t *win = nullptr;      // [quads*4 groups] uint4: 4 steps, word = sign<<31 | tile row*128 | class  (or | id)
-  uint32_t *woff = nullptr;     // [steps*4 groups]: sign<<31 | column<<1 | class, 0xFFFFFFFF = none  (or column<<7 | id)
+  uint32_t *win = nullptr;      // [quads*4 groups] uint4: 4 steps; word formats in rowtile.cu
+  uint32_t *woff = nullptr;     // [steps*4 groups]
 };
 
 // Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).
@@ -86,22 +87,8 @@ struct SpinOp {
   int32_t *ell_col = nullptr;
   double2 *ell_val = nullptr;
   int32_t *rowlen = nullptr;
-  // row blocks = runs of states sharing the top `tbits` bits (contiguous in rank order); hops that
-  // leave those bits alone stay inside a block, so a block x 8 columns is a closed shared-memory tile
-  int32_t tbits = 0, nblocks = 0, max_block = 0;
-  int2 *blocks = nullptr;  // device [nblocks] (start, size)
-  int32_t nblocks_l1 = 0;   // finer blocks for the L1-blocked row pass
-  int2 *blocks_l1 = nullptr;
-  // packed tile CSR for the shared-memory kernels: per row two lists -- sources inside the row block
-  // (word = slot<<11 | coef_id<<4, slot = rel<<3 | swizzle) and outside it (word = row<<11 | coef_id<<4)
-  // -- each padded to rounds of 8 words; *_ptr are row pointers in rounds
-  uint32_t *pkell = nullptr;  // packed ELL [ell_w][n]: (col << 7) | coef_id, thread-per-row kernels
-  int2 *rowsplit = nullptr;   // [n]: entries [x,y) of a row have their source inside the row's block
-  uint32_t *pk_in = nullptr, *pk_off = nullptr;
-  int32_t *pk_in_ptr = nullptr, *pk_off_ptr = nullptr;  // [n+1]
-  double2 *coef = nullptr;       // [ncoef] distinct signed coefficients, coef[0] = 0
+  double2 *coef = nullptr;       // [128] distinct signed coefficients (table decode), coef[0] = 0
   int32_t ncoef = 0;
-  bool pk_swizzled = false;      // built for the column pass (slot swizzled with rel&7)
   // column-resident kernels: schedules for 16-byte (sc8) and 8-byte (sc16) vector elements
   Sched sc8, sc16;
   ColBlk cb8, cb16;
@@ -130,25 +117,24 @@ struct RankState {
 };
 
 struct Options {
-  // kernel variants: 6 = column-resident shared-memory kernel (default; falls back to 1 when a column does
-  // not fit in shared memory or in DIRECT mode), 1 = generic global-gather kernels, 0 = packed
-  // shared-memory tile kernel, 2 = unpacked tile kernel, 3 = L1-blocked row pass, 4/5 = rotating-slot tiles
+  // column pass: 6 = column-resident shared-memory kernels (default; falls back to 1 when a column does not fit
+  // in shared memory and has no block schedules, or in DIRECT mode), 1 = generic global-gather kernel
   int64_t colpass_variant = 6;
   int64_t sched = 1;            // 1 = conflict-free edge-coloured schedule, 0 = natural CSR order (for comparison)
   int64_t colres_rows = 0;      // > 0: force the block-split column-resident kernel with at most this many rows per block
-  int64_t rowres_cols = 570;    // max columns of a block of the block-resident row pass ((cols+1) x 128 B of shared memory)
-  int64_t rowpass_variant = 1;  // 1 = generic L2-slab kernel (default, fastest measured), 4 = block-resident shared-memory row pass
+  // row pass: 4 = tile-resident shared-memory kernel (default in SPARSE mode), 1 = generic L2-slab kernel
+  int64_t rowpass_variant = 4;
+  int64_t rowres_cols = 0;      // > 0: cap on the columns of a row-pass block (default: what two tile buffers hold)
+  int64_t tma2d = 1;            // row pass tiles by 2-D TMA tensor copies (0: one 128-byte bulk copy per column)
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
-  int64_t row_slab = 128;       // rows swept per grid.y index of the row pass (slab x all columns stays in L2)
-  int64_t tile_rows = 1800;     // max rows of a shared-memory tile (x 8 columns x 16 B <= 227 KB)
+  int64_t row_slab = 128;       // rows per slab of the row pass (slab x all columns stays in L2)
   int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
   int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
-  int64_t fast4 = 1;            // column-resident kernel: sign/class/phase decode for purely real-or-imaginary coefficients
-  int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the row pass instead of a separate sweep
+  int64_t fast4 = 1;            // sign/class/phase decode for purely real-or-imaginary coefficients
+  int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the last pass of H x v
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
-  int64_t l1_rows = 256;        // max dw states of an L1-blocked row-pass block (x 32 rows x 16 B)
 };
 
 struct Ctx {
@@ -205,6 +191,7 @@ struct Ctx {
   std::vector<ProfRec> prof;
   // fused Lanczos dot: the row pass leaves one partial of Re<v,Hv> per CTA when dot_request is set
   bool dot_request = false, dot_done = false;
+  bool dot_final_rowpass = false;  // the accumulating row pass is the last contribution to H x v
   double *dot_partial = nullptr;
   int64_t dot_cap = 0, dot_npartial = 0;
   double *red = nullptr;       // device reduction scratch
@@ -233,9 +220,12 @@ void set_error(const std::string &s);
 
 // ---- internal entry points shared between translation units ----
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
-                  double const_add, bool want_csr, bool pack_swizzled = true);
+                  double const_add, bool want_csr);
 void free_spin_op(SpinOp &op);
 int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
+int build_rowtile(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
+                  const std::vector<uint8_t> &code, int fmt, int64_t cap);  // rowtile.cu
+int64_t rowtile_cap();
 int nccl_allreduce_sum(double *dev_buf, int n);
 int nccl_all_to_all(const double2 *send, double2 *recv, const int64_t *counts_send, const int64_t *offs_send,
                     const int64_t *counts_recv, const int64_t *offs_recv);

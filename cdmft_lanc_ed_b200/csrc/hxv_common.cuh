@@ -110,7 +110,11 @@ struct ColResArgs {
   const double2 *coef;  // [128] (table decode)
   double m0, m1;        // fast decode (m0..m3 for the four-class variant)
   double m2, m3;
+  int accum;            // 1: out += (the row pass wrote out first), 0: out =
+  double *dot_partial;  // != nullptr: Re<v,out> of the final out, one partial per CTA (fused Lanczos alpha)
 };
+__device__ __forceinline__ double colres_dotre(double2 x, double2 y) { return fma(x.x, y.x, x.y * y.y); }
+__device__ __forceinline__ double colres_dotre(double x, double y) { return x * y; }
 
 __device__ __forceinline__ void colres_fma(double2 &acc, double h, double2 x) { rfma(acc, h, x); }
 __device__ __forceinline__ void colres_fma(double &acc, double h, double x) { acc = fma(h, x, acc); }
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
   const char *xs_b = (const char *)xs;
   const char *coef_b = (const char *)coef;
   uint32_t phase = 0;
+  double dsum = 0.0;
   for (int64_t c = blockIdx.x; c < ncols; c += gridDim.x) {
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, bytes);
@@ -219,8 +224,10 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
       if (t + 1 < t1) mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
       const int nquad = (int)(m.w >> 16);
       const bool valid = m.z != 0xFFFFFFFFu;
-      T acc;
+      T acc, yold;
       colres_zero(acc);
+      colres_zero(yold);
+      if (a.accum && valid) yold = oc[m.z];  // requested first, needed last
       if (dg.enabled && valid)
         acc = colres_scale(__hiloint2double((int)m.y, (int)m.x) + dtab[m.w & 0xFFFFu], xs[m.z]);
       for (int kq = 0; kq < nquad; kq++) {
@@ -240,10 +247,26 @@ __global__ void __launch_bounds__(1024, 1) k_colres(int64_t n, int64_t ncols, co
           colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
         }
       }
-      if (valid) oc[m.z] = acc;
+      if (valid) {
+        acc = acc + yold;
+        oc[m.z] = acc;
+        if (a.dot_partial) dsum += colres_dotre(xs[m.z], acc);
+      }
       m = mnext;
     }
     __syncthreads();  // every gather of this column is done before the next bulk copy lands
+  }
+  if (a.dot_partial) {  // fixed summation order: lanes -> warps -> CTA, one partial per CTA
+    __shared__ double wsum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+    if (lane == 0) wsum[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += wsum[w];
+      a.dot_partial[blockIdx.x] = tot;
+    }
   }
 }
 
@@ -393,8 +416,24 @@ inline size_t colres_smem(int64_t n, int elem, int nimp_diag) {
 // launch on the context's stream; returns kColresNA when the kernel does not apply (the caller then uses the
 // generic kernel), 0 on success, the usual non-zero rc on a CUDA error
 constexpr int kColresNA = -7;
+// does the whole-column kernel apply to (s, T, dg)?  (it is the only column pass that can accumulate)
 template <typename T>
-inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg) {
+inline bool colres_applicable(const SpinOp &s, const DiagArgs &dg) {
+  Ctx &c = ctx();
+  const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
+  if (c.opt.colpass_variant != 6 || c.opt.colres_rows > 0) return false;
+  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return false;
+  if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return false;  // bulk copies need 16-byte aligned columns
+  if (colres_smem(s.n, (int)sizeof(T), dg.enabled ? dg.nimp : -1) > 232448) return false;
+  if (dg.enabled && dg.f_row != s.f) return false;  // the schedule carries the operator's own row diagonal
+  return true;
+}
+
+// accum: out += instead of out = ; final: out is the finished H x v after this launch, so a pending Lanczos
+// dot request (Ctx::dot_request) is served here
+template <typename T>
+inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg, bool accum = false,
+                         bool final = false) {
   Ctx &c = ctx();
   const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
   if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return kColresNA;
@@ -403,6 +442,7 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   if (smem > 232448) return kColresNA;
   if (dg.enabled && dg.f_row != s.f) return kColresNA;  // the schedule carries the operator's own row diagonal
   ColResArgs a{};
+  a.accum = accum ? 1 : 0;
   a.tbase = sc.tbase; a.qbase = sc.qbase; a.meta = (const uint4 *)sc.meta; a.words = sc.words;
   a.coef = s.coef; a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1]; a.m2 = s.sc_mag[2]; a.m3 = s.sc_mag[3];
   void (*kern)(int64_t, int64_t, const T *, T *, ColResArgs, DiagArgs) =
@@ -427,6 +467,16 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   const int per_sm = it->second;
   if (per_sm < 1) return kColresNA;
   const int64_t grid = std::min<int64_t>(ncols, (int64_t)c.sm_count * per_sm);
+  if (final && c.dot_request) {
+    if (c.dot_cap < grid) {
+      dev_free(c.dot_partial);
+      CB_CHECK(dev_alloc(&c.dot_partial, grid));
+      c.dot_cap = grid;
+    }
+    a.dot_partial = c.dot_partial;
+    c.dot_npartial = grid;
+    c.dot_done = true;
+  }
   kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);
   c.launches++;
   return 0;

@@ -16,7 +16,8 @@
 namespace cb {
 
 OpArgs op_args(const SpinOp &s);
-int rowpass_real_as_pairs(int64_t nrows, const double *v, double *out);  // hxv.cu
+int rowpass_real_as_pairs(int64_t nrows, const double *v, double *out, bool accum);  // hxv.cu
+bool rowtile_applicable(const SpinOp &s);  // rowtile.cu
 DiagArgs diag_args(int64_t coloff);
 
 template <bool DIRECT, int CB>
@@ -98,18 +99,19 @@ __global__ void __launch_bounds__(256) k_rowpass_r(int64_t n /*rows*/, int64_t n
 }
 
 // diag + Hup on a real vector: column-resident kernel when a column fits in shared memory, else the generic one
-int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg) {
+int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final) {
   Ctx &c = ctx();
   if (ncols <= 0 || s.n <= 0) return 0;
   const bool direct = c.mode == CDMFT_B200_DIRECT;
   prof_begin(0);
   int rc = kColresNA;
   if (c.opt.colpass_variant == 6) {
-    if (c.opt.colres_rows > 0) rc = launch_colblk<double>(s, ncols, v, out, dg);
-    if (rc == kColresNA) rc = launch_colres<double>(s, ncols, v, out, dg);
-    if (rc == kColresNA) rc = launch_colblk<double>(s, ncols, v, out, dg);
+    if (c.opt.colres_rows > 0 && !accum) rc = launch_colblk<double>(s, ncols, v, out, dg);
+    if (rc == kColresNA) rc = launch_colres<double>(s, ncols, v, out, dg, accum, final);
+    if (rc == kColresNA && !accum) rc = launch_colblk<double>(s, ncols, v, out, dg);
   }
   if (rc != 0 && rc != kColresNA) { prof_end(); return rc; }
+  if (rc == kColresNA && accum) { prof_end(); return fail("internal: accumulating real column pass without the column-resident kernel"); }
   if (rc == kColresNA) {
     dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((ncols + 3) / 4));
     if (grid.y > 65535) { prof_end(); return fail("colpass_r: too many column groups"); }
@@ -130,8 +132,18 @@ int hxv_device_real(const double *v, double *hv) {
   if (!c.real_h || c.jhflag) return fail("hxv_device_real: not applicable");
   if (c.spmd || c.sim || c.opt.force_sharded) return hxv_sharded_real(v, hv);
   const bool direct = c.mode == CDMFT_B200_DIRECT;
-  CB_CHECK(colpass_real(c.up, c.dimdw, v, hv, diag_args(0)));
-  if (!direct && !(c.dimup & 1) && c.opt.colpass_variant != 5) return rowpass_real_as_pairs(c.dimup, v, hv);  // 16-byte gathers (two rows per lane)
+  // preferred order (see hxv_local_terms): tile-resident row pass writes hv, column-resident pass accumulates
+  if (!direct && !(c.dimup & 1) && rowtile_applicable(c.dw) && colres_applicable<double>(c.up, diag_args(0))) {
+    CB_CHECK(rowpass_real_as_pairs(c.dimup, v, hv, false));
+    return colpass_real(c.up, c.dimdw, v, hv, diag_args(0), true, true);
+  }
+  CB_CHECK(colpass_real(c.up, c.dimdw, v, hv, diag_args(0), false, false));
+  if (!direct && !(c.dimup & 1)) {  // 16-byte gathers (two rows per lane)
+    c.dot_final_rowpass = true;  // last contribution (real mode has no Jx/Jp term); pairs: u0*y0 + u1*y1
+    const int rc = rowpass_real_as_pairs(c.dimup, v, hv, true);
+    c.dot_final_rowpass = false;
+    return rc;
+  }
   {
     const SpinOp &s = c.dw;
     dim3 grid((unsigned)s.n, (unsigned)((c.dimup + 255) / 256));

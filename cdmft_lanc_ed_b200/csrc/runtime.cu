@@ -338,8 +338,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "force_sharded") c.opt.force_sharded = value;
   else if (k == "col_batch") c.opt.col_batch = value;
   else if (k == "row_slab") c.opt.row_slab = value;
-  else if (k == "tile_rows") c.opt.tile_rows = value;
-  else if (k == "l1_rows") c.opt.l1_rows = value;
+  else if (k == "tma2d") c.opt.tma2d = value;
   else if (k == "overlap") c.opt.overlap = value;
   else if (k == "real_lanczos") c.opt.real_lanczos = value;
   else if (k == "row_rb") c.opt.row_rb = value;

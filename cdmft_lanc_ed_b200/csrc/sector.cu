@@ -136,75 +136,6 @@ __global__ void k_csr_to_ell(int64_t n, const int32_t *__restrict__ rowptr, cons
   }
 }
 
-// packed tile CSR (see ctx.h): per row two lists (sources inside / outside the row block), each
-// padded to rounds of 8 words; word = (slot_or_row << 11) | (coef_id << 4)
-__device__ __forceinline__ int find_block(const int2 *__restrict__ blocks, int nblocks, int64_t i) {
-  int lo = 0, hi = nblocks - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (blocks[mid].x <= i) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
-__global__ void k_pk_rounds(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                            const int2 *__restrict__ blocks, int nblocks, int32_t *__restrict__ rounds_in,
-                            int32_t *__restrict__ rounds_off) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int2 b = blocks[find_block(blocks, nblocks, i)];
-  int nin = 0, noff = 0;
-  for (int32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
-    if ((uint32_t)(col[p] - b.x) < (uint32_t)b.y) nin++; else noff++;
-  }
-  rounds_in[i] = (nin + 7) >> 3;
-  rounds_off[i] = (noff + 7) >> 3;
-}
-__global__ void k_pk_fill(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                          const uint8_t *__restrict__ coefidx, const int2 *__restrict__ blocks, int nblocks,
-                          const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ off_ptr, int swz,
-                          uint32_t *__restrict__ pk_in, uint32_t *__restrict__ pk_off) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int2 b = blocks[find_block(blocks, nblocks, i)];
-  const int g0 = b.x, ng = b.y;
-  int64_t qi = (int64_t)in_ptr[i] * 8, qo = (int64_t)off_ptr[i] * 8;
-  const int64_t ei = (int64_t)in_ptr[i + 1] * 8, eo = (int64_t)off_ptr[i + 1] * 8;
-  for (int32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
-    const int32_t j = col[p];
-    const uint32_t rel = (uint32_t)(j - g0), id = coefidx[p];
-    if (rel < (uint32_t)ng) pk_in[qi++] = ((((rel << 3) | (swz ? (rel & 7u) : 0u))) << 11) | (id << 4);
-    else pk_off[qo++] = ((uint32_t)j << 11) | (id << 4);
-  }
-  const uint32_t rel = (uint32_t)(i - g0);  // padding: coefficient id 0 (= 0.0) on a valid slot / row
-  while (qi < ei) pk_in[qi++] = (((rel << 3) | (swz ? (rel & 7u) : 0u))) << 11;
-  while (qo < eo) pk_off[qo++] = (uint32_t)i << 11;
-}
-
-// packed ELL: word[k*n + i] = (col << 7) | coef_id for the k-th entry of row i (columns ascending)
-__global__ void k_pkell_fill(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                             const uint8_t *__restrict__ coefidx, int ell_w, uint32_t *__restrict__ pkell) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t p0 = rowptr[i], len = rowptr[i + 1] - p0;
-  for (int k = 0; k < ell_w; k++)
-    pkell[(int64_t)k * n + i] = k < len ? (((uint32_t)col[p0 + k] << 7) | coefidx[p0 + k]) : 0u;
-}
-
-// per row: [k0,k1) = entries (columns ascending) whose source lies inside the row's own block
-__global__ void k_rowsplit(int64_t n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                           const int2 *__restrict__ blocks, int nblocks, int2 *__restrict__ split) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int2 b = blocks[find_block(blocks, nblocks, i)];
-  const int32_t p0 = rowptr[i], p1 = rowptr[i + 1];
-  int k0 = 0, k1 = 0;
-  for (int32_t p = p0; p < p1; p++) {
-    if (col[p] < b.x) k0++;
-    if (col[p] < b.x + b.y) k1++;
-  }
-  split[i] = make_int2(k0, k1);
-}
-
 // ED_SPARSE_MAP (ED_SPARSE_MAP.f90:101-121 via ED_SETUP.f90:757-759): counting pass + ordered fill.
 // States of one impurity configuration appear in ascending sector index, so the position inside
 // the row is the number of earlier sector states with the same impurity bits.
@@ -433,105 +364,6 @@ static int upload_schedule(Sched &sc, const SchedHost &h) {
 }
 
 // ------------------------------------------------------------------------------------
-// Operator streams of the block-resident row pass (RowRes in ctx.h).  Blocks = runs of states sharing their
-// top t bits, t the smallest value with every block <= cap columns.  Inside a block the columns are sorted by
-// their number of in-block entries and dealt four to a warp task (one column per 8-lane group).
-// ------------------------------------------------------------------------------------
-static int build_rowres(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
-                        const std::vector<uint8_t> &code, bool fast, int64_t cap) {
-  Ctx &c = ctx();
-  RowRes &rr = op.rr;
-  int t = 0;
-  for (; t <= ns; t++) {
-    int64_t mx = 0;
-    for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, op.npart - k));
-    if (mx <= cap) break;
-  }
-  std::vector<int2> blk;
-  int64_t start = 0, mx = 0;
-  for (uint32_t P = 0; P < (1u << t); P++) {
-    const int64_t sz = binom64(ns - t, op.npart - __builtin_popcount(P));
-    if (sz <= 0) continue;
-    blk.push_back(make_int2((int)start, (int)sz));
-    start += sz;
-    mx = std::max(mx, sz);
-  }
-  if (start != op.n) return fail("internal: rowres blocks do not cover the sector");
-  std::vector<int32_t> tbase(blk.size() + 1, 0), task_col;
-  std::vector<uint4> task;
-  std::vector<uint32_t> win, woff;
-  const uint32_t NONE = fast ? 0xFFFFFFFFu : 0u;
-  auto word_in = [&](int64_t rel, uint32_t cd) -> uint32_t {
-    return fast ? ((cd & 1u) << 31) | ((uint32_t)rel << 7) | ((cd >> 1) & 1u) : ((uint32_t)rel << 7) | cd;
-  };
-  auto word_off = [&](int64_t j, uint32_t cd) -> uint32_t {
-    return fast ? ((cd & 1u) << 31) | ((uint32_t)j << 1) | ((cd >> 1) & 1u) : ((uint32_t)j << 7) | cd;
-  };
-  for (size_t b = 0; b < blk.size(); b++) {
-    const int g0 = blk[b].x, ng = blk[b].y;
-    tbase[b] = (int32_t)task.size();
-    std::vector<int32_t> order(ng), nin(ng, 0);
-    for (int k = 0; k < ng; k++) {
-      order[k] = k;
-      for (int32_t p = rowptr[g0 + k]; p < rowptr[g0 + k + 1]; p++) nin[k] += (col[p] >= g0 && col[p] < g0 + ng);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return nin[x] > nin[y]; });
-    for (int k0 = 0; k0 < ng; k0 += 4) {
-      int cols[4], kin = 0, koff = 0;
-      for (int q = 0; q < 4; q++) {
-        cols[q] = k0 + q < ng ? order[k0 + q] : -1;
-        if (cols[q] >= 0) {
-          const int len = rowptr[g0 + cols[q] + 1] - rowptr[g0 + cols[q]];
-          kin = std::max(kin, nin[cols[q]]);
-          koff = std::max(koff, len - nin[cols[q]]);
-        }
-        task_col.push_back(cols[q]);
-      }
-      const int nq = (kin + 3) / 4;
-      const size_t qb = win.size() / 16, ob = woff.size() / 4;
-      task.push_back(make_uint4((uint32_t)qb, (uint32_t)nq, (uint32_t)ob, (uint32_t)koff));
-      win.resize(win.size() + (size_t)nq * 16, word_in(ng, 0));  // idle steps read the zero line behind the tile
-      woff.resize(woff.size() + (size_t)koff * 4, NONE);
-      for (int q = 0; q < 4; q++) {
-        if (cols[q] < 0) continue;
-        int ki = 0, ko = 0;
-        for (int32_t p = rowptr[g0 + cols[q]]; p < rowptr[g0 + cols[q] + 1]; p++) {
-          const int32_t j = col[p];
-          if (j >= g0 && j < g0 + ng) {
-            win[(qb + ki / 4) * 16 + q * 4 + (ki & 3)] = word_in(j - g0, code[p]);  // uint4 (4 steps) per quad and group
-            ki++;
-          } else {
-            woff[(ob + ko) * 4 + q] = word_off(j, code[p]);
-            ko++;
-          }
-        }
-      }
-    }
-  }
-  tbase[blk.size()] = (int32_t)task.size();
-  rr.nblocks = (int32_t)blk.size();
-  rr.max_block = (int32_t)mx;
-  rr.ntask = (int32_t)task.size();
-  rr.fmt = fast ? 1 : 0;
-  win.resize(win.size() + 64, 0u);  // slack for the one-quad-ahead prefetch
-  woff.resize(woff.size() + 16, NONE);
-  CB_CHECK(dev_alloc(&rr.blocks, (int64_t)blk.size()));
-  CB_CHECK(dev_alloc(&rr.tbase, (int64_t)tbase.size()));
-  CB_CHECK(dev_alloc(&rr.task, (int64_t)task.size()));
-  CB_CHECK(dev_alloc(&rr.task_col, (int64_t)task_col.size()));
-  CB_CHECK(dev_alloc(&rr.win, (int64_t)win.size()));
-  CB_CHECK(dev_alloc(&rr.woff, (int64_t)woff.size()));
-  CB_CUDA(cudaMemcpyAsync(rr.blocks, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(rr.tbase, tbase.data(), tbase.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(rr.task, task.data(), task.size() * sizeof(uint4), cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(rr.task_col, task_col.data(), task_col.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(rr.win, win.data(), win.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaMemcpyAsync(rr.woff, woff.data(), woff.size() * 4, cudaMemcpyHostToDevice, c.stream));
-  CB_CUDA(cudaStreamSynchronize(c.stream));
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------
 // Block-split schedules (ColBlk in ctx.h) for columns larger than shared memory: one build_schedule_host per
 // row block on the in-block part of the CSR (relative indices) plus, per warp task, the off-block entries of
 // its 32 rows as a lane-parallel stream.  code3 of an off-block fast word: class (2 bits) | imaginary << 2.
@@ -672,7 +504,7 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
 }
 
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
-                  double const_add, bool want_csr, bool pack_swizzled) {
+                  double const_add, bool want_csr) {
   Ctx &c = ctx();
   const int ns = c.ns;
   op.npart = npart;
@@ -734,54 +566,8 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
     CB_CHECK(dev_alloc(&op.ell_val, (int64_t)op.ell_w * op.n));
     LAUNCH_1D(k_csr_to_ell, op.n, op.n, op.rowptr, op.col, op.val, op.ell_w, op.ell_col, op.ell_val);
   }
-  // row blocks by the top tbits bits: smallest tbits with every block <= tile_rows
-  {
-    const int64_t cap = std::max<int64_t>(8, c.opt.tile_rows);
-    int t = 0;
-    for (; t <= ns; t++) {
-      int64_t mx = 0;
-      for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, npart - k));
-      if (mx <= cap) break;
-    }
-    op.tbits = t;
-    std::vector<int2> blk;
-    int64_t start = 0, mx = 0;
-    for (uint32_t P = 0; P < (1u << t); P++) {
-      int64_t sz = binom64(ns - t, npart - __builtin_popcount(P));
-      if (sz <= 0) continue;
-      blk.push_back(make_int2((int)start, (int)sz));
-      start += sz;
-      mx = std::max(mx, sz);
-    }
-    if (start != op.n) return fail("internal: row blocks do not cover the sector");
-    op.nblocks = (int32_t)blk.size();
-    op.max_block = (int32_t)mx;
-    CB_CHECK(dev_alloc(&op.blocks, (int64_t)blk.size()));
-    CB_CUDA(cudaMemcpyAsync(op.blocks, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
-  }
-  // second, finer decomposition for the L1-blocked row pass (block x 32 rows x 16 B must stay in L1)
-  {
-    const int64_t cap = std::max<int64_t>(8, c.opt.l1_rows);
-    int t = 0;
-    for (; t <= ns; t++) {
-      int64_t mx = 0;
-      for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, npart - k));
-      if (mx <= cap) break;
-    }
-    std::vector<int2> blk;
-    int64_t start = 0;
-    for (uint32_t P = 0; P < (1u << t); P++) {
-      int64_t sz = binom64(ns - t, npart - __builtin_popcount(P));
-      if (sz <= 0) continue;
-      blk.push_back(make_int2((int)start, (int)sz));
-      start += sz;
-    }
-    op.nblocks_l1 = (int32_t)blk.size();
-    CB_CHECK(dev_alloc(&op.blocks_l1, (int64_t)blk.size()));
-    CB_CUDA(cudaMemcpyAsync(op.blocks_l1, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
-  }
-  // packed tile CSR: distinct signed coefficients -> 7-bit ids (host; the matrices are small)
-  if (want_csr && op.nnz > 0 && op.n < (1 << 21) && (int64_t)op.max_block < (1 << 18)) {
+  // distinct signed coefficients -> 7-bit ids (host; the per-spin matrices are small)
+  if (want_csr && op.nnz > 0 && op.n < (1 << 21)) {
     std::vector<double2> hval(op.nnz);
     CB_CUDA(cudaMemcpyAsync(hval.data(), op.val, op.nnz * sizeof(double2), cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
@@ -801,37 +587,10 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
       ids[k] = (uint8_t)found;
     }
     if (ok) {
-      uint8_t *d_ids = nullptr;
-      int32_t *d_rounds = nullptr;
-      CB_CHECK(dev_alloc(&d_ids, op.nnz));
-      CB_CHECK(dev_alloc(&d_rounds, op.n));
-      CB_CUDA(cudaMemcpyAsync(d_ids, ids.data(), op.nnz, cudaMemcpyHostToDevice, c.stream));
-      int32_t *d_rounds2 = nullptr;
-      CB_CHECK(dev_alloc(&d_rounds2, op.n));
-      CB_CHECK(dev_alloc(&op.pk_in_ptr, op.n + 1));
-      CB_CHECK(dev_alloc(&op.pk_off_ptr, op.n + 1));
-      LAUNCH_1D(k_pk_rounds, op.n, op.n, op.rowptr, op.col, op.blocks, op.nblocks, d_rounds, d_rounds2);
-      k_exclusive_scan<<<1, 1024, 0, c.stream>>>(op.n, d_rounds, op.pk_in_ptr);
-      k_exclusive_scan<<<1, 1024, 0, c.stream>>>(op.n, d_rounds2, op.pk_off_ptr);
-      c.launches += 2;
-      int32_t tot_in = 0, tot_off = 0;
-      CB_CUDA(cudaMemcpyAsync(&tot_in, op.pk_in_ptr + op.n, 4, cudaMemcpyDeviceToHost, c.stream));
-      CB_CUDA(cudaMemcpyAsync(&tot_off, op.pk_off_ptr + op.n, 4, cudaMemcpyDeviceToHost, c.stream));
-      CB_CUDA(cudaStreamSynchronize(c.stream));
-      CB_CHECK(dev_alloc(&op.pk_in, (int64_t)tot_in * 8));
-      CB_CHECK(dev_alloc(&op.pk_off, (int64_t)tot_off * 8));
-      LAUNCH_1D(k_pk_fill, op.n, op.n, op.rowptr, op.col, d_ids, op.blocks, op.nblocks, op.pk_in_ptr, op.pk_off_ptr,
-                pack_swizzled ? 1 : 0, op.pk_in, op.pk_off);
-      cudaFree(d_rounds2);
-      CB_CHECK(dev_alloc(&op.rowsplit, op.n));
-      LAUNCH_1D(k_rowsplit, op.n, op.n, op.rowptr, op.col, op.blocks, op.nblocks, op.rowsplit);
-      CB_CHECK(dev_alloc(&op.pkell, (int64_t)op.ell_w * op.n));
-      LAUNCH_1D(k_pkell_fill, op.n, op.n, op.rowptr, op.col, d_ids, op.ell_w, op.pkell);
       op.ncoef = (int32_t)table.size();
       CB_CHECK(dev_alloc(&op.coef, 128));
       table.resize(128, make_double2(0.0, 0.0));
       CB_CUDA(cudaMemcpyAsync(op.coef, table.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice, c.stream));
-      op.pk_swizzled = pack_swizzled;
       CB_CUDA(cudaStreamSynchronize(c.stream));
       std::vector<int32_t> hrp, hcol;
       if (op.n < (1 << 24)) {
@@ -883,8 +642,12 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
           }
         }
       }
-      // operator streams of the block-resident row pass
-      if (op.n < (1 << 24)) CB_CHECK(build_rowres(op, ns, hrp, hcol, code, fast, std::max<int64_t>(8, std::min<int64_t>(1760, c.opt.rowres_cols))));
+      // operator streams of the tile-resident row pass (rowtile.cu)
+      if (!hrp.empty()) {
+        const bool f4 = (fast || fast4) && c.opt.fast4;
+        const int64_t cap = c.opt.rowres_cols > 0 ? std::min<int64_t>(c.opt.rowres_cols, rowtile_cap()) : rowtile_cap();
+        CB_CHECK(build_rowtile(op, ns, hrp, hcol, f4 ? (fast ? code : code4) : ids, f4 ? 1 : 0, std::max<int64_t>(4, cap)));
+      }
       // schedules of the column-resident kernels (only when a column can live in shared memory)
       if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 24)) {
         const bool natural = c.opt.sched == 0;
@@ -938,8 +701,6 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
           CB_CHECK(build_colblk(op, op.cb16, ns, hrp, hcol, codeb, 16, fmtb, c.opt.sched == 0, cap, hf.data(), hmu.data()));
         }
       }
-      cudaFree(d_ids);
-      cudaFree(d_rounds);
     }
   }
   CB_CUDA(cudaStreamSynchronize(c.stream));
@@ -952,7 +713,7 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
 void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
-  dev_free(op.rowlen); dev_free(op.blocks); dev_free(op.blocks_l1); dev_free(op.pkell); dev_free(op.rowsplit); dev_free(op.pk_in); dev_free(op.pk_off); dev_free(op.pk_in_ptr); dev_free(op.pk_off_ptr); dev_free(op.coef);
+  dev_free(op.rowlen); dev_free(op.coef);
   dev_free(op.rr.blocks); dev_free(op.rr.tbase); dev_free(op.rr.task); dev_free(op.rr.task_col); dev_free(op.rr.win); dev_free(op.rr.woff);
   for (ColBlk *cb : {&op.cb8, &op.cb16}) {
     dev_free(cb->blk); dev_free(cb->tbase); dev_free(cb->qbase); dev_free(cb->meta); dev_free(cb->words); dev_free(cb->toff); dev_free(cb->woff);
@@ -1071,10 +832,7 @@ int cdmft_b200_build_hv_sector(int32_t isector, int32_t mode, int64_t *nloc) {
   c.hsector = isector;
   c.mode = mode;
   CB_CHECK(build_spin_op(c.up, nup, c.terms_up, c.e_up, c.const0, mode == CDMFT_B200_SPARSE));
-  // Hdw acts on the contiguous index of the transposed vector when sharded (column pass, swizzled
-  // tile) and on the strided index of v otherwise (row pass, natural tile)
-  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE,
-                         c.spmd || c.sim || c.opt.force_sharded));
+  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE));
   c.dimup = c.up.n; c.dimdw = c.dw.n; c.dim = c.dimup * c.dimdw;
   c.p_eff = (int)std::min<int64_t>(c.nranks, c.dimdw);
   c.rk.clear();

@@ -48,8 +48,8 @@ def test_fullsize_properties(ed, wl):
     w = _hxv(ed, n, c1 * u + c2 * v)
     assert _rel(w, c1 * hu + c2 * hv) < 1e-12
     # every SPARSE kernel variant agrees with the default one
-    for opts in [dict(colpass_variant=1), dict(fast4=0), dict(rowpass_variant=4), dict(rowpass_variant=4, rowres_cols=260), dict(sched=0), dict(colpass_variant=5), dict(colpass_variant=4), dict(colpass_variant=0, rowpass_variant=0), dict(colpass_variant=2, rowpass_variant=2),
-                 dict(colpass_variant=1, rowpass_variant=3), dict(force_sharded=1)]:
+    for opts in [dict(colpass_variant=1), dict(fast4=0), dict(rowpass_variant=1), dict(rowres_cols=260), dict(tma2d=0), dict(sched=0),
+                 dict(colpass_variant=1, rowpass_variant=1), dict(force_sharded=1)]:
         ed.delete_Hv_sector()
         for k, val in opts.items():
             ed.set_option(k, val)
@@ -58,7 +58,7 @@ def test_fullsize_properties(ed, wl):
             assert _rel(_hxv(ed, n, v), hv) < RTOL, opts
         finally:
             for k in opts:
-                ed.set_option(k, {"colpass_variant": 6, "rowpass_variant": 1, "force_sharded": 0, "sched": 1, "rowres_cols": 570, "fast4": 1}[k])
+                ed.set_option(k, {"colpass_variant": 6, "rowpass_variant": 4, "force_sharded": 0, "sched": 1, "rowres_cols": 0, "fast4": 1, "tma2d": 1}[k])
     # DIRECT (matrix-free) == SPARSE
     ed.delete_Hv_sector()
     ed.build_Hv_sector(isec, False)

@@ -242,35 +242,26 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
 
 
 @pytest.mark.parametrize("opts", [
-    dict(rowpass_variant=4, rowres_cols=570),                  # block-resident row pass (TMA-staged tiles)
-    dict(rowpass_variant=4, rowres_cols=9),                    # ... many small blocks: mostly off-block gathers
-    dict(rowpass_variant=4, rowres_cols=40),
-    dict(rowpass_variant=4, rowres_cols=1760),                 # ... one block
-    dict(colpass_variant=6, sched=1),                          # column-resident kernel, edge-coloured schedule (default)
-    dict(colpass_variant=6, sched=0),                          # ... natural CSR order
+    dict(),                                                    # defaults: tile-resident row pass writes, column-resident pass accumulates
+    dict(tma2d=0),                                             # tiles by per-column bulk copies instead of 2-D TMA tensor copies
+    dict(rowres_cols=9),                                       # many small blocks: mostly off-block gathers
+    dict(rowres_cols=9, tma2d=0),
+    dict(rowres_cols=40),
+    dict(rowres_cols=100, fast4=0),                            # coefficient-table decode instead of sign/class/phase bits
+    dict(fast4=0),
+    dict(colpass_variant=1),                                   # tile-resident row pass accumulating after the generic column pass
+    dict(colpass_variant=1, rowres_cols=33, tma2d=0),
+    dict(rowpass_variant=1),                                   # generic L2-slab row pass after the column-resident kernel
+    dict(colpass_variant=6, sched=0),                          # column-resident kernel, natural CSR order
     dict(colpass_variant=6, colres_rows=40),                   # block-split column-resident kernel (Ns=18 path), forced small blocks
     dict(colpass_variant=6, colres_rows=9, sched=0),
     dict(colpass_variant=6, colres_rows=130, force_sharded=1),
     dict(colpass_variant=6, colres_rows=40, fast4=0),
-    dict(colpass_variant=6, fast4=0),                          # ... coefficient-table decode instead of sign/class/phase bits
-    dict(colpass_variant=6, force_sharded=1),                  # ... on both spins (transposed layout)
+    dict(colpass_variant=6, force_sharded=1),                  # column-resident kernel on both spins (transposed layout)
     dict(colpass_variant=1, rowpass_variant=1, col_batch=1),   # generic global-gather kernels
     dict(colpass_variant=1, rowpass_variant=1, col_batch=8),
-    dict(row_rb=4, row_slab=256), dict(row_rb=1, row_slab=256), dict(row_rb=1, row_slab=64),
-    dict(colpass_variant=0, rowpass_variant=0, tile_rows=1800),  # shared-memory tiles, one block
-    dict(colpass_variant=0, rowpass_variant=0, tile_rows=40),    # many row blocks: off-block gathers
-    dict(colpass_variant=0, rowpass_variant=0, tile_rows=9),
-    dict(colpass_variant=0, rowpass_variant=1, tile_rows=25, force_sharded=1),
-    dict(colpass_variant=2, rowpass_variant=2, tile_rows=40),    # unpacked tile kernels
-    dict(colpass_variant=1, rowpass_variant=3, l1_rows=256),     # L1-blocked row pass
-    dict(colpass_variant=4, rowpass_variant=1, tile_rows=1800),  # rotating-slot shared-memory column pass
-    dict(colpass_variant=4, rowpass_variant=1, tile_rows=21),
-    dict(colpass_variant=5, tile_rows=1800),   # in-block Hup in shared memory, off-block Hup folded into the row pass
-    dict(colpass_variant=5, tile_rows=21),
-    dict(colpass_variant=5, tile_rows=33, force_sharded=1),
-    dict(colpass_variant=4, rowpass_variant=1, tile_rows=50, force_sharded=1),
-    dict(colpass_variant=0, rowpass_variant=3, l1_rows=12),
-    dict(colpass_variant=2, rowpass_variant=0, tile_rows=30, force_sharded=1),
+    dict(rowpass_variant=1, row_rb=4, row_slab=256), dict(rowpass_variant=1, row_rb=1, row_slab=256),
+    dict(rowpass_variant=1, row_rb=1, row_slab=64), dict(rowpass_variant=1, row_rb=1, row_slab=1024),
 ])
 @pytest.mark.parametrize("name", ["hm2x2_nb2", "bhz2_nb1", "rand_c_L2O2B1_S2"])
 def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
@@ -279,7 +270,7 @@ def test_kernel_variants_agree_with_oracle(ed, oracle_lib, name, opts):
     mdl = MODELS[name]()
     orc = oracle_lib.Oracle(mdl)
     ed.ed_set_model(mdl)
-    defaults = dict(colpass_variant=6, sched=1, fast4=1, colres_rows=0, rowpass_variant=1, rowres_cols=570, col_batch=4, tile_rows=1800, force_sharded=0, l1_rows=256, row_rb=2, row_slab=128)
+    defaults = dict(colpass_variant=6, sched=1, fast4=1, colres_rows=0, rowpass_variant=4, rowres_cols=0, tma2d=1, col_batch=4, force_sharded=0, row_rb=2, row_slab=128)
     try:
         for k, v in {**defaults, **opts}.items():
             ed.set_option(k, v)

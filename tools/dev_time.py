@@ -29,7 +29,9 @@ def time_hxv(n, iters=10, warm=3):
     return s.elapsed_time(e) / iters
 
 
-SWEEP = [dict(colpass_variant=6, sched=1), dict(colpass_variant=6, sched=0), dict(colpass_variant=1), dict(rowpass_variant=4)]
+SWEEP = [dict(), dict(tma2d=0), dict(rowpass_variant=1), dict(row_slab=256), dict(row_slab=64), dict(rowres_cols=480)]
+if os.environ.get("DEV_SWEEP"):
+    SWEEP = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in grp.split(",") if kv) for grp in os.environ["DEV_SWEEP"].split(";")]
 
 
 def main():
@@ -41,7 +43,7 @@ def main():
     isec = models.get_sector(mdl.ns, *sec)
     for sparse in (True,):
         for opts in SWEEP:
-            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=6, sched=1, rowpass_variant=1, rowres_cols=570, tile_rows=1800, l1_rows=256, row_rb=2, row_slab=128).items():
+            for k, v in dict(col_batch=4, force_sharded=0, colpass_variant=6, sched=1, rowpass_variant=4, rowres_cols=0, tma2d=1, row_rb=2, row_slab=128).items():
                 E.set_option(k, v)
             for k, v in opts.items():
                 E.set_option(k, v)
