@@ -53,17 +53,17 @@ struct ColBlk {
 // Operator streams of the tile-resident row pass (k_rowtile, rowtile.cu).  Columns (states of this spin) are cut
 // into blocks = runs of states sharing their leading bits; a work item is one block x 8 rows of the other spin's
 // index, kept in shared memory; per warp task of 4 columns (one per 8-lane group) the in-block entries run against
-// the tile and the off-block entries (hops that change the leading bits) against global memory / L2.
+// the tile and the off-block entries (hops that change the leading bits) against global memory / L2.  Every
+// (block, warp) owns contiguous runs of the three streams.
 struct RowRes {
-  int32_t nblocks = 0, max_block = 0, ntask = 0;
-  int32_t fmt = 0;              // 0 = coefficient-table ids, 1 = sign / class / phase bits
+  int32_t nblocks = 0, max_block = 0, ntask = 0, nwarps = 0;
+  int32_t fmt = 0;              // 0 = coefficient-table ids, 1 = sign / class bits (real H), 2 = sign / class / phase bits
   double in_frac = 0.0;         // share of the entries whose source lies inside the block
   int2 *blocks = nullptr;       // [nblocks] (first column, columns)
-  int32_t *tbase = nullptr;     // [nblocks+1] first task of each block
-  uint4 *task = nullptr;        // [ntask] {first in-block quad, in-block quads, first off-block step, off-block steps}
-  int32_t *task_col = nullptr;  // [ntask*4] column (relative to the block) of each lane group, -1 = none
-  uint32_t *win = nullptr;      // [quads*4 groups] uint4: 4 steps; word formats in rowtile.cu
-  uint32_t *woff = nullptr;     // [steps*4 groups]
+  int4 *wbase = nullptr;        // [nblocks*nwarps] {first task, tasks, first in-block unit, first off-block step}
+  uint32_t *thdr = nullptr;     // [ntask*4 groups] column (0xFFFF = none) | quads << 16 | off-block steps << 24
+  uint4 *win = nullptr;         // [units*4 groups] 8 (16-bit words) or 4 (32-bit words) steps of one lane group; formats in rowtile.cu
+  uint4 *woff = nullptr;        // [steps] one off-block word per lane group
 };
 
 // Per-spin operator of the active sector: Hs(s)%map + spH0ups(1)/spH0dws(1).
@@ -122,8 +122,9 @@ struct Options {
   int64_t colpass_variant = 6;
   int64_t sched = 1;            // 1 = conflict-free edge-coloured schedule, 0 = natural CSR order (for comparison)
   int64_t colres_rows = 0;      // > 0: force the block-split column-resident kernel with at most this many rows per block
-  // row pass: 4 = tile-resident shared-memory kernel (default in SPARSE mode), 1 = generic L2-slab kernel
-  int64_t rowpass_variant = 4;
+  // row pass: 1 = generic L2-slab kernel (default: 2.77 ms at K3), 4 = tile-resident shared-memory kernel (3.2 ms at K3:
+  // HBM traffic is algorithmic, but the off-block gathers and the register budget keep it latency-bound)
+  int64_t rowpass_variant = 1;
   int64_t rowres_cols = 0;      // > 0: cap on the columns of a row-pass block (default: what two tile buffers hold)
   int64_t tma2d = 1;            // row pass tiles by 2-D TMA tensor copies (0: one 128-byte bulk copy per column)
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
@@ -194,6 +195,7 @@ struct Ctx {
   bool dot_final_rowpass = false;  // the accumulating row pass is the last contribution to H x v
   double *dot_partial = nullptr;
   int64_t dot_cap = 0, dot_npartial = 0;
+  unsigned int *rt_queue = nullptr;  // work queue of the tile-resident row pass (rowtile.cu)
   double *red = nullptr;       // device reduction scratch
   double *red_host = nullptr;  // pinned
 };

@@ -235,7 +235,7 @@ int cdmft_b200_finalize(void) {
   if (c.hstatus) cdmft_b200_delete_hv_sector();
   cudaStreamSynchronize(c.stream);
   if (c.nccl_comm) { nccl.CommDestroy(c.nccl_comm); c.nccl_comm = nullptr; }
-  dev_free(c.red); dev_free(c.cross_tab); dev_free(c.dot_partial); c.dot_cap = 0;
+  dev_free(c.red); dev_free(c.rt_queue); dev_free(c.cross_tab); dev_free(c.dot_partial); c.dot_cap = 0;
   dev_free(c.stage_v); dev_free(c.stage_hv); c.stage_n = 0;
   for (auto &k : c.kv) dev_free(k);
   c.kv_n = 0;

@@ -646,7 +646,7 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
       if (!hrp.empty()) {
         const bool f4 = (fast || fast4) && c.opt.fast4;
         const int64_t cap = c.opt.rowres_cols > 0 ? std::min<int64_t>(c.opt.rowres_cols, rowtile_cap()) : rowtile_cap();
-        CB_CHECK(build_rowtile(op, ns, hrp, hcol, f4 ? (fast ? code : code4) : ids, f4 ? 1 : 0, std::max<int64_t>(4, cap)));
+        CB_CHECK(build_rowtile(op, ns, hrp, hcol, f4 ? (fast ? code : code4) : ids, f4 ? (fast ? 1 : 2) : 0, std::max<int64_t>(4, cap)));
       }
       // schedules of the column-resident kernels (only when a column can live in shared memory)
       if ((size_t)op.n * 8 + 4096 <= 232448 && op.n < (1 << 24)) {
@@ -714,7 +714,7 @@ void free_spin_op(SpinOp &op) {
   dev_free(op.map); dev_free(op.lin_lo); dev_free(op.lin_hi); dev_free(op.f); dev_free(op.terms);
   dev_free(op.rowptr); dev_free(op.col); dev_free(op.val); dev_free(op.ell_col); dev_free(op.ell_val);
   dev_free(op.rowlen); dev_free(op.coef);
-  dev_free(op.rr.blocks); dev_free(op.rr.tbase); dev_free(op.rr.task); dev_free(op.rr.task_col); dev_free(op.rr.win); dev_free(op.rr.woff);
+  dev_free(op.rr.blocks); dev_free(op.rr.wbase); dev_free(op.rr.thdr); dev_free(op.rr.win); dev_free(op.rr.woff);
   for (ColBlk *cb : {&op.cb8, &op.cb16}) {
     dev_free(cb->blk); dev_free(cb->tbase); dev_free(cb->qbase); dev_free(cb->meta); dev_free(cb->words); dev_free(cb->toff); dev_free(cb->woff);
   }

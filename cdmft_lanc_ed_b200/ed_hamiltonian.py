@@ -23,7 +23,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcdmft_b200.so")
+# CDMFT_B200_LIB: developer override (kernel experiments build several libraries side by side)
+LIB_PATH = os.environ.get("CDMFT_B200_LIB") or os.path.join(_PKG, "libcdmft_b200.so")
 
 SPARSE, DIRECT = 1, 0  # ed_sparse_H = T / F (ED_INPUT_VARS.f90:145)
 
