@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -136,6 +137,8 @@ struct Options {
   int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the last pass of H x v
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
+  int64_t lanczos_batch = 4;    // Krylov drivers: steps enqueued between two read-backs of (alfa, beta)
+  int64_t lanczos_store = 1;    // ground-state driver: keep the Krylov vectors in HBM when they fit (no second pass)
 };
 
 struct Ctx {
@@ -172,6 +175,7 @@ struct Ctx {
   int64_t dim = 0, dimup = 0, dimdw = 0;
   int p_eff = 1;  // min(P, DimDw)
   SpinOp up, dw;
+  std::map<int, SpinOp *> map_ops;  // map-only SpinOps per particle number (apply_op), valid for the current model
   std::vector<RankState> rk;
   // CUDA-IPC peer windows (SPMD, optional): peers' vt and recvbuf mapped into this process so the
   // transposing kernel stores straight into the destination GPU over NVLink (pack + exchange + unpack
@@ -197,6 +201,10 @@ struct Ctx {
   int64_t dot_cap = 0, dot_npartial = 0;
   unsigned int *rt_queue = nullptr;  // work queue of the tile-resident row pass (rowtile.cu)
   double *red = nullptr;       // device reduction scratch
+  double *lz_hist = nullptr;   // device history of the Krylov drivers: (alfa_j, beta_{j+1}) per step
+  int lz_hist_cap = 0;
+  std::vector<void *> lz_slots;  // Krylov-vector slots of the ground-state driver (freed with the sector)
+  size_t lz_slot_bytes = 0;
   double *red_host = nullptr;  // pinned
 };
 
@@ -224,6 +232,9 @@ void set_error(const std::string &s);
 int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, const std::vector<double> &e,
                   double const_add, bool want_csr);
 void free_spin_op(SpinOp &op);
+int cached_map_op(int npart, const SpinOp **out);  // lanczos.cu
+void free_map_ops();
+void lz_free_slots();  // lanczos.cu
 int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
 int build_rowtile(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
                   const std::vector<uint8_t> &code, int fmt, int64_t cap);  // rowtile.cu

@@ -547,7 +547,8 @@ static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs) {
   const int P = c.p_eff;
   // measured on B200 (K3): peer-memory transposes win at P=2 (8.4 vs 8.7 ms), the overlapped NCCL path wins
   // at P=4 (4.6 vs 4.9) and P=8 (2.5 vs 2.8) -> use_ipc 1 = auto (P<=2), 2 = always, 0 = never
-  const bool use_ipc = c.spmd && P > 1 && !c.rk.empty() && c.ipc_ready &&
+  // (the stream-ordered barriers of that path span the full communicator: only when no rank was shrunk away)
+  const bool use_ipc = c.spmd && P > 1 && P == c.nranks && !c.rk.empty() && c.ipc_ready &&
                        (c.opt.use_ipc == 2 || (c.opt.use_ipc == 1 && P <= 2));
   const bool overlap = !use_ipc && c.spmd && P > 1 && !c.rk.empty() && c.opt.overlap && c.comm_stream;
   if (use_ipc) {

@@ -7,7 +7,8 @@
 // and from the reference itself
 //   vvinit = c^+_is|gs>, c_is|gs>, mixed channels       ED_GF_NORMAL.f90:180-199,244-266,590-620
 //   add_to_lanczos_gf_normal                              ED_GF_NORMAL.f90:915-975
-// The vectors never leave HBM between iterations; each iteration moves 2 scalars to the host.
+// The vectors never leave HBM between iterations and the scalars of the recurrence stay on the device; the
+// drivers read (alfa, beta) back once per batch of steps (option lanczos_batch).
 // Dot products use a fixed two-stage reduction tree -> bitwise reproducible run to run.
 #include <algorithm>
 #include <cmath>
@@ -181,25 +182,84 @@ static inline int hxv_t(const double *v, double *hv) { return hxv_device_real(v,
 // vector kernels move 96 B/state (one dot, one fused 3-term update + norm) instead of the textbook
 // 176 B/state (swap/scale, add+dot, axpy+norm); half of that in real mode.
 // ------------------------------------------------------------------------------------
+// The scalars of the recurrence never visit the host inside a step: beta_{j-1}, beta_j live in scal[0..1], the two
+// reductions of a step land in dotp[0] (Re<u_j, H u_j>) and nrm[0] (|u_{j+1}|^2) after their all-reduce, the update
+// kernel derives its three coefficients from them, and k_lz_advance appends (alfa_j, beta_{j+1}) to a device
+// history that the drivers read back once per batch of steps.
 template <typename T>
-__global__ void __launch_bounds__(256) k_lanczos_update(int64_t n, T *__restrict__ um, const T *__restrict__ u, const T *__restrict__ t,
-                                                        double ct, double cu, double cum, double2 *__restrict__ partial) {
+__global__ void __launch_bounds__(256) k_lanczos_update(int64_t n, T *out /* may alias um */, const T *um, const T *__restrict__ u,
+                                                        const T *__restrict__ t, const double *__restrict__ scal,
+                                                        const double *__restrict__ dotp, double2 *__restrict__ partial) {
+  const double bp = scal[0], bc = scal[1];
+  const double a = dotp[0] / (bc * bc);
+  const double ct = 1.0 / bc, cu = a / bc, cum = bc / bp;
   double re = 0, im = 0;
   GRID_STRIDE(i, n) {
     const T y = lin3(ct, t[i], cu, u[i], cum, um[i]);
-    um[i] = y;
+    out[i] = y;
     re += norm2(y);
   }
   block_sum2(re, im);
   if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(re, 0.0);
+}
+// eigenvector assembly from stored Krylov vectors: acc (=|+=) sum_k z[k] v[k], terms added in ascending k with
+// one fma each -- the same operations, in the same order, as the step-by-step axpy of the two-pass scheme
+constexpr int kAsmVecs = 8;
+template <typename T>
+struct AsmArgs {
+  const T *v[kAsmVecs];
+  double z[kAsmVecs];
+  int nv;
+  int first;  // 1: acc starts from zero
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_assemble(int64_t n, T *__restrict__ acc, AsmArgs<T> a) {
+  GRID_STRIDE(i, n) {
+    T x;
+    if (a.first) set_real(x, 0.0); else x = acc[i];
+#pragma unroll
+    for (int k = 0; k < kAsmVecs; k++)
+      if (k < a.nv) x = axpy1(x, a.z[k], a.v[k][i]);
+    acc[i] = x;
+  }
+}
+__global__ void k_lz_init(double *scal) { scal[0] = scal[1] = 1.0; }
+__global__ void k_lz_advance(double *scal, const double *__restrict__ dotp, const double *__restrict__ nrm, double *__restrict__ hist,
+                             int iter /*0-based*/) {
+  const double bc = scal[1];
+  const double bn = sqrt(nrm[0]);
+  hist[2 * iter] = dotp[0] / (bc * bc);
+  hist[2 * iter + 1] = bn;
+  scal[0] = bc;
+  scal[1] = bn;
 }
 
 template <typename T>
 struct LanczosRun {
   int64_t n = 0;
   T *um = nullptr, *u = nullptr, *t = nullptr;  // u_{j-1}, u_j, H u_j
-  double beta_prev = 1.0, beta_cur = 1.0;
+  T *next = nullptr;                             // != nullptr: u_{j+1} is written here (Krylov vectors are kept) instead of over u_{j-1}
+  int steps = 0;                                 // steps enqueued since lanczos_start
 };
+
+static double *lz_scal() { return ctx().red + 2 * kRedBlocks + 8; }  // [2]
+static double *lz_dot() { return ctx().red + 2 * kRedBlocks; }       // [2]
+static double *lz_nrm() { return ctx().red + 2 * kRedBlocks + 2; }   // [2]
+static int lz_hist_reserve(int nsteps) {
+  Ctx &c = ctx();
+  if (c.lz_hist_cap >= nsteps) return 0;
+  dev_free(c.lz_hist);
+  CB_CHECK(dev_alloc(&c.lz_hist, (int64_t)2 * nsteps));
+  c.lz_hist_cap = nsteps;
+  return 0;
+}
+// stage-2 reduction of the partials in c.red into out[0..1] + all-reduce over ranks; stays on the device
+static int finish_reduce_dev(double *out) {
+  Ctx &c = ctx();
+  k_reduce_final<<<1, 256, 0, c.stream>>>(kRedBlocks, (const double2 *)c.red, out);
+  c.launches++;
+  return nccl_allreduce_sum(out, 2);
+}
 
 // u holds the start vector on entry; normalises it (iter == 1 branch of lanczos_iteration)
 template <typename T>
@@ -216,48 +276,65 @@ static int lanczos_start(LanczosRun<T> &L) {
     CB_CUDA(cudaMemsetAsync(L.um, 0, (size_t)L.n * sizeof(T), c.stream));
     prof_end();
   }
-  L.beta_prev = L.beta_cur = 1.0;
+  k_lz_init<<<1, 1, 0, c.stream>>>(lz_scal());
+  c.launches++;
+  L.steps = 0;
   return 0;
 }
 
-// one Lanczos step; on return alfa = alfa_j, beta = beta_{j+1}; the normalised vector of this step is
-// v_j = L.um / L.beta_prev (buffers are rotated)
+// enqueue one Lanczos step (no host synchronisation): (alfa_j, beta_{j+1}) go to the device history at position
+// L.steps; afterwards the normalised vector of this step is v_j = L.um / beta_j (buffers are rotated)
 template <typename T>
-static int lanczos_step(LanczosRun<T> &L, double *alfa, double *beta) {
+static int lanczos_step(LanczosRun<T> &L) {
   Ctx &c = ctx();
-  std::complex<double> z;
-  // alpha = Re<u, H u>: the row pass reduces it on the fly when it can (single rank, generic SPARSE row pass)
+  // alpha = Re<u, H u>: the last pass of H x v reduces it on the fly when it can (single rank)
   c.dot_request = c.opt.fuse_dot != 0;
   c.dot_done = false;
   int rc = hxv_t(L.u, L.t);
   c.dot_request = false;
   CB_CHECK(rc);
   prof_begin(4);
+  CB_CHECK(zero_partials());
   if (c.dot_done) {
-    CB_CHECK(zero_partials());
     k_sum_partials<<<kRedBlocks, 256, 0, c.stream>>>(c.dot_npartial, c.dot_partial, (double2 *)c.red);
     c.launches++;
-    CB_CHECK(finish_reduce(&z));
-  } else {
-    CB_CHECK(dot(L.n, L.u, L.t, &z));
+  } else if (L.n > 0) {
+    k_dot<T><<<std::min<unsigned>(vec_grid(L.n), kRedBlocks), 256, 0, c.stream>>>(L.n, L.u, L.t, (double2 *)c.red);
+    c.launches++;
   }
-  prof_end();
-  const double a = z.real() / (L.beta_cur * L.beta_cur);
+  CB_CHECK(finish_reduce_dev(lz_dot()));
   CB_CHECK(zero_partials());
   if (L.n > 0) {
-    prof_begin(4);
     k_lanczos_update<T><<<std::min<unsigned>(vec_grid(L.n), kRedBlocks), 256, 0, c.stream>>>(
-        L.n, L.um, L.u, L.t, 1.0 / L.beta_cur, a / L.beta_cur, L.beta_cur / L.beta_prev, (double2 *)c.red);
+        L.n, L.next ? L.next : L.um, L.um, L.u, L.t, lz_scal(), lz_dot(), (double2 *)c.red);
     c.launches++;
-    prof_end();
   }
-  CB_CHECK(finish_reduce(&z));
-  const double bnext = std::sqrt(z.real());
-  std::swap(L.um, L.u);
-  L.beta_prev = L.beta_cur;
-  L.beta_cur = bnext;
-  *alfa = a;
-  *beta = bnext;
+  CB_CHECK(finish_reduce_dev(lz_nrm()));
+  k_lz_advance<<<1, 1, 0, c.stream>>>(lz_scal(), lz_dot(), lz_nrm(), c.lz_hist, L.steps);
+  c.launches++;
+  prof_end();
+  if (L.next) {
+    L.um = L.u;
+    L.u = L.next;
+    L.next = nullptr;
+  } else {
+    std::swap(L.um, L.u);
+  }
+  L.steps++;
+  return 0;
+}
+// read steps [from, to) of the device history (one copy + one synchronisation per batch)
+static int lanczos_fetch(int from, int to, std::vector<double> &al, std::vector<double> &be) {
+  Ctx &c = ctx();
+  if (to <= from) return 0;
+  std::vector<double> h((size_t)2 * (to - from));
+  CB_CUDA(cudaMemcpyAsync(h.data(), c.lz_hist + 2 * from, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  CB_CUDA(cudaGetLastError());
+  for (int k = 0; k < to - from; k++) {
+    al.push_back(h[2 * k]);
+    be.push_back(h[2 * k + 1]);
+  }
   return 0;
 }
 
@@ -367,20 +444,81 @@ static int split_real(int64_t n, const double2 *z, double *r, double *im2) {
   return 0;
 }
 
+// Steps are enqueued in batches and (alfa, beta) read back once per batch; the stopping rules are then applied
+// step by step exactly as SciFortran applies them, so the number of steps REPORTED and every returned coefficient
+// are those of the step-by-step loop (steps enqueued past the stopping point are discarded).
 template <typename T>
 static int tridiag_run(LanczosRun<T> &L, int32_t nitermax, double threshold, double *alanc, double *blanc, int32_t *ndone) {
   for (int i = 0; i < nitermax; i++) { alanc[i] = 0; blanc[i] = 0; }
+  CB_CHECK(lz_hist_reserve(std::max(nitermax, 1)));
   CB_CHECK(lanczos_start(L));
-  double a = 0, b = 0;
+  std::vector<double> al, be;
   int done = 0;
-  for (int iter = 1; iter <= nitermax; iter++) {
-    CB_CHECK(lanczos_step(L, &a, &b));
-    alanc[iter - 1] = a;
-    done = iter;
-    if (std::fabs(b) < threshold) break;
-    if (iter < nitermax) blanc[iter] = b;
+  bool stop = false;
+  const int batch = (int)std::max<int64_t>(1, ctx().opt.lanczos_batch);
+  while (!stop && L.steps < nitermax) {
+    const int from = L.steps, to = std::min(nitermax, from + batch);
+    for (int k = from; k < to; k++) CB_CHECK(lanczos_step(L));
+    CB_CHECK(lanczos_fetch(from, to, al, be));
+    for (int iter = from + 1; iter <= to; iter++) {
+      alanc[iter - 1] = al[iter - 1];
+      done = iter;
+      if (std::fabs(be[iter - 1]) < threshold) { stop = true; break; }
+      if (iter < nitermax) blanc[iter] = be[iter - 1];
+    }
   }
   if (ndone) *ndone = done;
+  return 0;
+}
+
+// Pool of Krylov-vector slots (ground-state driver, "store" mode): HBM is large enough to keep every Lanczos
+// vector of a sector that fits one GPU many times over (K3, real vectors: 69 x 1.3 GB), so the eigenvector is
+// assembled from the stored vectors in one streaming pass instead of re-running the whole recurrence.
+static int lz_slot(int j, size_t bytes, void **out) {
+  Ctx &c = ctx();
+  if (c.lz_slot_bytes < bytes) {  // slots of another sector / element type: start over
+    for (void *p : c.lz_slots) cudaFree(p);
+    c.lz_slots.clear();
+    c.lz_slot_bytes = bytes;
+  }
+  while ((int)c.lz_slots.size() <= j) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(c.lz_slot_bytes, 16));
+    if (e != cudaSuccess) return fail("lanczos: cudaMalloc of a Krylov-vector slot failed: %s", cudaGetErrorString(e));
+    c.lz_slots.push_back(p);
+  }
+  *out = c.lz_slots[j];
+  return 0;
+}
+void lz_free_slots() {
+  Ctx &c = ctx();
+  for (void *p : c.lz_slots) cudaFree(p);
+  c.lz_slots.clear();
+  c.lz_slot_bytes = 0;
+}
+// how many slots every rank can afford (collective: all ranks get the same number)
+static int lz_slot_budget(size_t bytes, int want, int *out) {
+  Ctx &c = ctx();
+  size_t fr = 0, tot = 0;
+  CB_CUDA(cudaMemGetInfo(&fr, &tot));
+  const size_t have = c.lz_slot_bytes >= bytes ? c.lz_slots.size() : 0;
+  if (c.lz_slot_bytes < bytes) fr += c.lz_slots.size() * c.lz_slot_bytes;  // would be released first
+  const size_t reserve = std::max<size_t>((size_t)6 << 30, tot / 16);
+  size_t m = have + (fr > reserve ? (fr - reserve) / std::max<size_t>(bytes, 16) : 0);
+  m = std::min<size_t>(m, (size_t)want);
+  if (c.spmd && c.nranks > 1) {  // min over ranks = -max(-m): the library only loads the sum reduction
+    // sum of one-hot? keep it simple: gather every rank's value through a sum into its own cell
+    double *w = c.red + 3008;
+    if (2 * c.nranks + 3008 > 4096) return fail("lanczos: too many ranks for the scratch");
+    std::vector<double> mine(c.nranks, 0.0), all(c.nranks, 0.0);
+    mine[c.rank] = (double)m;
+    CB_CUDA(cudaMemcpyAsync(w, mine.data(), c.nranks * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    CB_CHECK(nccl_allreduce_sum(w, c.nranks));
+    CB_CUDA(cudaMemcpyAsync(all.data(), w, c.nranks * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    for (int r = 0; r < c.nranks; r++) m = std::min<size_t>(m, (size_t)all[r]);
+  }
+  *out = (int)m;
   return 0;
 }
 
@@ -390,23 +528,48 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
                   double *alanc_out, double *blanc_out) {
   Ctx &c = ctx();
   const int64_t nloc = L.n;
+  T *const kv_u = L.u, *const kv_um = L.um;
+  const size_t vbytes = (size_t)std::max<int64_t>(nloc, 1) * sizeof(T);
+  // store mode: slot[j] = u_{j+1} (slot[0] = normalised start vector); budget agreed between the ranks
+  int nslots = 0;
+  if (c.opt.lanczos_store) CB_CHECK(lz_slot_budget(vbytes, nitermax + 1, &nslots));
+  bool storing = nslots >= 3;
+  auto slot = [&](int j, T **p) -> int { void *q = nullptr; CB_CHECK(lz_slot(j, vbytes, &q)); *p = (T *)q; return 0; };
+  if (storing) CB_CHECK(slot(0, &L.u));
   if (nloc > 0) CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+  CB_CHECK(lz_hist_reserve(std::max(nitermax, 1)));
   CB_CHECK(lanczos_start(L));
   std::vector<double> al, bl;  // bl[i] couples i-1,i ; bl[0]=0
+  std::vector<double> ha, hb;  // history as fetched: alfa_j, beta_{j+1}
   std::vector<double> d, Z;
-  double a = 0, b = 0, esave = 0, e0 = 0;
-  for (int iter = 1; iter <= nitermax; iter++) {
-    CB_CHECK(lanczos_step(L, &a, &b));
-    al.push_back(a);
-    if ((int)bl.size() < (int)al.size()) bl.push_back(0.0);
-    if (std::fabs(b) < threshold) break;  // invariant subspace
-    if (iter < nitermax) bl.push_back(b);
-    d = al;
-    std::vector<double> e(bl.begin(), bl.begin() + al.size());
-    CB_CHECK(tridiag_eigh((int)al.size(), d, e, nullptr));
-    e0 = d[0];
-    if ((int)al.size() >= ncheck && std::fabs(e0 - esave) <= threshold) break;
-    esave = e0;
+  double esave = 0, e0 = 0;
+  bool stop = false;
+  const int batch = (int)std::max<int64_t>(1, c.opt.lanczos_batch);
+  while (!stop && L.steps < nitermax) {
+    // nothing can stop before ncheck steps except an invariant subspace: first batch = ncheck steps
+    const int from = L.steps;
+    const int to = std::min<int>(nitermax, from + (from == 0 ? std::max<int>(batch, std::min<int>(ncheck, 64)) : batch));
+    for (int k = from; k < to; k++) {
+      if (storing) {
+        if (k + 1 < nslots) CB_CHECK(slot(k + 1, &L.next));   // step k+1 writes u_{k+2} into slot k+1
+        else storing = false;  // out of slots: carry on in place (the eigenvector then needs the second pass)
+      }
+      CB_CHECK(lanczos_step(L));
+    }
+    CB_CHECK(lanczos_fetch(from, to, ha, hb));
+    for (int iter = from + 1; iter <= to; iter++) {
+      const double a = ha[iter - 1], b = hb[iter - 1];
+      al.push_back(a);
+      if ((int)bl.size() < (int)al.size()) bl.push_back(0.0);
+      if (std::fabs(b) < threshold) { stop = true; break; }  // invariant subspace
+      if (iter < nitermax) bl.push_back(b);
+      d = al;
+      std::vector<double> e(bl.begin(), bl.begin() + al.size());
+      CB_CHECK(tridiag_eigh((int)al.size(), d, e, nullptr));
+      e0 = d[0];
+      if ((int)al.size() >= ncheck && std::fabs(e0 - esave) <= threshold) { stop = true; break; }
+      esave = e0;
+    }
   }
   const int nlanc = (int)al.size();
   d = al;
@@ -415,19 +578,41 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
     CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
   }
   e0 = d[0];
-  // second pass: vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter (same recurrence, same start)
-  if (nloc > 0) {
-    CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
-    CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * sizeof(T), c.stream));
-  }
-  CB_CHECK(lanczos_start(L));
-  for (int iter = 1; iter <= nlanc; iter++) {
-    CB_CHECK(lanczos_step(L, &a, &b));
+  auto zcoef = [&](int iter) { return Z[(size_t)(iter - 1) * nlanc + 0] / (iter == 1 ? 1.0 : hb[iter - 2]); };
+  if (storing) {
+    // vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter = slot[iter-1] / beta_iter: one streaming pass
+    prof_begin(4);
+    for (int i0 = 1; i0 <= nlanc; i0 += kAsmVecs) {
+      AsmArgs<T> aa{};
+      aa.nv = std::min(kAsmVecs, nlanc - i0 + 1);
+      aa.first = i0 == 1;
+      for (int k = 0; k < aa.nv; k++) {
+        aa.v[k] = (const T *)c.lz_slots[i0 - 1 + k];
+        aa.z[k] = zcoef(i0 + k);
+      }
+      if (nloc > 0) {
+        k_assemble<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, aa);
+        c.launches++;
+      }
+    }
+    prof_end();
+  } else {
+    // second pass: same recurrence, same start: bitwise the same vectors, so beta_iter is the value the first
+    // pass returned; no synchronisation inside
+    L.u = kv_u; L.um = kv_um; L.next = nullptr;
     if (nloc > 0) {
-      prof_begin(4);
-      k_axpy_real<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, Z[(size_t)(iter - 1) * nlanc + 0] / L.beta_prev);
-      c.launches++;
-      prof_end();
+      CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+      CB_CUDA(cudaMemsetAsync(gs, 0, (size_t)nloc * sizeof(T), c.stream));
+    }
+    CB_CHECK(lanczos_start(L));
+    for (int iter = 1; iter <= nlanc; iter++) {
+      CB_CHECK(lanczos_step(L));
+      if (nloc > 0) {
+        prof_begin(4);
+        k_axpy_real<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, zcoef(iter));
+        c.launches++;
+        prof_end();
+      }
     }
   }
   std::complex<double> z;
@@ -438,6 +623,27 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
   if (alanc_out) std::copy(al.begin(), al.end(), alanc_out);
   if (blanc_out) std::copy(bl.begin(), bl.begin() + nlanc, blanc_out);
   return 0;
+}
+
+// Fock map + Lin tables of one particle number, without hop terms (apply_op, scatter/gather helpers)
+int cached_map_op(int npart, const SpinOp **out) {
+  Ctx &c = ctx();
+  auto it = c.map_ops.find(npart);
+  if (it == c.map_ops.end()) {
+    SpinOp *op = new SpinOp();
+    std::vector<Term> none;
+    std::vector<double> e0(c.ns, 0.0);
+    const int rc = build_spin_op(*op, npart, none, e0, 0.0, false);
+    if (rc) { free_spin_op(*op); delete op; return rc; }
+    it = c.map_ops.emplace(npart, op).first;
+  }
+  *out = it->second;
+  return 0;
+}
+void free_map_ops() {
+  Ctx &c = ctx();
+  for (auto &kv : c.map_ops) { free_spin_op(*kv.second); delete kv.second; }
+  c.map_ops.clear();
 }
 
 }  // namespace cb
@@ -480,6 +686,7 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
   if (nloc != local_n()) return fail("lanczos_gs: nloc mismatch");
   if ((int64_t)nitermax > c.dim) nitermax = (int32_t)c.dim;
   if (ncheck <= 0) ncheck = 10;
+  if (threshold <= 0) threshold = 1e-12;  // same default as lanczos_tridiag
   CB_CHECK(ensure_kv(std::max<int64_t>(nloc, 1), 3));
   const bool dev = is_device_ptr(vect);
   double2 *gs = nullptr;  // start vector, later the accumulated eigenvector
@@ -530,6 +737,8 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   // operators change the column split; the reference gathers on the master for those (ED_EIGENSPACE.f90:499-569).
   if (c.spmd && ispin != 1) return fail("apply_op: spin-down operators on a sharded vector are not supported (gather the state first)");
   const int ns = c.ns;
+  for (int k = 0; k < nops; k++)  // validate everything before any resource exists
+    if (pos[k] < 1 || pos[k] > ns) return fail("apply_op: pos out of range");
   int nup = (isector - 1) / (ns + 1), ndw = (isector - 1) % (ns + 1);
   int jnup = nup + (ispin == 1 ? (iop > 0 ? 1 : -1) : 0), jndw = ndw + (ispin == 2 ? (iop > 0 ? 1 : -1) : 0);
   if (jnup < 0 || jnup > ns || jndw < 0 || jndw > ns) { if (jsector) *jsector = 0; return 0; }  // getCsector = 0
@@ -543,31 +752,34 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
     idim = idimup * q;
     jdim = jdimup * q;
   }
-  SpinOp src, dst;
-  std::vector<Term> none;
-  std::vector<double> e0(ns, 0.0);
-  CB_CHECK(build_spin_op(src, ispin == 1 ? nup : ndw, none, e0, 0.0, false));
-  CB_CHECK(build_spin_op(dst, ispin == 1 ? jnup : jndw, none, e0, 0.0, false));
+  // Fock maps + Lin tables of the two particle numbers: cached per particle number (the GF loops of
+  // ED_GF_NORMAL.f90 call this once per channel with the same sectors; the cache dies with the model)
+  const SpinOp *src = nullptr, *dst = nullptr;
+  CB_CHECK(cached_map_op(ispin == 1 ? nup : ndw, &src));
+  CB_CHECK(cached_map_op(ispin == 1 ? jnup : jndw, &dst));
   const bool ds = is_device_ptr(state), dd = is_device_ptr(out);
   double2 *d_state = (double2 *)state, *d_out = (double2 *)out;
-  if (!ds) { CB_CHECK(dev_alloc(&d_state, idim)); CB_CUDA(cudaMemcpyAsync(d_state, state, idim * 16, cudaMemcpyHostToDevice, c.stream)); }
-  if (!dd) CB_CHECK(dev_alloc(&d_out, jdim));
-  CB_CUDA(cudaMemsetAsync(d_out, 0, jdim * 16, c.stream));
-  for (int k = 0; k < nops; k++) {
-    if (pos[k] < 1 || pos[k] > ns) return fail("apply_op: pos out of range");
-    if (idim == 0) continue;
-    k_apply_op<<<(unsigned)((idim + 255) / 256), 256, 0, c.stream>>>(idim, idimup, jdimup, ispin, iop, pos[k] - 1, src.map,
-                                                                      dst.lin_lo, dst.lin_hi, ns / 2,
-                                                                      make_double2(coef[2 * k], coef[2 * k + 1]), d_state, d_out);
-    c.launches++;
-  }
-  if (!dd) CB_CUDA(cudaMemcpyAsync(out, d_out, jdim * 16, cudaMemcpyDeviceToHost, c.stream));
-  CB_CUDA(cudaStreamSynchronize(c.stream));
-  if (!ds) cudaFree(d_state);
-  if (!dd) cudaFree(d_out);
-  free_spin_op(src);
-  free_spin_op(dst);
-  return 0;
+  int rc = 0;
+  auto body = [&]() -> int {
+    if (!ds) { CB_CHECK(dev_alloc(&d_state, idim)); CB_CUDA(cudaMemcpyAsync(d_state, state, idim * 16, cudaMemcpyHostToDevice, c.stream)); }
+    if (!dd) CB_CHECK(dev_alloc(&d_out, jdim));
+    CB_CUDA(cudaMemsetAsync(d_out, 0, jdim * 16, c.stream));
+    for (int k = 0; k < nops; k++) {
+      if (idim == 0) continue;
+      k_apply_op<<<(unsigned)((idim + 255) / 256), 256, 0, c.stream>>>(idim, idimup, jdimup, ispin, iop, pos[k] - 1, src->map,
+                                                                        dst->lin_lo, dst->lin_hi, ns / 2,
+                                                                        make_double2(coef[2 * k], coef[2 * k + 1]), d_state, d_out);
+      c.launches++;
+    }
+    if (!dd) CB_CUDA(cudaMemcpyAsync(out, d_out, jdim * 16, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+  };
+  rc = body();  // single clean-up path, whatever happened
+  if (!ds && d_state) cudaFree(d_state);
+  if (!dd && d_out) cudaFree(d_out);
+  return rc;
 }
 
 int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlanc, const double *alanc, const double *blanc,

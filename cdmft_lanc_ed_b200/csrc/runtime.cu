@@ -226,6 +226,24 @@ int cdmft_b200_init_rank(int32_t device, int32_t nranks, int32_t rank, const voi
   }
   CB_CUDA(cudaEventCreateWithFlags(&c.ev_in, cudaEventDisableTiming));
   CB_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
+  // First use of a collective sets up its channels / peer connections (hundreds of ms): do it here, once, for the
+  // two kinds this library issues -- the 2-double all-reduce of the Krylov scalars and the send/recv all-to-all of
+  // the transposes (both streams) -- so that no product or Krylov step pays for it.
+  if (nranks > 1) {
+    double *w = c.red + 3008;  // 2*nranks doubles of scratch
+    if (2 * nranks + 3008 > 4096) return fail("init_rank: too many ranks for the warm-up scratch");
+    CB_CUDA(cudaMemsetAsync(w, 0, (size_t)2 * nranks * sizeof(double), c.stream));
+    CB_NCCL(nccl.AllReduce(w, w, 2, kNcclDouble, kNcclSum, c.nccl_comm, c.stream));
+    for (cudaStream_t st : {c.stream, c.comm_stream}) {
+      CB_NCCL(nccl.GroupStart());
+      for (int p = 0; p < nranks; p++) {
+        CB_NCCL(nccl.Send((void *)(w + p), 1, kNcclDouble, p, c.nccl_comm, st));
+        CB_NCCL(nccl.Recv((void *)(w + nranks + p), 1, kNcclDouble, p, c.nccl_comm, st));
+      }
+      CB_NCCL(nccl.GroupEnd());
+      CB_CUDA(cudaStreamSynchronize(st));
+    }
+  }
   return 0;
 }
 
@@ -235,7 +253,7 @@ int cdmft_b200_finalize(void) {
   if (c.hstatus) cdmft_b200_delete_hv_sector();
   cudaStreamSynchronize(c.stream);
   if (c.nccl_comm) { nccl.CommDestroy(c.nccl_comm); c.nccl_comm = nullptr; }
-  dev_free(c.red); dev_free(c.rt_queue); dev_free(c.cross_tab); dev_free(c.dot_partial); c.dot_cap = 0;
+  dev_free(c.red); dev_free(c.lz_hist); c.lz_hist_cap = 0; dev_free(c.rt_queue); dev_free(c.cross_tab); dev_free(c.dot_partial); c.dot_cap = 0;
   dev_free(c.stage_v); dev_free(c.stage_hv); c.stage_n = 0;
   for (auto &k : c.kv) dev_free(k);
   c.kv_n = 0;
@@ -245,6 +263,8 @@ int cdmft_b200_finalize(void) {
   if (c.ev_comm) { cudaEventDestroy(c.ev_comm); c.ev_comm = nullptr; }
   if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
   c.stream = nullptr;
+  free_map_ops();
+  lz_free_slots();
   c.inited = false; c.have_model = false;
   return 0;
 }
@@ -335,6 +355,8 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   std::string k(key);
   if (k == "colpass_variant") c.opt.colpass_variant = value;
   else if (k == "rowpass_variant") c.opt.rowpass_variant = value;
+  else if (k == "lanczos_batch") c.opt.lanczos_batch = value;
+  else if (k == "lanczos_store") c.opt.lanczos_store = value;
   else if (k == "force_sharded") c.opt.force_sharded = value;
   else if (k == "col_batch") c.opt.col_batch = value;
   else if (k == "row_slab") c.opt.row_slab = value;
@@ -470,6 +492,7 @@ int cdmft_b200_set_model(const cdmft_b200_model *m) {
   dev_free(c.cross_tab);
   CB_CHECK(dev_alloc(&c.cross_tab, (int64_t)tab.size()));
   CB_CUDA(cudaMemcpy(c.cross_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  free_map_ops();  // Fock maps cached for the previous model (Ns may have changed)
   c.have_model = true;
   return 0;
 }

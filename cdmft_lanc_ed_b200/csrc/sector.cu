@@ -874,6 +874,7 @@ int cdmft_b200_delete_hv_sector(void) {
     nccl_barrier();
     cudaStreamSynchronize(c.stream);
   }
+  lz_free_slots();  // Krylov vectors kept by the ground-state driver
   free_spin_op(c.up);
   free_spin_op(c.dw);
   for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }

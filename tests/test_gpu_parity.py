@@ -191,7 +191,9 @@ def test_sharded_path_simulated_ranks(oracle_lib, name, P):
 def test_lanczos_tridiag_and_gs(ed, oracle_lib):
     """sp_lanc_tridiag / sp_lanc_eigh: alpha/beta on the leading coefficients (later ones
     diverge chaotically between any two summation orders), E0 and eigenvector residual to 1e-10."""
-    for mdl, (nup, ndw) in [(models.hm2x2(1), (4, 4)), (models.bhz2(1), (4, 4)), (models.hm2x2(2), (6, 6))]:
+    # the Kanamori models carry the non-local Jx/Jp term (k_nonlocal runs AFTER the passes that can fuse the alpha dot)
+    for mdl, (nup, ndw) in [(models.hm2x2(1), (4, 4)), (models.bhz2(1), (4, 4)), (models.hm2x2(2), (6, 6)),
+                            (models.bhz2(1, kanamori=True), (4, 4)), (models.random_model(2, 2, 1, seed=15, kanamori=True), (3, 3))]:
         orc = oracle_lib.Oracle(mdl)
         ed.ed_set_model(mdl)
         isec = models.get_sector(mdl.ns, nup, ndw)
@@ -327,7 +329,8 @@ def test_fused_dot_matches_separate_dot(ed, oracle_lib):
     """The Lanczos alpha reduced inside the row pass (option fuse_dot, default on) equals the separate
     dot-product sweep and the oracle, for complex vectors, real vectors (paired rows) and an odd DimUp."""
     for mdl, (nup, ndw) in [(models.hm2x2(2), (6, 6)), (models.bhz2(1), (2, 2)), (models.hm2x2(1), (3, 4)),
-                            (models.random_model(3, 1, 1, complex_h=False, seed=5), (2, 3))]:
+                            (models.random_model(3, 1, 1, complex_h=False, seed=5), (2, 3)),
+                            (models.bhz2(1, kanamori=True), (4, 4)), (models.random_model(2, 2, 1, seed=15, kanamori=True), (4, 3))]:
         orc = oracle_lib.Oracle(mdl)
         ed.ed_set_model(mdl)
         isec = models.get_sector(mdl.ns, nup, ndw)
@@ -351,6 +354,49 @@ def test_fused_dot_matches_separate_dot(ed, oracle_lib):
             ed.set_option("fuse_dot", 1)
             ed.delete_Hv_sector()
             orc.delete_hv_sector()
+
+
+def test_krylov_batching_does_not_change_results(ed, oracle_lib):
+    """The drivers keep the scalars of the recurrence on the device and read (alfa, beta) back once per batch
+    of steps (option lanczos_batch): every batch size returns bitwise the same coefficients, the same number of
+    steps and the same ground state as the step-by-step loop (batch 1), including an early stop on an
+    invariant subspace in the middle of a batch."""
+    try:
+        # (third case: a beta threshold so coarse that the loop stops in the middle of a batch)
+        for mdl, (nup, ndw), nit, thr in [(models.hm2x2(2), (6, 6), 50, 1e-12), (models.bhz2(1), (4, 4), 50, 1e-12),
+                                          (models.hm2x2(1), (3, 3), 40, None)]:
+            ed.ed_set_model(mdl)
+            isec = models.get_sector(mdl.ns, nup, ndw)
+            n = ed.build_Hv_sector(isec, True)
+            v0 = _rand_vec(n, seed=3)
+            kstop = None
+            if thr is None:  # just above the smallest beta of the first 30 steps -> the loop stops at that step
+                ed.set_option("lanczos_batch", 1)
+                _, _, b0 = ed.sp_lanc_tridiag(v0, nit)
+                kstop = int(np.argmin(b0[1:30])) + 1
+                thr = float(b0[kstop]) * (1 + 1e-9)
+            ref = None
+            # (batch, store): store = the ground-state driver keeps its Krylov vectors and assembles the eigenvector
+            # from them; off = the reference's second pass through the recurrence.  Bitwise the same vector.
+            for batch, store in ((1, 0), (4, 1), (7, 0), (64, 1), (4, 0)):
+                ed.set_option("lanczos_batch", batch)
+                ed.set_option("lanczos_store", store)
+                nd, a, b = ed.sp_lanc_tridiag(v0, nit, thr)
+                vec = np.zeros(n, dtype=np.complex128)
+                e0, nlanc, al, bl = ed.sp_lanc_eigh(vec, 300, 1e-13)
+                cur = (nd, a.copy(), b.copy(), e0, nlanc, al.copy(), bl.copy(), vec.copy())
+                if ref is None:
+                    ref = cur
+                    if kstop is not None:
+                        assert nd == kstop, (nd, kstop)  # stopped early (inside a batch for at least one of the batch sizes)
+                else:
+                    assert cur[0] == ref[0] and cur[4] == ref[4], (mdl.name, batch)
+                    for x, y in zip(cur[1:], ref[1:]):
+                        assert np.array_equal(np.asarray(x), np.asarray(y)), (mdl.name, batch)
+            ed.delete_Hv_sector()
+    finally:
+        ed.set_option("lanczos_batch", 4)
+        ed.set_option("lanczos_store", 1)
 
 
 @pytest.mark.parametrize("P", [2, 3, 8])
