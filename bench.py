@@ -204,6 +204,8 @@ def run_ours(args):
     else:
         E.ed_init(local)
     E.set_stream(torch.cuda.current_stream().cuda_stream)
+    for kv in args.opt:
+        E.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     builder, margs, (nup, ndw) = WORKLOADS[args.workload]
     mdl = getattr(models, builder)(*margs)
@@ -383,6 +385,7 @@ def main():
     ap.add_argument("--workload", default="K3", choices=list(WORKLOADS))
     ap.add_argument("--direct", action="store_true", help="ed_sparse_H=F (matrix-free kernels)")
     ap.add_argument("--no-ipc", action="store_true", help="N>1: NCCL all-to-all transposes instead of peer-memory stores")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="library option (cdmft_b200_set_option), repeatable")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lanczos", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

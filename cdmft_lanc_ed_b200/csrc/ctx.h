@@ -131,14 +131,16 @@ struct Options {
   int64_t force_sharded = 0;    // single rank: run the transpose path anyway (P=1)
   int64_t col_batch = 4;
   int64_t row_slab = 128;       // rows per slab of the row pass (slab x all columns stays in L2)
-  int64_t use_ipc = 1;          // SPMD: use the peer-memory transposes when ipc_import was called
+  int64_t use_ipc = 1;          // SPMD with peer windows (ipc_import): 1 = copy-engine exchange (default), 2 = transposing kernels that
+                                // store into peer memory, 0 = NCCL send/recv
+  int64_t xchg_chunks = 4;      // copy-engine exchange: chunks of the Hdw pass pipelined against the way back
   int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
   int64_t fast4 = 1;            // sign/class/phase decode for purely real-or-imaginary coefficients
   int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the last pass of H x v
   int64_t real_lanczos = 1;     // Krylov drivers keep real vectors when H and the start vector are real
   int64_t overlap = 1;          // SPMD: overlap the transpose of v with the diag+Hup pass
   int64_t lanczos_batch = 4;    // Krylov drivers: steps enqueued between two read-backs of (alfa, beta)
-  int64_t lanczos_store = 1;    // ground-state driver: keep the Krylov vectors in HBM when they fit (no second pass)
+  int64_t lanczos_store = 1;    // ground-state driver: keep the Krylov vectors in HBM as far as they fit (1; n > 1: at most n); 0 = two passes
 };
 
 struct Ctx {
@@ -182,6 +184,10 @@ struct Ctx {
   // in one kernel).  Indexed by rank; entry for this rank = local pointer.
   bool ipc_ready = false;
   std::vector<double2 *> peer_vt, peer_recv;
+  // copy-engine exchange (hxv.cu, hxv_sharded_ce): one stream + event per peer, created on first use
+  std::vector<cudaStream_t> peer_stream;
+  std::vector<cudaEvent_t> peer_done;
+  cudaEvent_t ev_pack = nullptr;
   double2 *vfull = nullptr;  // all-gathered vector for the non-local (Jx/Jp) term, SPMD only
   // staging for host-pointer calls
   double2 *stage_v = nullptr, *stage_hv = nullptr;

@@ -475,8 +475,6 @@ __global__ void __launch_bounds__(256) k_nonlocal(int64_t nloc, const double2 *_
 }
 
 static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs);
-int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final);  // hxv_real.cu
-
 int hxv_device(const double2 *v, double2 *hv) {
   Ctx &c = ctx();
   CB_CHECK(hxv_local_terms(v, hv, false));
@@ -514,6 +512,123 @@ int hxv_device(const double2 *v, double2 *hv) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// Copy-engine exchange (SPMD with CUDA-IPC peer windows): the two distributed transposes of spMatVec_mpi_main /
+// directMatVec_MPI_main (vector_transpose_MPI, ED_HAMILTONIAN_COMMON.f90:30-94) without a single SM cycle spent
+// on NVLink traffic:
+//   way out : k_transpose_block packs my columns, already transposed, one block per destination; the DMA engines
+//             copy every block straight into the owner's vt (2-D copy: rows of my q_dw elements at pitch DimDw),
+//             one stream per peer, all peers at once -- while the SMs run the diag + Hup column pass;
+//   way back: the Hdw pass on vt runs in chunks of my up-rows; behind every chunk its transposed blocks are
+//             packed and handed to the DMA engines while the next chunk computes; the owners add the received
+//             blocks to Hv (k_copy_block, accumulating);
+//   two stream-ordered barriers per product (all blocks of every vt have landed / every receive window is
+//   complete); the one of product n also tells everybody that vt and the windows of product n-1 are free again.
+// v / hv: this rank's shard, 16-byte elements (complex, or the paired-row view of a real vector), DU rows.
+// ------------------------------------------------------------------------------------
+int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final);  // hxv_real.cu
+static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU) {
+  Ctx &c = ctx();
+  RankState &me = c.rk[0];
+  const int P = c.p_eff;
+  auto usplit = [&](int p) { return split_of(DU, P, p); };
+  const Split me_up = usplit(me.rank);
+  cudaStream_t S = c.stream;
+  if ((int)c.peer_stream.size() < P) {
+    int lo = 0, hi = 0;
+    CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    while ((int)c.peer_stream.size() < P) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CB_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+      CB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c.peer_stream.push_back(st);
+      c.peer_done.push_back(ev);
+    }
+    CB_CUDA(cudaEventCreateWithFlags(&c.ev_pack, cudaEventDisableTiming));
+  }
+  DiagArgs nodiag{};
+  // ---- way out: pack (transposing), DMA into the owners' vt, diag + Hup meanwhile
+  std::vector<int64_t> os(P, 0);
+  {
+    int64_t so = 0;
+    for (int p = 0; p < P; p++) { os[p] = so; so += usplit(p).q * me.dw.q; }
+  }
+  prof_begin(2);
+  for (int k = 0; k < P; k++) {
+    const int p = (me.rank + k) % P;
+    const Split pu = usplit(p);
+    if (p == me.rank) transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.vt, c.dimdw, me.dw.off);
+    else transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+  }
+  prof_end();
+  CB_CUDA(cudaEventRecord(c.ev_pack, S));
+  for (int k = 1; k < P; k++) {
+    const int p = (me.rank + k) % P;  // staggered: at step k every rank targets a different GPU
+    const Split pu = usplit(p);
+    if (pu.q <= 0 || me.dw.q <= 0) continue;
+    CB_CUDA(cudaStreamWaitEvent(c.peer_stream[p], c.ev_pack, 0));
+    CB_CUDA(cudaMemcpy2DAsync(c.peer_vt[p] + me.dw.off, (size_t)c.dimdw * 16, me.sendbuf + os[p], (size_t)me.dw.q * 16,
+                              (size_t)me.dw.q * 16, (size_t)pu.q, cudaMemcpyDeviceToDevice, c.peer_stream[p]));
+    CB_CUDA(cudaEventRecord(c.peer_done[p], c.peer_stream[p]));
+  }
+  if (pairs) CB_CHECK(colpass_real(c.up, me.dw.q, (const double *)v, (double *)hv, diag_args(me.dw.off), false, false));
+  else CB_CHECK(colpass(c.up, me.dw.q, v, hv, diag_args(me.dw.off)));
+  prof_begin(3);  // what is left of the exchange after the overlap + the barrier
+  for (int k = 1; k < P; k++) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[(me.rank + k) % P], 0));
+  CB_CHECK(nccl_barrier());  // all blocks of every vt have landed
+  prof_end();
+  // ---- Hdw on vt in chunks of my up-rows; way back pipelined behind the chunks
+  const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(c.opt.xchg_chunks, me_up.q));
+  std::vector<int64_t> ob(P, 0);  // receive-window layout of peer p: block of sender s at q_dw(p) * up_off(s)
+  {
+    int64_t so = 0;
+    for (int p = 0; p < P; p++) { ob[p] = so; so += split_of(c.dimdw, P, p).q * me_up.q; }
+  }
+  for (int ch = 0; ch < nch; ch++) {
+    const Split cs = split_of(me_up.q, nch, ch);  // rows [cs.off, cs.off + cs.q) of my up range
+    if (cs.q <= 0) continue;
+    CB_CHECK(colpass(c.dw, cs.q, me.vt + cs.off * c.dimdw, me.hvt + cs.off * c.dimdw, nodiag));
+    prof_begin(2);
+    for (int k = 0; k < P; k++) {
+      const int p = (me.rank + k) % P;
+      const Split pd = split_of(c.dimdw, P, p);
+      // block: p's columns (rows of hvt) x this chunk of my up-rows, transposed: [iup_chunk + idw_p * cs.q]
+      if (p == me.rank) transpose_block<true>(me.hvt + cs.off * c.dimdw, c.dimdw, pd.off, pd.q, cs.q, hv, DU, me_up.off + cs.off);
+      else transpose_block<false>(me.hvt + cs.off * c.dimdw, c.dimdw, pd.off, pd.q, cs.q, me.sendbuf + ob[p] + pd.q * cs.off, cs.q, 0);
+    }
+    prof_end();
+    CB_CUDA(cudaEventRecord(c.ev_pack, S));
+    for (int k = 1; k < P; k++) {
+      const int p = (me.rank + k) % P;
+      const Split pd = split_of(c.dimdw, P, p);
+      if (pd.q <= 0) continue;
+      CB_CUDA(cudaStreamWaitEvent(c.peer_stream[p], c.ev_pack, 0));
+      // into p's window: sender block at q_dw(p) * up_off(me), inside it this chunk at q_dw(p) * cs.off
+      CB_CUDA(cudaMemcpyAsync(c.peer_recv[p] + pd.q * (me_up.off + cs.off), me.sendbuf + ob[p] + pd.q * cs.off,
+                              (size_t)pd.q * cs.q * 16, cudaMemcpyDeviceToDevice, c.peer_stream[p]));
+      if (ch == nch - 1) CB_CUDA(cudaEventRecord(c.peer_done[p], c.peer_stream[p]));
+    }
+  }
+  prof_begin(3);
+  for (int k = 1; k < P; k++) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[(me.rank + k) % P], 0));
+  CB_CHECK(nccl_barrier());  // every receive window is complete
+  prof_end();
+  prof_begin(2);
+  for (int p = 0; p < P; p++) {
+    if (p == me.rank) continue;
+    const Split pu = usplit(p);
+    // sender p's block: its up-rows x my columns, chunk by chunk [iup_chunk + idw * cs.q]
+    const int nchp = (int)std::max<int64_t>(1, std::min<int64_t>(c.opt.xchg_chunks, pu.q));
+    for (int ch = 0; ch < nchp; ch++) {
+      const Split cs = split_of(pu.q, nchp, ch);
+      copy_block<true>(me.recvbuf + me.dw.q * (pu.off + cs.off), me.dw.q, cs.q, hv, DU, pu.off + cs.off);
+    }
+  }
+  prof_end();
+  return 0;
+}
+
 // PAIRS (real Krylov mode on a sharded layout): v / hv hold REAL vectors.  The diag + Hup pass runs the real
 // kernels; for everything after it two adjacent up-rows of the real vector are one double2 of a "complex"
 // vector with DimUp/2 rows -- transposes, exchanges and the Hdw pass act on the other index, and a real
@@ -548,8 +663,9 @@ static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs) {
   // measured on B200 (K3): peer-memory transposes win at P=2 (8.4 vs 8.7 ms), the overlapped NCCL path wins
   // at P=4 (4.6 vs 4.9) and P=8 (2.5 vs 2.8) -> use_ipc 1 = auto (P<=2), 2 = always, 0 = never
   // (the stream-ordered barriers of that path span the full communicator: only when no rank was shrunk away)
-  const bool use_ipc = c.spmd && P > 1 && P == c.nranks && !c.rk.empty() && c.ipc_ready &&
-                       (c.opt.use_ipc == 2 || (c.opt.use_ipc == 1 && P <= 2));
+  const bool ipc_ok = c.spmd && P > 1 && P == c.nranks && !c.rk.empty() && c.ipc_ready;
+  if (ipc_ok && c.opt.use_ipc == 1) return hxv_sharded_ce(v, hv, pairs, DU);
+  const bool use_ipc = ipc_ok && c.opt.use_ipc == 2;
   const bool overlap = !use_ipc && c.spmd && P > 1 && !c.rk.empty() && c.opt.overlap && c.comm_stream;
   if (use_ipc) {
     // peer-memory transpose: every rank stores its transposed blocks straight into the owners' vt

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256) k_assemble(int64_t n, T *__restrict__ acc
   }
 }
 __global__ void k_lz_init(double *scal) { scal[0] = scal[1] = 1.0; }
+__global__ void k_lz_set(double *scal, double bp, double bc) { scal[0] = bp; scal[1] = bc; }
 __global__ void k_lz_advance(double *scal, const double *__restrict__ dotp, const double *__restrict__ nrm, double *__restrict__ hist,
                              int iter /*0-based*/) {
   const double bc = scal[1];
@@ -533,7 +534,8 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
   // store mode: slot[j] = u_{j+1} (slot[0] = normalised start vector); budget agreed between the ranks
   int nslots = 0;
   if (c.opt.lanczos_store) CB_CHECK(lz_slot_budget(vbytes, nitermax + 1, &nslots));
-  bool storing = nslots >= 3;
+  if (c.opt.lanczos_store > 1) nslots = (int)std::min<int64_t>(nslots, c.opt.lanczos_store);  // > 1: cap on the slots (tests)
+  const bool storing = nslots >= 3;
   auto slot = [&](int j, T **p) -> int { void *q = nullptr; CB_CHECK(lz_slot(j, vbytes, &q)); *p = (T *)q; return 0; };
   if (storing) CB_CHECK(slot(0, &L.u));
   if (nloc > 0) CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
@@ -545,15 +547,22 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
   double esave = 0, e0 = 0;
   bool stop = false;
   const int batch = (int)std::max<int64_t>(1, c.opt.lanczos_batch);
+  // where step k (0-based; input u_{k+1}, output u_{k+2}) writes: slot k+1 while slots last, then the two work
+  // buffers (never over a stored vector), then in place between the work buffers
+  auto set_next = [&](int k) -> int {
+    L.next = nullptr;
+    if (!storing) return 0;
+    if (k + 1 < nslots) return slot(k + 1, &L.next);
+    if (k + 1 == nslots) L.next = kv_um;
+    else if (k + 1 == nslots + 1) L.next = kv_u;
+    return 0;
+  };
   while (!stop && L.steps < nitermax) {
     // nothing can stop before ncheck steps except an invariant subspace: first batch = ncheck steps
     const int from = L.steps;
     const int to = std::min<int>(nitermax, from + (from == 0 ? std::max<int>(batch, std::min<int>(ncheck, 64)) : batch));
     for (int k = from; k < to; k++) {
-      if (storing) {
-        if (k + 1 < nslots) CB_CHECK(slot(k + 1, &L.next));   // step k+1 writes u_{k+2} into slot k+1
-        else storing = false;  // out of slots: carry on in place (the eigenvector then needs the second pass)
-      }
+      CB_CHECK(set_next(k));
       CB_CHECK(lanczos_step(L));
     }
     CB_CHECK(lanczos_fetch(from, to, ha, hb));
@@ -578,13 +587,23 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
     CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
   }
   e0 = d[0];
-  auto zcoef = [&](int iter) { return Z[(size_t)(iter - 1) * nlanc + 0] / (iter == 1 ? 1.0 : hb[iter - 2]); };
-  if (storing) {
-    // vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter = slot[iter-1] / beta_iter: one streaming pass
+  // vect = sum_iter v_iter * Z(iter,1), v_iter = u_iter / beta_iter, beta_1 = 1, beta_iter = the value step iter-1 returned
+  auto beta_of = [&](int iter) { return iter <= 1 ? 1.0 : hb[iter - 2]; };
+  auto zcoef = [&](int iter) { return Z[(size_t)(iter - 1) * nlanc + 0] / beta_of(iter); };
+  auto axpy_gs = [&](const T *vec, int iter) {
+    if (nloc <= 0) return;
     prof_begin(4);
-    for (int i0 = 1; i0 <= nlanc; i0 += kAsmVecs) {
+    k_axpy_real<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, vec, zcoef(iter));
+    c.launches++;
+    prof_end();
+  };
+  if (storing) {
+    // stored vectors u_1..u_m (slots 0..m-1): one streaming pass, terms added in ascending order
+    const int m = std::min(nslots, nlanc);
+    prof_begin(4);
+    for (int i0 = 1; i0 <= m; i0 += kAsmVecs) {
       AsmArgs<T> aa{};
-      aa.nv = std::min(kAsmVecs, nlanc - i0 + 1);
+      aa.nv = std::min(kAsmVecs, m - i0 + 1);
       aa.first = i0 == 1;
       for (int k = 0; k < aa.nv; k++) {
         aa.v[k] = (const T *)c.lz_slots[i0 - 1 + k];
@@ -596,9 +615,22 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
       }
     }
     prof_end();
+    if (nlanc > m) {
+      // the vectors past the last slot: re-run the recurrence from (u_{m-1}, u_m) = (slot m-2, slot m-1) with the
+      // betas the first pass returned -- bitwise the same vectors as a second pass from the start would produce
+      L.um = (T *)c.lz_slots[m - 2];
+      L.u = (T *)c.lz_slots[m - 1];
+      k_lz_set<<<1, 1, 0, c.stream>>>(lz_scal(), beta_of(m - 1), beta_of(m));
+      c.launches++;
+      L.steps = m - 1;
+      for (int k = m - 1; k + 1 < nlanc; k++) {  // step k: u_{k+1} -> u_{k+2}
+        CB_CHECK(set_next(k));
+        CB_CHECK(lanczos_step(L));
+        axpy_gs(L.u, k + 2);
+      }
+    }
   } else {
-    // second pass: same recurrence, same start: bitwise the same vectors, so beta_iter is the value the first
-    // pass returned; no synchronisation inside
+    // second pass: same recurrence, same start: bitwise the same vectors; no synchronisation inside
     L.u = kv_u; L.um = kv_um; L.next = nullptr;
     if (nloc > 0) {
       CB_CUDA(cudaMemcpyAsync(L.u, gs, (size_t)nloc * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
@@ -607,12 +639,7 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
     CB_CHECK(lanczos_start(L));
     for (int iter = 1; iter <= nlanc; iter++) {
       CB_CHECK(lanczos_step(L));
-      if (nloc > 0) {
-        prof_begin(4);
-        k_axpy_real<T><<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, gs, L.um, zcoef(iter));
-        c.launches++;
-        prof_end();
-      }
+      axpy_gs(L.um, iter);
     }
   }
   std::complex<double> z;

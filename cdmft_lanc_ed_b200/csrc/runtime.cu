@@ -259,6 +259,11 @@ int cdmft_b200_finalize(void) {
   c.kv_n = 0;
   if (c.red_host) { cudaFreeHost(c.red_host); c.red_host = nullptr; }
   if (c.comm_stream) { cudaStreamSynchronize(c.comm_stream); cudaStreamDestroy(c.comm_stream); c.comm_stream = nullptr; }
+  for (auto st : c.peer_stream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  c.peer_stream.clear();
+  for (auto ev : c.peer_done) if (ev) cudaEventDestroy(ev);
+  c.peer_done.clear();
+  if (c.ev_pack) { cudaEventDestroy(c.ev_pack); c.ev_pack = nullptr; }
   if (c.ev_in) { cudaEventDestroy(c.ev_in); c.ev_in = nullptr; }
   if (c.ev_comm) { cudaEventDestroy(c.ev_comm); c.ev_comm = nullptr; }
   if (c.own_stream) { cudaStreamDestroy(c.own_stream); c.own_stream = nullptr; }
@@ -357,6 +362,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "rowpass_variant") c.opt.rowpass_variant = value;
   else if (k == "lanczos_batch") c.opt.lanczos_batch = value;
   else if (k == "lanczos_store") c.opt.lanczos_store = value;
+  else if (k == "xchg_chunks") c.opt.xchg_chunks = value;
   else if (k == "force_sharded") c.opt.force_sharded = value;
   else if (k == "col_batch") c.opt.col_batch = value;
   else if (k == "row_slab") c.opt.row_slab = value;

@@ -378,7 +378,8 @@ def test_krylov_batching_does_not_change_results(ed, oracle_lib):
             ref = None
             # (batch, store): store = the ground-state driver keeps its Krylov vectors and assembles the eigenvector
             # from them; off = the reference's second pass through the recurrence.  Bitwise the same vector.
-            for batch, store in ((1, 0), (4, 1), (7, 0), (64, 1), (4, 0)):
+            # store = n > 1 caps the slots: the vectors past the n-th are recomputed from the last two stored ones.
+            for batch, store in ((1, 0), (4, 1), (7, 0), (64, 1), (4, 0), (4, 5), (3, 12), (8, 3)):
                 ed.set_option("lanczos_batch", batch)
                 ed.set_option("lanczos_store", store)
                 nd, a, b = ed.sp_lanc_tridiag(v0, nit, thr)
