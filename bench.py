@@ -183,11 +183,16 @@ def _config(workload, ngpus, sparse):
 
 
 # ---------------------------------------------------------------------------------------------
+SEED = 20261018          # counter-based synthetic vector (cdmft_lanc_ed_b200/synth.py): v(i) depends on the GLOBAL index only
+NVLINK_GBS = 900.0       # NVLink 5 per direction and GPU (B200_PROFILING.md)
+KINDS = {0: "column_pass", 1: "row_pass", 2: "transpose_pack_unpack", 3: "exchange_exposed"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from cdmft_lanc_ed_b200 import models
+    from cdmft_lanc_ed_b200 import models, synth
     from cdmft_lanc_ed_b200 import ed_hamiltonian as E
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,8 +202,6 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         E.ed_set_MpiComm(local)
     else:
@@ -207,91 +210,164 @@ def run_ours(args):
     for kv in args.opt:
         E.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
-    builder, margs, (nup, ndw) = WORKLOADS[args.workload]
-    mdl = getattr(models, builder)(*margs)
-    E.ed_set_model(mdl)
-    isec = models.get_sector(mdl.ns, nup, ndw)
-    dim = E.getDim(isec)[0]
-    sparse = not args.direct
-    nloc = E.build_Hv_sector(isec, sparse)
-    if world > 1 and not args.no_ipc:
-        E.ipc_exchange()  # peer-memory transposes (CUDA IPC windows over NVLink)
-    small = 16 * dim <= 4 * 126e6
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if small else None
-
-    # seeded synthetic vector (one stream per rank)
-    g = torch.Generator(device="cuda")
-    g.manual_seed(12345 + rank)
-    v = torch.randn(nloc, 2, dtype=torch.float64, device="cuda", generator=g).view(-1)
-    v = torch.view_as_complex(v.view(nloc, 2)).contiguous()
-    hv = torch.empty_like(v)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        if flush is not None:
-            flush.zero_()
-        E.spHtimesV_p(nloc, v, hv)
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    peaks = _load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    peak = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks and "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    class Sector:
+        """one workload sector on the device(s): build, counter-based vector, timed H x v, per-kind timers, checksum"""
+
+        def __init__(self, workload, sparse):
+            builder, margs, (nup, ndw) = WORKLOADS[workload]
+            self.workload, self.sparse = workload, sparse
+            self.mdl = getattr(models, builder)(*margs)
+            E.ed_set_model(self.mdl)
+            self.isec = models.get_sector(self.mdl.ns, nup, ndw)
+            self.dim, self.dimup, self.dimdw = E.getDim(self.isec)
+            t0 = time.perf_counter()
+            self.nloc = E.build_Hv_sector(self.isec, sparse)
+            if world > 1 and not args.no_ipc:
+                E.ipc_exchange()  # CUDA-IPC windows: copy-engine exchange over NVLink
+            self.build_s = time.perf_counter() - t0
+            from cdmft_lanc_ed_b200 import shard_plan as sp
+            self.off = sum(sp.vecdim(self.dimup, self.dimdw, world, r) for r in range(rank)) if world > 1 else 0
+            self.scale = synth.default_scale(self.dim)
+            self.v = synth.counter_vec_torch(self.off, self.nloc, SEED, self.scale)
+            self.hv = torch.empty_like(self.v)
+            small = 16 * self.dim <= 4 * 126e6
+            self.flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if small else None
+
+        def step(self):
+            if self.flush is not None:
+                self.flush.zero_()
+            E.spHtimesV_p(self.nloc, self.v, self.hv)
+
+        def time_hxv(self, steps, warmup):
+            for _ in range(max(warmup, 3)):
+                self.step()
+            barrier()
+            l0 = E.launch_count()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            if self.flush is not None:  # time the H x v only, not the flush
+                ms = 0.0
+                for _ in range(steps):
+                    self.flush.zero_()
+                    ev[0].record()
+                    E.spHtimesV_p(self.nloc, self.v, self.hv)
+                    ev[1].record()
+                    torch.cuda.synchronize()
+                    ms += ev[0].elapsed_time(ev[1])
+            else:
+                ev[0].record()
+                for _ in range(steps):
+                    E.spHtimesV_p(self.nloc, self.v, self.hv)
+                ev[1].record()
+                barrier()
+                ms = ev[0].elapsed_time(ev[1])
+            barrier()
+            launches = E.launch_count() - l0
+            return allmax(ms) / steps, launches
+
+        def kinds(self, steps):
+            """per-kind CUDA-event durations (events inside the library, on the launching stream)"""
+            E.set_option("profile", 1)
+            for k in KINDS:
+                E.profile_query(k)
+            n = min(steps, 10)
+            for _ in range(n):
+                self.step()
+            out = {}
+            for k, nm in KINDS.items():
+                tot, cnt = E.profile_query(k)
+                if cnt:
+                    out[nm] = {"ms_per_step": tot / n, "launches_per_step": cnt / n}
+            E.set_option("profile", 0)
+            return out
+
+        def checksum(self):
+            """(Re<v,Hv>, |Hv|^2) over all ranks: the same numbers at every GPU count (counter-based v)"""
+            torch.cuda.synchronize()
+            E.spHtimesV_p(self.nloc, self.v, self.hv)
+            torch.cuda.synchronize()
+            a = float(torch.vdot(self.v, self.hv).real) if self.nloc else 0.0
+            b = float(torch.vdot(self.hv, self.hv).real) if self.nloc else 0.0
+            return allsum([a, b])
+
+        def close(self):
+            if E.spHtimesV_p is not None:
+                E.delete_Hv_sector()
+            self.v = self.hv = self.flush = None
+            torch.cuda.empty_cache()
+
+    def nvlink(sec, ms_step, kern):
+        if world == 1:
+            return None
+        elem = 16
+        out_bytes = 2.0 * (world - 1) / world * sec.nloc * elem  # two transposes, everything but the own block leaves
+        return {"bytes_out_per_gpu_per_hxv": out_bytes, "peak_GBps_per_direction": NVLINK_GBS,
+                "floor_ms": out_bytes / (NVLINK_GBS * 1e9) * 1e3,
+                "frac_of_step": out_bytes / (ms_step * 1e-3) / 1e9 / NVLINK_GBS,
+                "exposed_exchange_ms": (kern.get("exchange_exposed") or {}).get("ms_per_step"),
+                "note": "copy-engine exchange: the DMA copies overlap the column passes; exposed = what the compute stream still waits for (incl. 2 barriers)"}
+
+    def gs_lanczos(sec, niter, tol, fixed=None):
+        """sp_lanc_eigh semantics from the constant start vector; warm call reported (the first call allocates)"""
+        out = {}
+        for rep in range(2):
+            vec = torch.zeros(sec.nloc, dtype=torch.complex128, device="cuda")
+            barrier()
+            t0 = time.perf_counter()
+            # fixed: exactly `fixed` iterations (ncheck past nitermax: the energy test never fires)
+            e0, nit, _, _ = E.sp_lanc_eigh(vec, niter if fixed is None else fixed, tol if fixed is None else 1e-300,
+                                           10 if fixed is None else fixed + 1)
+            barrier()
+            dt = allmax(time.perf_counter() - t0)
+            out["first_call_seconds" if rep == 0 else "seconds"] = dt
+            del vec
+        real = sec.mdl.is_real and (world == 1 or sec.dimup % 2 == 0)
+        out.update({"iterations": nit, "e0": e0, "threshold": tol if fixed is None else 0.0, "nitermax": niter if fixed is None else fixed,
+                    "start": "constant 1/sqrt(Dim)",
+                    "vectors": ("real (8 B) -- H and start vector real" + ("" if world == 1 else ", sharded: paired-row view")) if real else "complex(8)",
+                    "krylov_vectors_kept_in_hbm": "as many as fit (option lanczos_store); the rest recomputed from the last two"})
+        return out
 
     clk_path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{rank}.csv")
     os.makedirs(os.path.dirname(clk_path), exist_ok=True)
     sampler = _clock_sampler_start(clk_path) if rank == 0 else (None, None)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    l0 = E.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    barrier()
-    if small:  # time the H x v only, not the flush
-        tot = 0.0
-        for _ in range(args.steps):
-            flush.zero_()
-            ev[0].record()
-            E.spHtimesV_p(nloc, v, hv)
-            ev[1].record()
-            torch.cuda.synchronize()
-            tot += ev[0].elapsed_time(ev[1])
-        ms = tot
-    else:
-        ev[0].record()
-        for _ in range(args.steps):
-            E.spHtimesV_p(nloc, v, hv)
-        ev[1].record()
-        barrier()
-        ms = ev[0].elapsed_time(ev[1])
-    barrier()
-    launches = E.launch_count() - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_step = ms / args.steps
-    value = 32.0 * dim / (ms_step * 1e-3) / 1e9
 
-    # ---- per-kernel durations (separate profiled loop, CUDA events inside the library, launch stream)
-    E.set_option("profile", 1)
-    for _ in range(min(args.steps, 10)):
-        step()
-    kinds = {0: "column_pass", 1: "row_pass", 2: "transpose_pack_unpack", 3: "nccl_all_to_all"}
-    kern = {}
-    nprof = min(args.steps, 10)
-    for k, nm in kinds.items():
-        tot, n = E.profile_query(k)
-        if n:
-            kern[nm] = {"ms_per_step": tot / nprof, "launches_per_step": n / nprof}
-    E.set_option("profile", 0)
-    # clocks were sampled (nvidia-smi -lms 100) from the first warm-up step to the end of the profiled loop
+    # ================= headline: args.workload (K3), SPARSE unless --direct =================
+    sparse = not args.direct
+    sec = Sector(args.workload, sparse)
+    dim, nloc = sec.dim, sec.nloc
+    ms_step, launches = sec.time_hxv(args.steps, args.warmup)
+    value = 32.0 * dim / (ms_step * 1e-3) / 1e9
+    kern = sec.kinds(args.steps)
     clocks = _clock_sampler_stop(*sampler, clk_path, gpu_index=local) if rank == 0 else None
+    chk = sec.checksum()
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         vh = torch.empty(nloc, dtype=torch.complex128, pin_memory=True)
         hh = torch.empty(nloc, dtype=torch.complex128, pin_memory=True)
-        vh.copy_(v)
+        vh.copy_(sec.v)
         E.spHtimesV_p(nloc, vh, hh)  # warm (allocates the staging buffers)
         nst = min(args.steps, 10)
         barrier()
@@ -299,67 +375,86 @@ def run_ours(args):
         for _ in range(nst):
             E.spHtimesV_p(nloc, vh, hh)  # synchronous on return for host pointers
         barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        ok = bool(torch.allclose(hh.cuda(), hv, rtol=0, atol=0))
+        dt = allmax(time.perf_counter() - t0)
+        ok = bool(torch.equal(hh.cuda(), sec.hv))
         e2e = {"value": 32.0 * dim * nst / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 16 * nloc * world,
                "d2h_bytes_per_step": 16 * nloc * world, "ms_per_step": dt / nst * 1e3, "steps": nst,
                "matches_device_path": ok, "call": "cdmft_b200_hxv64(nloc, host v, host hv) with pinned host buffers"}
         del vh, hh
 
-    # ---- ground-state Lanczos seconds (sp_lanc_eigh semantics, constant start vector)
+    # ---- ground-state Lanczos seconds
     gs = None
     if not args.no_lanczos:
-        vec = torch.zeros(nloc, dtype=torch.complex128, device="cuda")
-        barrier()
-        t0 = time.perf_counter()
-        e0, nit, _, _ = E.sp_lanc_eigh(vec, args.lanc_niter, args.lanc_tol)
-        barrier()
-        gs = {"seconds": time.perf_counter() - t0, "iterations": nit, "hxv_calls": 2 * nit, "e0": e0,
-              "threshold": args.lanc_tol, "nitermax": args.lanc_niter, "start": "constant 1/sqrt(Dim)",
-              "vectors": ("real (8 B) -- H and start vector real" + ("" if world == 1 else ", sharded: paired-row view"))
-                         if (mdl.is_real and (world == 1 or E.getDim(isec)[1] % 2 == 0)) else "complex(8)"}
-        del vec
+        gs = gs_lanczos(sec, args.lanc_niter, args.lanc_tol)
+        gs["hxv_calls"] = "iterations + those recomputed for the eigenvector (0 when every Krylov vector fits in HBM)"
+        fx = gs_lanczos(sec, 0, 0.0, fixed=100)
+        gs["fixed_100_iterations"] = {"seconds": fx["seconds"], "iterations": fx["iterations"], "e0": fx["e0"]}
+        if not args.no_e2e and world == 1:  # host start vector -> lanczos_gs -> host eigenvector
+            hv0 = torch.zeros(nloc, dtype=torch.complex128, pin_memory=True)
+            t0 = time.perf_counter()
+            e0h, nith, _, _ = E.sp_lanc_eigh(hv0, args.lanc_niter, args.lanc_tol)
+            gs["e2e_host_buffers_seconds"] = time.perf_counter() - t0
+            gs["e2e_host_buffers_e0"] = e0h
+            del hv0
 
-    peaks = _load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
-    peak = peaks["hbm_gbs"] if peaks and "hbm_gbs" in peaks else 6650.0
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks and "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    prof = _load_json(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) or {}
-    roofline = None
-    # dominant kernel of the step = the kind with the largest share of the profiled loop.  Algorithmic bytes per
-    # launch: column pass reads its operand once and writes its output once (32 B/state of
-    # the shard, 16 B/state in real mode is not timed here); row pass reads v and read-modify-writes Hv (48 B/state).
-    cand = {k: kern[k] for k in ("column_pass", "row_pass") if k in kern}
-    if cand:
-        dom = max(cand, key=lambda k: cand[k]["ms_per_step"])
-        nl = cand[dom]["launches_per_step"]
-        dur = cand[dom]["ms_per_step"] / max(nl, 1)
-        per_state = 32.0 if dom == "column_pass" else 48.0
-        bytes_launch = per_state * nloc
-        ach = bytes_launch / (dur * 1e-3) / 1e9
-        names = {"column_pass": "column pass (k_colres: column-resident shared-memory kernel; k_colpass when a column does not fit)",
-                 "row_pass": "row pass (k_rowpass_rb)"}
-        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "peak_source": peak_src,
-                    "traffic": (prof.get(args.workload, {}).get(dom, {}) or {}).get("dram_bytes_per_launch") if world == 1 else None,
-                    "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_state": per_state, "avg_launch_ms": dur,
-                    "share_of_step": cand[dom]["ms_per_step"] / sum(x["ms_per_step"] for x in kern.values()),
-                    "other_kernels": {k: {"achieved": (32.0 if k == "column_pass" else 48.0) * nloc * x["launches_per_step"] / (x["ms_per_step"] * 1e-3) / 1e9,
-                                          "frac": (32.0 if k == "column_pass" else 48.0) * nloc * x["launches_per_step"] / (x["ms_per_step"] * 1e-3) / 1e9 / peak}
-                                      for k, x in cand.items() if k != dom},
-                    "step_frac_of_peak": value / world / peak}
+    # ---- roofline: B_alg = 32 B x Dim per H x v against the measured HBM copy bandwidth
+    prof = _load_json(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")) or _load_json(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) or {}
+    model_bytes = {"column_pass": 32.0, "row_pass": 48.0}
+    per_kernel = {}
+    tot_kern = sum(x["ms_per_step"] for x in kern.values()) or 1.0
+    for k, x in kern.items():
+        if k in model_bytes and x["ms_per_step"] > 0:
+            # sharded runs launch the column pass twice (Hup on v, Hdw on vt): bytes per launch = model x shard states
+            ach = model_bytes[k] * nloc * max(1.0, round(x["launches_per_step"])) / (x["ms_per_step"] * 1e-3) / 1e9 if world == 1 else \
+                model_bytes[k] * nloc * 2.0 / (x["ms_per_step"] * 1e-3) / 1e9
+            per_kernel[k] = {"algorithmic_bytes_per_state": model_bytes[k], "ms_per_step": x["ms_per_step"], "achieved": ach, "frac": ach / peak,
+                             "share_of_step": x["ms_per_step"] / tot_kern,
+                             "traffic_ncu_static": (prof.get(args.workload, {}).get(k, {}) or {}).get("dram_bytes_per_launch") if world == 1 else None}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
+    names = {"column_pass": "k_colres (column-resident shared-memory kernel; k_colblk / k_colpass when a column does not fit)",
+             "row_pass": "k_rowpass_rb (L2-slab row pass)"}
+    roofline = {"bound": "hbm", "achieved": value / world, "peak": peak, "unit": "GB/s", "frac": value / world / peak,
+                "definition": "SURVEY 8(d): 32 B x Dim / t_step / (n_gpus x peak) -- read v once, write Hv once",
+                "peak_source": peak_src, "dominant_kernel": names.get(dom, dom),
+                "traffic": per_kernel.get(dom, {}).get("traffic_ncu_static") if dom else None,
+                "traffic_source": "dram__bytes_read+write of that kernel from the ncu --set full capture under profiles/ (static, not measured in this run)",
+                "kernels": per_kernel, "nvlink": nvlink(sec, ms_step, kern)}
+
+    # ================= sub-records: the other BASELINE configs (few steps each) =================
+    sub = {}
+    if not args.no_sub:
+        ns_ = min(args.steps, 5)
+        if sparse:
+            sec.close()
+            d = Sector(args.workload, False)  # BASELINE config 3: DIRECT (matrix-free) H x v
+            ms_d, _ = d.time_hxv(ns_, 3)
+            cd = d.checksum()
+            sub[f"{args.workload}_direct"] = {"ms_per_step": ms_d, "GBps": 32.0 * d.dim / ms_d / 1e6, "frac": 32.0 * d.dim / ms_d / 1e6 / world / peak,
+                                              "checksum": cd, "kernels": d.kinds(ns_)}
+            d.close()
+        else:
+            sec.close()
+        if args.workload == "K3" and world == 1:  # BASELINE config 4: complex Hamiltonian (BHZ), Ns=16
+            k4 = Sector("K4", True)
+            ms4, _ = k4.time_hxv(ns_, 3)
+            sub["K4"] = {"ms_per_step": ms4, "GBps": 32.0 * k4.dim / ms4 / 1e6, "frac": 32.0 * k4.dim / ms4 / 1e6 / peak,
+                         "checksum": k4.checksum(), "kernels": k4.kinds(ns_)}
+            if not args.no_lanczos:
+                g4 = gs_lanczos(k4, args.lanc_niter, args.lanc_tol)
+                sub["K4"]["gs_lanczos"] = {k: g4[k] for k in ("seconds", "iterations", "e0", "vectors")}
+            k4.close()
+        if world >= 8 and not args.no_k5:  # BASELINE config 5 / north-star target: Ns=18 half filling on the whole box
+            sub["K5"] = _k5_record(E, Sector, gs_lanczos, nvlink, args, world, rank, peak, allmax, barrier)
+    else:
+        sec.close()
 
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
-        E.delete_Hv_sector()
-        torch.cuda.empty_cache()
         r = _cpu_port_hxv(args.workload, budget_s=40.0, steps=1, warmup=0)
         cpu = {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    if E.spHtimesV_p is not None:
-        E.delete_Hv_sector()
+        if gs:
+            gs["cpu_port_seconds_estimate"] = gs["iterations"] * 2 * r["ms_per_step"] * 1e-3 * (dim / r["dim"])
+            gs["cpu_port_note"] = "two-pass sp_lanc_eigh on the CPU port = 2 x iterations H x v at the measured CPU rate (vector ops not counted)"
     E.ed_finalize()
     if world > 1:
         dist.destroy_process_group()
@@ -367,13 +462,53 @@ def run_ours(args):
         line = {
             "metric": "hxv_algorithmic_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "vs_baseline": None, "dtype": "c128", "data": f"synthetic (counter-based vector, seed {SEED})",
             "config": _config(args.workload, world, sparse),
-            "hxv_per_s": 1e3 / ms_step, "gpu_launches": launches, "kernels": kern, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu, "gs_lanczos": gs, "clocks": clocks,
+            "hxv_per_s": 1e3 / ms_step, "gpu_launches": launches, "checksum": {"re_v_hv": chk[0], "hv_norm2": chk[1]},
+            "kernels": kern, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": cpu, "gs_lanczos": gs, "configs": sub, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     return 0
+
+
+def _k5_record(E, Sector, gs_lanczos, nvlink, args, world, rank, peak, allmax, barrier):
+    """Ns=18 half-filled sector (Dim 2 363 904 400; the reference's int32 getDim overflows, ED_SETUP.f90:321):
+    H x v, NVLink share, ground-state Lanczos and a sampled-row check against the oracle."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    k5 = Sector("K5", True)
+    ns_ = min(args.steps, 5)
+    ms5, _ = k5.time_hxv(ns_, 3)
+    kern5 = k5.kinds(ns_)
+    rec = {"dim": k5.dim, "nloc_rank0": k5.nloc, "build_s": k5.build_s, "ms_per_step": ms5, "GBps": 32.0 * k5.dim / ms5 / 1e6,
+           "frac_of_aggregate_hbm": 32.0 * k5.dim / ms5 / 1e6 / world / peak, "kernels": kern5, "nvlink": nvlink(k5, ms5, kern5),
+           "checksum": k5.checksum()}
+    # sampled rows: every rank reads a few hundred rows of ITS shard of Hv; rank 0 evaluates the same rows with the
+    # oracle from the index function alone (no 38 GB host vector)
+    rng = np.random.default_rng(77 + rank)
+    loc = np.unique(rng.integers(0, max(k5.nloc, 1), size=300)) if k5.nloc else np.zeros(0, dtype=np.int64)
+    vals = k5.hv[torch.from_numpy(loc).cuda()].cpu().numpy() if k5.nloc else np.zeros(0, dtype=np.complex128)
+    parts = [None] * world
+    dist.all_gather_object(parts, (loc + k5.off, vals))
+    if rank == 0:
+        from oracle import edo  # checker only
+        edo.lib().edo_set_num_threads(os.cpu_count() or 1)
+        orc = edo.Oracle(k5.mdl)
+        orc.build_hv_sector(k5.isec, edo.DIRECT_SERIAL)
+        rows = np.concatenate([p[0] for p in parts])
+        got = np.concatenate([p[1] for p in parts])
+        ref = orc.hxv_rows_counter(rows, SEED, k5.scale)
+        orc.delete_hv_sector()
+        rec["sampled_rows"] = {"rows": int(rows.size), "max_abs_err": float(np.abs(got - ref).max()),
+                               "max_rel_err": float(np.abs(got - ref).max() / np.abs(ref).max()),
+                               "oracle": "edo_hxv_rows_counter (pull form of the direct products on the counter-based vector)"}
+    if not args.no_lanczos:
+        g5 = gs_lanczos(k5, args.lanc_niter, args.lanc_tol)
+        rec["gs_lanczos"] = {k: g5[k] for k in ("first_call_seconds", "seconds", "iterations", "e0", "vectors", "threshold")}
+    k5.close()
+    return rec
 
 
 def main():
@@ -389,6 +524,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lanczos", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (DIRECT mode, K4, and K5 at 8 GPUs)")
+    ap.add_argument("--no-k5", action="store_true")
     ap.add_argument("--lanc-niter", type=int, default=512)
     ap.add_argument("--lanc-tol", type=float, default=1e-12)
     args = ap.parse_args()

@@ -789,6 +789,59 @@ int32_t edo_hxv(edo_ctx *c, int64_t n, const edo_c64 *v, edo_c64 *hv) {
 }
 
 /* ------------------------------------------------------------------ */
+/* sampled rows against a counter-based vector (see ed_oracle.h)         */
+/* ------------------------------------------------------------------ */
+static inline uint64_t mix64(uint64_t x) { x ^= x >> 31; x *= 0xD6E8FEB86659FD93ULL; x ^= x >> 32; return x; }
+static inline edo_c64 counter_at(int64_t idx, uint64_t seed, double scale) {
+  const uint64_t x = mix64(((uint64_t)idx + 1ULL) * 0x9E3779B97F4A7C15ULL + seed * 0xBF58476D1CE4E5B9ULL);
+  const uint64_t y = mix64(x * 0x94D049BB133111EBULL + 0x2545F4914F6CDD1DULL);
+  const double re = (double)(x >> 11) * 0x1p-53 * 2.0 - 1.0, im = (double)(y >> 11) * 0x1p-53 * 2.0 - 1.0;
+  return scale * re + I * (scale * im);
+}
+void edo_counter_vec(int64_t i0, int64_t n, uint64_t seed, double scale, edo_c64 *out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < n; k++) out[k] = counter_at(i0 + k, seed, scale);
+}
+typedef struct { const edo_ctx *c; edo_c64 acc; int64_t fixed; int up; uint64_t seed; double scale; } pull_ud;
+static void pull_cb(void *ud_, int32_t k2, edo_c64 h) {
+  pull_ud *ud = (pull_ud *)ud_;
+  const edo_ctx *c = ud->c;
+  /* k2 = the state c^+_a c_b |m> the reference pushes H(k,i) v(i) to; row i collects conjg(H(k,i)) v(k) */
+  int64_t k;
+  if (ud->up) k = (int64_t)edo_binary_search(c->map_up, (int32_t)c->dimup, k2) - 1 + ud->fixed * c->dimup;
+  else k = ud->fixed + ((int64_t)edo_binary_search(c->map_dw, (int32_t)c->dimdw, k2) - 1) * c->dimup;
+  ud->acc += conj(h) * counter_at(k, ud->seed, ud->scale);
+}
+typedef struct { edo_c64 acc; uint64_t seed; double scale; } nlpull_ud;
+static void nlpull_cb(void *ud_, int64_t j, edo_c64 h) {
+  nlpull_ud *ud = (nlpull_ud *)ud_;
+  ud->acc += h * counter_at(j - 1, ud->seed, ud->scale); /* nonlocal_row is already row-wise (H_non_local.f90) */
+}
+int32_t edo_hxv_rows_counter(edo_ctx *c, int64_t nrows, const int64_t *rows, uint64_t seed, double scale, edo_c64 *out) {
+  if (!c->hstatus) FAIL("directMatVec_cc ERROR: Hsector NOT set");
+  const int Nspin = c->m.nspin;
+  for (int64_t r = 0; r < nrows; r++)
+    if (rows[r] < 0 || rows[r] >= c->dim) FAIL("hxv_rows_counter: row out of range");
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t r = 0; r < nrows; r++) {
+    const int64_t i = rows[r], iup = i % c->dimup, idw = i / c->dimup; /* 0-based */
+    edo_c64 acc = local_element(c, c->map_up[iup], c->map_dw[idw], c->quirk) * counter_at(i, seed, scale);
+    pull_ud uu = {c, 0, idw, 1, seed, scale};
+    spin_hops(c, 1, c->map_up[iup], pull_cb, &uu);
+    pull_ud ud = {c, 0, iup, 0, seed, scale};
+    spin_hops(c, Nspin, c->map_dw[idw], pull_cb, &ud);
+    acc += uu.acc + ud.acc;
+    if (c->jhflag) {
+      nlpull_ud nu = {0, seed, scale};
+      nonlocal_row(c, iup + 1, idw + 1, nlpull_cb, &nu);
+      acc += nu.acc;
+    }
+    out[r] = acc;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
 /* inspection                                                           */
 /* ------------------------------------------------------------------ */
 int64_t edo_get_csr(const edo_ctx *c, int32_t which, int64_t *rowptr, int32_t *col, edo_c64 *val) {

@@ -119,6 +119,19 @@ int32_t edo_vector_transpose_sim(int32_t P, int64_t nrow, int64_t ncol, const ed
  * diagonal spH0d values for global rows; non-local spH0nd */
 int64_t edo_get_csr(const edo_ctx *c, int32_t which, int64_t *rowptr, int32_t *col, edo_c64 *val);
 int32_t edo_get_diag(const edo_ctx *c, double *d /* [Dim] */);
+
+/* ---- sampled rows of H x v against a counter-based synthetic vector -------------------------------
+ * For sectors whose vector does not fit in host memory (Ns = 18 half filling: 38 GB; the reference itself cannot
+ * address it, ED_SETUP.f90:321 int32 getDim).  v(i) = scale * (re, im)(hash(i, seed)) is a pure function of the
+ * 0-based GLOBAL index, so any shard of it can be generated anywhere (edo_counter_vec here, synth.py for numpy /
+ * torch) and single rows of H x v evaluated without materialising v.  Row i is evaluated with the pull form of the
+ * direct products (direct/HxV_local.f90, HxV_up.f90, HxV_dw.f90, HxV_non_local.f90): the reference pushes
+ * H(k,i) v(i) from every column i; a single ROW collects H(i,k) v(k) = conjg(H(k,i)) v(k) over the hops of its
+ * own state (H is Hermitian by construction, checked against the Jordan-Wigner ED in tests/test_oracle_pin.py).
+ * Needs an active sector of any kind (only the Fock maps are used). */
+void edo_counter_vec(int64_t i0, int64_t n, uint64_t seed, double scale, edo_c64 *out);
+int32_t edo_hxv_rows_counter(edo_ctx *c, int64_t nrows, const int64_t *rows /* 0-based global */, uint64_t seed, double scale,
+                             edo_c64 *out /* [nrows] */);
 int64_t edo_get_nonlocal(const edo_ctx *c, int64_t *rowptr, int64_t *col, edo_c64 *val);
 /* dense Hmat = diag + kron(Hdw,1) + kron(1,Hup) (+nd)  (ED_HAMILTONIAN_SPARSE_HxV.f90:112-148) */
 int32_t edo_dense_hmat(edo_ctx *c, int32_t isector, edo_c64 *hmat /* [Dim,Dim] column-major */);

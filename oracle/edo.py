@@ -54,6 +54,7 @@ def lib():
         L.edo_sector_dims.restype = C.c_int64
         L.edo_get_csr.restype = C.c_int64
         L.edo_get_nonlocal.restype = C.c_int64
+        L.edo_counter_vec.restype = None
         _LIB = L
     return _LIB
 
@@ -78,6 +79,13 @@ def sector_map(ns, n):
     m = np.empty(cnt, dtype=np.int32)
     L.edo_build_sector_map(C.c_int32(ns), C.c_int32(n), _p(m))
     return m
+
+
+def counter_vec(i0, n, seed, scale):
+    """The oracle's copy of the counter-based synthetic vector (cdmft_lanc_ed_b200/synth.py holds the numpy / torch ones)."""
+    out = np.empty(n, dtype=np.complex128)
+    lib().edo_counter_vec(C.c_int64(i0), C.c_int64(n), C.c_uint64(seed), C.c_double(scale), _p(out))
+    return out
 
 
 def shard_of(dimup, dimdw, P, rank):
@@ -222,6 +230,14 @@ class Oracle:
         hv = np.empty_like(v)
         _chk(self.L.edo_hxv(self.h, C.c_int64(v.size), _p(v), _p(hv)))
         return hv
+
+    def hxv_rows_counter(self, rows, seed, scale):
+        """Rows `rows` (0-based global indices) of H x v for the counter-based vector v(i) = scale * hash(i, seed)
+        (ed_oracle.h: edo_hxv_rows_counter); works on any active sector, never materialises v."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty(rows.size, dtype=np.complex128)
+        _chk(self.L.edo_hxv_rows_counter(self.h, C.c_int64(rows.size), _p(rows), C.c_uint64(seed), C.c_double(scale), _p(out)))
+        return out
 
     def get_csr(self, which):
         nnz = self.L.edo_get_csr(self.h, C.c_int32(which), None, None, None)

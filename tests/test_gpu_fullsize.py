@@ -48,8 +48,8 @@ def test_fullsize_properties(ed, wl):
     w = _hxv(ed, n, c1 * u + c2 * v)
     assert _rel(w, c1 * hu + c2 * hv) < 1e-12
     # every SPARSE kernel variant agrees with the default one
-    for opts in [dict(colpass_variant=1), dict(fast4=0), dict(rowpass_variant=1), dict(rowres_cols=260), dict(tma2d=0), dict(sched=0),
-                 dict(colpass_variant=1, rowpass_variant=1), dict(force_sharded=1)]:
+    for opts in [dict(colpass_variant=1), dict(fast4=0), dict(rowpass_variant=4), dict(rowpass_variant=4, rowres_cols=260),
+                 dict(rowpass_variant=4, tma2d=0), dict(sched=0), dict(colpass_variant=1, rowpass_variant=4), dict(force_sharded=1)]:
         ed.delete_Hv_sector()
         for k, val in opts.items():
             ed.set_option(k, val)
@@ -58,7 +58,7 @@ def test_fullsize_properties(ed, wl):
             assert _rel(_hxv(ed, n, v), hv) < RTOL, opts
         finally:
             for k in opts:
-                ed.set_option(k, {"colpass_variant": 6, "rowpass_variant": 4, "force_sharded": 0, "sched": 1, "rowres_cols": 0, "fast4": 1, "tma2d": 1}[k])
+                ed.set_option(k, {"colpass_variant": 6, "rowpass_variant": 1, "force_sharded": 0, "sched": 1, "rowres_cols": 0, "fast4": 1, "tma2d": 1}[k])
     # DIRECT (matrix-free) == SPARSE
     ed.delete_Hv_sector()
     ed.build_Hv_sector(isec, False)
@@ -109,6 +109,98 @@ def test_fullsize_K3_against_oracle(ed, oracle_lib):
     assert np.abs(hv - ref).max() / np.abs(ref).max() < RTOL
     # checksum of checksums: column sums of |Hv|^2 agree as well
     assert abs(np.vdot(hv, hv).real - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
+
+
+def test_fullsize_K4_against_oracle(ed, oracle_lib):
+    """One full K4 (complex BHZ hoppings) H x v against the CPU oracle, SPARSE and DIRECT."""
+    import os
+    mdl = models.bhz2(3)
+    isec = models.get_sector(16, 8, 8)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(isec, True)
+    v = _vec(n, 13)
+    hv = _hxv(ed, n, v).cpu().numpy()
+    ed.delete_Hv_sector()
+    ed.build_Hv_sector(isec, False)
+    hvd = _hxv(ed, n, v).cpu().numpy()
+    ed.delete_Hv_sector()
+    vh = v.cpu().numpy()
+    cores = os.cpu_count() or 1
+    oracle_lib.lib().edo_set_num_threads(cores)
+    orc = oracle_lib.Oracle(mdl)
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_MPI, cores)
+    ref = orc.hxv(vh)
+    orc.delete_hv_sector()
+    assert np.abs(hv - ref).max() / np.abs(ref).max() < RTOL
+    assert np.abs(hvd - ref).max() / np.abs(ref).max() < RTOL
+
+
+@pytest.mark.parametrize("wl", ["K3", "K4"])
+def test_fullsize_sampled_rows_of_counter_vector(ed, oracle_lib, wl):
+    """The check the Ns=18 sector relies on (no host copy of the vector): v is the counter-based vector of
+    cdmft_lanc_ed_b200/synth.py, the oracle evaluates single rows of H x v from the index function alone."""
+    from cdmft_lanc_ed_b200 import synth
+    mdl = models.hm2x2(3) if wl == "K3" else models.bhz2(3)
+    isec = models.get_sector(16, 8, 8)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(isec, True)
+    sc = synth.default_scale(n)
+    v = synth.counter_vec_torch(0, n, 2024, sc)
+    hv = _hxv(ed, n, v)
+    rows = np.unique(np.random.default_rng(5).integers(0, n, size=4000))
+    got = hv[torch.from_numpy(rows).cuda()].cpu().numpy()
+    ed.delete_Hv_sector()
+    orc = oracle_lib.Oracle(mdl)
+    orc.build_hv_sector(isec, oracle_lib.DIRECT_SERIAL)
+    ref = orc.hxv_rows_counter(rows, 2024, sc)
+    orc.delete_hv_sector()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < RTOL
+
+
+def test_ns18_sector_against_oracle(oracle_lib):
+    """BASELINE config 5's model (3x2 cluster, Nbath=2, Ns=18) on a sector that fits one GPU and the oracle:
+    (9,2), DimUp 48 620 x DimDw 153.  A 778-KB up-column does not fit in shared memory, so the SPARSE column pass
+    is the block-split kernel k_colblk at its real block sizes; with simulated ranks the Hdw pass on the transposed
+    vector runs too.  H x v (SPARSE, DIRECT, P = 1 and 3) and the leading Krylov coefficients (complex and real
+    start vectors) against the oracle."""
+    import os
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    from cdmft_lanc_ed_b200 import synth
+    mdl = models.hm_ns18()
+    isec = models.get_sector(18, 9, 2)
+    cores = os.cpu_count() or 1
+    oracle_lib.lib().edo_set_num_threads(cores)
+    orc = oracle_lib.Oracle(mdl)
+    orc.build_hv_sector(isec, oracle_lib.SPARSE_MPI, min(cores, 16))
+    n = orc.dim
+    assert n == 48620 * 153
+    sc = synth.default_scale(n)
+    vh = synth.counter_vec_numpy(0, n, 9, sc)
+    ref = orc.hxv(vh)
+    ond, oa, ob = orc.lanc_tridiag(vh, 12)
+    vr = (vh.real / np.linalg.norm(vh.real)).astype(np.complex128)
+    ondr, oar, obr = orc.lanc_tridiag(vr, 12)
+    orc.delete_hv_sector()
+    for P in (1, 3):
+        if P == 1:
+            E.ed_init(0)
+        else:
+            E.ed_init_sim(P, 0)
+        try:
+            E.ed_set_model(mdl)
+            for sparse in (True, False):
+                assert E.build_Hv_sector(isec, sparse) == n
+                hv = E.hxv(vh)
+                assert np.abs(hv - ref).max() / np.abs(ref).max() < RTOL, (P, sparse)
+                if sparse:
+                    nd, a, b = E.sp_lanc_tridiag(vh, 12)
+                    assert nd == ond and np.abs(a[:10] - oa[:10]).max() <= RTOL * np.abs(oa[:10]).max()
+                    assert np.abs(b[:10] - ob[:10]).max() <= RTOL * np.abs(ob[:10]).max()
+                    ndr, ar, br = E.sp_lanc_tridiag(vr, 12)  # real Krylov vectors (8-byte block-split kernel)
+                    assert ndr == ondr and np.abs(ar[:10] - oar[:10]).max() <= RTOL * np.abs(oar[:10]).max()
+                E.delete_Hv_sector()
+        finally:
+            E.ed_finalize()
 
 
 def test_K2_gimp_matsubara_vs_oracle(ed, oracle_lib):
