@@ -839,6 +839,62 @@ __global__ void k_diag_only(int64_t n, int64_t ncols, double *__restrict__ out, 
   out[i + c * n] = diag_value(dg, i, mu_imp, c);
 }
 
+// ------------------------------------------------------------------------------------
+// Dense sector Hamiltonian, the optional `Hmat` of build_Hv_sector (ED_HAMILTONIAN.f90:123-127 ->
+// ED_HAMILTONIAN_SPARSE_HxV.f90:112-148: Hmat = spH0d [+ spH0nd] + kron(spH0dws, 1) + kron(1, spH0ups); caller
+// ED_DIAG.f90:199, the LAPACK branch for sectors below lanc_dim_threshold).  One thread per row i = (iup, idw)
+// of the GLOBAL sector: every rank assembles the whole matrix, as every rank of the reference does.
+// H is column-major [Dim, Dim], zeroed by the caller.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dense_hmat(int64_t dim, int64_t dimup, DiagArgs dg, OpArgs up, OpArgs dw, NonLocalArgs nl,
+                                                    int jhflag, double2 *__restrict__ H) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dim) return;
+  const int64_t iup = i % dimup, idw = i / dimup;
+  const uint32_t mup = (uint32_t)__ldg(up.map + iup), mdw = (uint32_t)__ldg(dw.map + idw);
+  auto add = [&](int64_t j, double re, double im) {
+    double2 *p = H + i + j * dim;
+    p->x += re;
+    p->y += im;
+  };
+  add(i, diag_value(dg, iup, mup & ((1u << dg.nimp) - 1u), idw), 0.0);
+  for (int t = 0; t < up.nterms; t++) {  // <i|H|j> = h(a,b) sg for |j> = c^+_b c_a |i>, as in the matrix-free column pass
+    const Term tm = up.terms[t];
+    if (((mup >> tm.a) & 1u) && !((mup >> tm.b) & 1u)) {
+      const uint32_t m = (mup & ~(1u << tm.a)) | (1u << tm.b);
+      const double sg = hop_sign_d(mup, tm.a, tm.b);
+      add(lin_rank_d(up.lin_lo, up.lin_hi, up.lbits, m) + idw * dimup, tm.re * sg, tm.im * sg);
+    }
+  }
+  for (int t = 0; t < dw.nterms; t++) {
+    const Term tm = dw.terms[t];
+    if (((mdw >> tm.a) & 1u) && !((mdw >> tm.b) & 1u)) {
+      const uint32_t m = (mdw & ~(1u << tm.a)) | (1u << tm.b);
+      const double sg = hop_sign_d(mdw, tm.a, tm.b);
+      add(iup + (int64_t)lin_rank_d(dw.lin_lo, dw.lin_hi, dw.lbits, m) * dimup, tm.re * sg, tm.im * sg);
+    }
+  }
+  if (!jhflag) return;
+  for (int ilat = 0; ilat < nl.nlat; ilat++)  // same conditions and signs as k_nonlocal
+    for (int io = 0; io < nl.norb; io++)
+      for (int jo = 0; jo < nl.norb; jo++) {
+        if (io == jo) continue;
+        const int is = io + ilat * nl.norb, js = jo + ilat * nl.norb;
+        const uint32_t bi = 1u << is, bj = 1u << js;
+        const bool nup_i = mup & bi, nup_j = mup & bj, ndw_i = mdw & bi, ndw_j = mdw & bj;
+        if (nl.jx != 0.0 && nup_j && ndw_i && !ndw_j && !nup_i) {
+          const uint32_t kdw = (mdw & ~bi) | bj, kup = (mup & ~bj) | bi;
+          const double sg = hop_sign2(mdw, js, is) * hop_sign2(mup, is, js);
+          add(lin_rank_d(nl.up_lo, nl.up_hi, nl.lbits, kup) + (int64_t)lin_rank_d(nl.dw_lo, nl.dw_hi, nl.lbits, kdw) * dimup, nl.jx * sg, 0.0);
+        }
+        if (nl.jp != 0.0 && nup_j && ndw_j && !ndw_i && !nup_i) {
+          const uint32_t kdw = (mdw & ~bj) | bi, kup = (mup & ~bj) | bi;
+          const double sg = hop_sign2(mdw, is, js) * hop_sign2(mup, is, js);
+          add(lin_rank_d(nl.up_lo, nl.up_hi, nl.lbits, kup) + (int64_t)lin_rank_d(nl.dw_lo, nl.dw_hi, nl.lbits, kdw) * dimup, nl.jp * sg, 0.0);
+        }
+      }
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -894,6 +950,112 @@ int cdmft_b200_get_diag(int64_t nloc, double *d) {
   CB_CUDA(cudaStreamSynchronize(c.stream));
   cudaFree(dd);
   return 0;
+}
+
+int cdmft_b200_build_hmat(void *hmat) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("build_hmat: Hsector NOT set (call build_hv_sector first)");
+  if (c.dim > 32768) return fail("build_hmat: Dim=%lld is too large for a dense matrix (the reference uses it below lanc_dim_threshold)", (long long)c.dim);
+  const int64_t n2 = c.dim * c.dim;
+  const bool dev = is_device_ptr(hmat);
+  double2 *d = (double2 *)hmat;
+  if (!dev) CB_CHECK(dev_alloc(&d, n2));
+  int rc = 0;
+  auto body = [&]() -> int {
+    CB_CUDA(cudaMemsetAsync(d, 0, (size_t)n2 * sizeof(double2), c.stream));
+    NonLocalArgs a{};
+    a.map_up = c.up.map; a.map_dw = c.dw.map;
+    a.up_lo = c.up.lin_lo; a.up_hi = c.up.lin_hi; a.dw_lo = c.dw.lin_lo; a.dw_hi = c.dw.lin_hi;
+    a.lbits = c.ns / 2; a.nlat = c.m.nlat; a.norb = c.m.norb; a.jx = c.m.jx; a.jp = c.m.jp; a.dimup = c.dimup;
+    if (c.dim > 0) {
+      k_dense_hmat<<<(unsigned)((c.dim + 127) / 128), 128, 0, c.stream>>>(c.dim, c.dimup, diag_args(0), op_args(c.up), op_args(c.dw), a,
+                                                                          c.jhflag ? 1 : 0, d);
+      c.launches++;
+    }
+    if (!dev) CB_CUDA(cudaMemcpyAsync(hmat, d, (size_t)n2 * sizeof(double2), cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+  };
+  rc = body();
+  if (!dev && d) cudaFree(d);
+  return rc;
+}
+
+// scatter_vector_MPI / gather_vector_MPI (ED_SETUP.f90:575-668): the root's full sector vector <-> every rank's
+// Ndw shard (shards are contiguous: rank r owns columns [off_r, off_r + q_r) of v(DimUp, DimDw)).  The reference
+// needs them around sp_lanc_tridiag (ED_GF_NORMAL.f90:214) and es_return_cvector (ED_EIGENSPACE.f90:499-569).
+// vfull is significant on the root only; host or device pointers.  Single rank / simulated ranks: plain copies.
+static int shard_bounds(int rank, int64_t *off, int64_t *cnt) {
+  Ctx &c = ctx();
+  *off = *cnt = 0;
+  if (rank >= c.p_eff) return 0;
+  const Split s = split_of(c.dimdw, c.p_eff, rank);
+  *off = s.off * c.dimup;
+  *cnt = s.q * c.dimup;
+  return 0;
+}
+static int scatter_gather(void *vfull, void *vloc, int root, bool scatter) {
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("%s: Hsector NOT set", scatter ? "scatter_vector" : "gather_vector");
+  const bool spmd = c.spmd && c.nranks > 1;
+  if (root < 0 || root >= (spmd ? c.nranks : 1)) return fail("scatter/gather_vector: bad root %d", root);
+  if (!spmd) {  // one process holds every shard back to back = the full vector
+    if (vfull == vloc || c.dim == 0) return 0;
+    CB_CUDA(cudaMemcpyAsync(scatter ? vloc : vfull, scatter ? vfull : vloc, (size_t)c.dim * 16, cudaMemcpyDefault, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+  }
+  int64_t moff = 0, mcnt = 0;
+  shard_bounds(c.rank, &moff, &mcnt);
+  const bool me_root = c.rank == root;
+  // device staging for host pointers
+  double2 *dfull = nullptr, *dloc = nullptr;
+  const bool full_dev = me_root && vfull && is_device_ptr(vfull), loc_dev = mcnt > 0 && is_device_ptr(vloc);
+  int rc = 0;
+  auto body = [&]() -> int {
+    if (me_root) {
+      if (full_dev) dfull = (double2 *)vfull;
+      else {
+        CB_CHECK(dev_alloc(&dfull, c.dim));
+        if (scatter) CB_CUDA(cudaMemcpyAsync(dfull, vfull, (size_t)c.dim * 16, cudaMemcpyHostToDevice, c.stream));
+      }
+    }
+    if (mcnt > 0) {
+      if (loc_dev) dloc = (double2 *)vloc;
+      else {
+        CB_CHECK(dev_alloc(&dloc, mcnt));
+        if (!scatter) CB_CUDA(cudaMemcpyAsync(dloc, vloc, (size_t)mcnt * 16, cudaMemcpyHostToDevice, c.stream));
+      }
+    }
+    std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
+    if (scatter) {
+      if (me_root) for (int p = 0; p < c.nranks; p++) shard_bounds(p, &os[p], &cs[p]);
+      cr[root] = mcnt;
+      CB_CHECK(nccl_all_to_all(dfull, dloc, cs.data(), os.data(), cr.data(), orr.data()));
+    } else {
+      cs[root] = mcnt;
+      if (me_root) for (int p = 0; p < c.nranks; p++) shard_bounds(p, &orr[p], &cr[p]);
+      CB_CHECK(nccl_all_to_all(dloc, dfull, cs.data(), os.data(), cr.data(), orr.data()));
+    }
+    if (scatter && mcnt > 0 && !loc_dev) CB_CUDA(cudaMemcpyAsync(vloc, dloc, (size_t)mcnt * 16, cudaMemcpyDeviceToHost, c.stream));
+    if (!scatter && me_root && !full_dev) CB_CUDA(cudaMemcpyAsync(vfull, dfull, (size_t)c.dim * 16, cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+  };
+  rc = body();
+  if (me_root && !full_dev && dfull) cudaFree(dfull);
+  if (mcnt > 0 && !loc_dev && dloc) cudaFree(dloc);
+  return rc;
+}
+int cdmft_b200_scatter_vector(const void *vfull, void *vloc, int32_t root) {
+  CB_REQUIRE_INIT();
+  return scatter_gather((void *)vfull, vloc, root, true);
+}
+int cdmft_b200_gather_vector(const void *vloc, void *vfull, int32_t root) {
+  CB_REQUIRE_INIT();
+  return scatter_gather(vfull, (void *)vloc, root, false);
 }
 
 }  // extern "C"

@@ -809,21 +809,37 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   return rc;
 }
 
+int cdmft_b200_add_to_lanczos_gf_full(const double vnorm2[2], double ei, double egs, int32_t finite_t, double beta, int32_t nlanc,
+                                      const double *alanc, const double *blanc, int32_t isign, double zeta, int32_t lmats,
+                                      const double *wm, double *gmats, int32_t lreal, const double *wr, double eps, double *greal,
+                                      double *poles, double *weights) {
+  if (nlanc <= 0) return fail("add_to_lanczos_gf: nlanc must be positive");
+  std::vector<double> d(alanc, alanc + nlanc), e(blanc, blanc + nlanc), Z;
+  CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
+  const std::complex<double> vn(vnorm2[0], vnorm2[1]);
+  std::complex<double> pesoBZ(0.0, 0.0);  // Boltzmann factor of the state the channel was built on
+  if (finite_t) {
+    if (beta * (ei - egs) < 200.0) pesoBZ = vn * std::exp(-beta * (ei - egs)) / zeta;
+  } else {
+    pesoBZ = vn / zeta;
+  }
+  std::complex<double> *gm = (std::complex<double> *)gmats, *gr = (std::complex<double> *)greal;
+  for (int j = 0; j < nlanc; j++) {
+    const double pole = (double)isign * (d[j] - ei);
+    const std::complex<double> peso = pesoBZ * Z[j] * Z[j];  // first row of the eigenvector matrix
+    if (poles) poles[j] = pole;
+    if (weights) { weights[2 * j] = peso.real(); weights[2 * j + 1] = peso.imag(); }
+    for (int i = 0; i < lmats; i++) gm[i] += peso / (std::complex<double>(0.0, wm[i]) - pole);
+    for (int i = 0; i < lreal; i++) gr[i] += peso / (std::complex<double>(wr[i], eps) - pole);
+  }
+  return 0;
+}
+
 int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlanc, const double *alanc, const double *blanc,
                                  int32_t isign, double zeta, int32_t lmats, const double *wm, double *g, double *poles,
                                  double *weights) {
-  std::vector<double> d(alanc, alanc + nlanc), e(blanc, blanc + nlanc), Z;
-  CB_CHECK(tridiag_eigh(nlanc, d, e, &Z));
-  const std::complex<double> pesoBZ = std::complex<double>(vnorm2[0], vnorm2[1]) / zeta;  // T=0 branch
-  std::complex<double> *gc = (std::complex<double> *)g;
-  for (int j = 0; j < nlanc; j++) {
-    double de = d[j] - ei;
-    std::complex<double> peso = pesoBZ * Z[j] * Z[j];  // Z(1,j): first row
-    if (poles) poles[j] = isign * de;
-    if (weights) { weights[2 * j] = peso.real(); weights[2 * j + 1] = peso.imag(); }
-    for (int i = 0; i < lmats; i++) gc[i] += peso / (std::complex<double>(0.0, wm[i]) - (double)isign * de);
-  }
-  return 0;
+  return cdmft_b200_add_to_lanczos_gf_full(vnorm2, ei, ei, 0, 0.0, nlanc, alanc, blanc, isign, zeta, lmats, wm, g, 0, nullptr, 0.0,
+                                           nullptr, poles, weights);
 }
 
 }  // extern "C"

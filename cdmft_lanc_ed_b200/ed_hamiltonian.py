@@ -54,7 +54,8 @@ ABI_SYMBOLS = [
     "cdmft_b200_get_csr_nnz", "cdmft_b200_get_csr", "cdmft_b200_get_diag", "cdmft_b200_get_sparse_map",
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
     "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
-    "cdmft_b200_colblk_host",
+    "cdmft_b200_colblk_host", "cdmft_b200_add_to_lanczos_gf_full", "cdmft_b200_build_hmat", "cdmft_b200_scatter_vector",
+    "cdmft_b200_gather_vector",
 ]
 
 
@@ -78,6 +79,8 @@ def _chk(rc):
 
 def _ptr(a):
     """numpy array, torch tensor (CPU or CUDA) or raw int address -> void*"""
+    if a is None:
+        return C.c_void_p(0)
     if isinstance(a, int):
         return C.c_void_p(a)
     if isinstance(a, np.ndarray):
@@ -474,6 +477,42 @@ def add_to_lanczos_gf_normal(vnorm2, Ei, alanc, blanc, isign, zeta, wm, g):
     return poles, weights
 
 
+def add_to_lanczos_gf_normal_full(vnorm2, Ei, Egs, finiteT, beta, alanc, blanc, isign, zeta, wm, gmats, wr, eps, greal):
+    """add_to_lanczos_gf_normal with the finite-temperature weight and the real-axis accumulation (impGreal);
+    gmats [Lmats] / greal [Lreal] complex128, accumulated in place; returns (poles, weights)."""
+    n = len(alanc)
+    a = np.ascontiguousarray(alanc, dtype=np.float64)
+    b = np.ascontiguousarray(blanc, dtype=np.float64)
+    wm = np.ascontiguousarray(wm, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    vn = (C.c_double * 2)(complex(vnorm2).real, complex(vnorm2).imag)
+    poles = np.zeros(n)
+    weights = np.zeros(n, dtype=np.complex128)
+    _chk(load_library().cdmft_b200_add_to_lanczos_gf_full(
+        vn, C.c_double(Ei), C.c_double(Egs), C.c_int32(int(finiteT)), C.c_double(beta), C.c_int32(n), _ptr(a), _ptr(b),
+        C.c_int32(isign), C.c_double(zeta), C.c_int32(wm.size), _ptr(wm), _ptr(gmats), C.c_int32(wr.size), _ptr(wr),
+        C.c_double(eps), _ptr(greal), _ptr(poles), _ptr(weights)))
+    return poles, weights
+
+
+def build_Hmat() -> np.ndarray:
+    """The dense `Hmat` of build_Hv_sector(isector, Hmat) for the active sector: complex128 [Dim, Dim], Fortran order."""
+    dim = getDim(_sector["isector"])[0]
+    h = np.zeros((dim, dim), dtype=np.complex128, order="F")
+    _chk(load_library().cdmft_b200_build_hmat(_ptr(h)))
+    return h
+
+
+def scatter_vector_MPI(vfull, vloc, root: int = 0):
+    """scatter_vector_MPI(MpiComm, v, vloc): the root's full vector -> every rank's shard (ED_SETUP.f90:575-611)."""
+    _chk(load_library().cdmft_b200_scatter_vector(_ptr(vfull), _ptr(vloc), C.c_int32(root)))
+
+
+def gather_vector_MPI(vloc, vfull, root: int = 0):
+    """gather_vector_MPI(MpiComm, vloc, v): shards -> the root's full vector (ED_SETUP.f90:633-668)."""
+    _chk(load_library().cdmft_b200_gather_vector(_ptr(vloc), _ptr(vfull), C.c_int32(root)))
+
+
 # --------------------------------------------------------------------------------------
 # local observables (ED_OBSERVABLES.f90:94-236)
 # --------------------------------------------------------------------------------------
@@ -486,39 +525,30 @@ def imp_weights(vec, nimp: int) -> np.ndarray:
 
 
 def observables_from_weights(W: np.ndarray, nlat: int, norb: int, peso: float = 1.0) -> dict:
-    """The reference's master loop (ED_OBSERVABLES.f90:120-192) evaluated on the impurity-configuration weights:
-    gs_weight = peso*W[mu, md], nup/ndw = bits imp_state_index(ilat,iorb)-1 of mu/md.  Fortran-ordered arrays."""
+    """Local observables of lanc_observables (ED_OBSERVABLES.f90:120-192) from the impurity-configuration weights
+    W[mu, md], as matrix contractions instead of a loop over configurations: with the occupation table
+    N[config, a] (a = imp_state_index - 1) and the marginals Wu = sum_md W, Wd = sum_mu W,
+        <n_a,up> = N^T Wu,  <n_a,dw> = N^T Wd,  <n_a,up n_b,dw> = N^T W N,  <n_a,s n_b,s> = N^T diag(W_s) N,
+    and Sz = (n_up - n_dw)/2, n = n_up + n_dw follow by linearity.  Returns Fortran-ordered arrays with the
+    reference's fill pattern (sz2 / n2: same-orbital entries only on the same site)."""
     nimp = nlat * norb
-    nmu = 1 << nimp
-    out = {k: np.zeros((nlat, norb), order="F") for k in ("dens_up", "dens_dw", "docc", "magz")}
-    out["s2tot"] = np.zeros(nlat)
-    out["sz2"] = np.zeros((nlat, nlat, norb, norb), order="F")
-    out["n2"] = np.zeros((nlat, nlat, norb, norb), order="F")
-    bits = np.array([[(m >> p) & 1 for p in range(nimp)] for m in range(nmu)], dtype=float)  # [config, pos]
-    pos = lambda il, io: io + il * norb  # imp_state_index - 1
-    for mu in range(nmu):
-        for md in range(nmu):
-            w = peso * W[mu, md]
-            if w == 0.0:
-                continue
-            nu = np.array([[bits[mu, pos(il, io)] for io in range(norb)] for il in range(nlat)])
-            nd = np.array([[bits[md, pos(il, io)] for io in range(norb)] for il in range(nlat)])
-            sz, nt = (nu - nd) / 2.0, nu + nd
-            out["dens_up"] += nu * w
-            out["dens_dw"] += nd * w
-            out["docc"] += nu * nd * w
-            out["magz"] += (nu - nd) * w
-            out["s2tot"] += sz.sum(axis=1) ** 2 * w
-            for il in range(nlat):
-                for io in range(norb):
-                    out["sz2"][il, il, io, io] += sz[il, io] ** 2 * w
-                    out["n2"][il, il, io, io] += nt[il, io] ** 2 * w
-                    for jl in range(nlat):
-                        for jo in range(io + 1, norb):
-                            out["sz2"][il, jl, io, jo] += sz[il, io] * sz[jl, jo] * w
-                            out["sz2"][il, jl, jo, io] += sz[il, jo] * sz[jl, io] * w
-                            out["n2"][il, jl, io, jo] += nt[il, io] * nt[jl, jo] * w
-                            out["n2"][il, jl, jo, io] += nt[il, jo] * nt[jl, io] * w
+    cfg = np.arange(1 << nimp)
+    N = ((cfg[:, None] >> np.arange(nimp)[None, :]) & 1).astype(float)  # [config, a]
+    W = peso * np.asarray(W, dtype=float)
+    Wu, Wd = W.sum(axis=1), W.sum(axis=0)
+    nu, nd = N.T @ Wu, N.T @ Wd
+    UD = N.T @ W @ N                       # <n_a,up n_b,dw>
+    UU, DD = (N.T * Wu) @ N, (N.T * Wd) @ N
+    SZ = (UU - UD - UD.T + DD) / 4.0       # <Sz_a Sz_b>
+    NN = UU + UD + UD.T + DD               # <n_a n_b>
+    shape2 = lambda x: np.asfortranarray(x.reshape(nlat, norb))  # a = iorb + ilat*norb
+    out = {"dens_up": shape2(nu), "dens_dw": shape2(nd), "docc": shape2(np.diag(UD).copy()), "magz": shape2(nu - nd)}
+    a_of = (np.arange(nlat)[:, None] * norb + np.arange(norb)[None, :])  # [ilat, iorb] -> a
+    out["s2tot"] = np.array([SZ[np.ix_(a_of[il], a_of[il])].sum() for il in range(nlat)])
+    for name, M in (("sz2", SZ), ("n2", NN)):
+        full = M[a_of[:, None, :, None], a_of[None, :, None, :]]  # [ilat, jlat, iorb, jorb]
+        same_orb = np.eye(norb, dtype=bool)[None, None, :, :] & ~np.eye(nlat, dtype=bool)[:, :, None, None]
+        out[name] = np.asfortranarray(np.where(same_orb, 0.0, full))
     out["dens"] = out["dens_up"] + out["dens_dw"]
     return out
 

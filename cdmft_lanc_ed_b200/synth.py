@@ -7,8 +7,8 @@ rows of H x v can be checked without materialising a vector that does not fit in
     mix64(x): x ^= x >> 31; x *= 0xD6E8FEB86659FD93; x ^= x >> 32
     v(i) = scale * ( (x >> 11) * 2^-53 * 2 - 1  +  1j * ((y >> 11) * 2^-53 * 2 - 1) )
 
-The same function exists in C in the test oracle (oracle/ed_oracle.c, edo_counter_vec); tests/test_synth_cpu.py
-checks that the three agree bit for bit."""
+The test infrastructure carries its own C copy of this function (edo_counter_vec); tests/test_synth_cpu.py checks
+that the three agree bit for bit."""
 from __future__ import annotations
 
 import numpy as np

@@ -183,6 +183,27 @@ int cdmft_b200_add_to_lanczos_gf(const double vnorm2[2], double ei, int32_t nlan
                                  const double *blanc, int32_t isign, double zeta, int32_t lmats,
                                  const double *wm, double *g, double *poles, double *weights);
 
+/* the same routine with all its branches: finite_t != 0 weighs the channel with exp(-beta (ei - egs)) / zeta (dropped
+ * when beta (ei - egs) >= 200, :930-936), and the real-axis function is accumulated next to the Matsubara one,
+ * greal[i] += peso / (wr[i] + i eps - isign (E_j - ei)) (:968-971).  Host arrays; gmats / greal may be NULL with
+ * lmats / lreal = 0.  No device is needed (the tridiagonal problem is nlanc x nlanc). */
+int cdmft_b200_add_to_lanczos_gf_full(const double vnorm2[2], double ei, double egs, int32_t finite_t, double beta,
+                                      int32_t nlanc, const double *alanc, const double *blanc, int32_t isign, double zeta,
+                                      int32_t lmats, const double *wm, double *gmats, int32_t lreal, const double *wr,
+                                      double eps, double *greal, double *poles, double *weights);
+
+/* ---- dense sector matrix and shard <-> full vector moves ---------------------------------------- */
+/* The optional `Hmat` of build_Hv_sector(isector, Hmat) (ED_HAMILTONIAN.f90:123-127 ->
+ * ED_HAMILTONIAN_SPARSE_HxV.f90:112-148; caller ED_DIAG.f90:199, the LAPACK branch): the dense Hamiltonian of the
+ * ACTIVE sector, complex(8) [Dim, Dim] column-major, host or device pointer.  Every rank receives the whole matrix,
+ * as in the reference.  Dim <= 32768. */
+int cdmft_b200_build_hmat(void *hmat);
+/* scatter_vector_MPI / gather_vector_MPI (ED_SETUP.f90:575-668) for the active sector: vfull = complex(8)[Dim]
+ * on `root` (ignored elsewhere), vloc = this rank's shard [nloc]; host or device pointers.  Collective in SPMD
+ * mode (NCCL send/recv); a plain copy with one rank or simulated ranks. */
+int cdmft_b200_scatter_vector(const void *vfull, void *vloc, int32_t root);
+int cdmft_b200_gather_vector(const void *vloc, void *vfull, int32_t root);
+
 /* ---- local observables (ED_OBSERVABLES.f90:94-236, lanc_observables) --------------------------- */
 /* w[mu + md*2^Nimp] = sum over all basis states whose up / dw Fock states have the impurity bits mu / md of
  * |vec|^2 (4^Nimp doubles, host).  Every observable of the reference's master loop (:120-192: dens, dens_up,

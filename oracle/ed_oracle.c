@@ -1135,6 +1135,33 @@ int32_t edo_add_to_lanczos_gf(edo_c64 vnorm2, double ei, int32_t nlanc, const do
   return 0;
 }
 
+/* the same routine with its two other branches: the Boltzmann weight of finite-temperature runs (:930-936) and the
+ * real-axis accumulation impGreal (:968-971, iw = dcmplx(wr(i), eps)); gr may be NULL (lreal = 0) */
+int32_t edo_add_to_lanczos_gf_full(edo_c64 vnorm2, double ei, double egs, int32_t finite_t, double beta, int32_t nlanc,
+                                   const double *alanc, const double *blanc, int32_t isign, double zeta, int32_t lmats,
+                                   const double *wm, edo_c64 *gm, int32_t lreal, const double *wr, double eps, edo_c64 *gr,
+                                   double *poles, edo_c64 *weights) {
+  double *diag = (double *)malloc(nlanc * sizeof(double)), *sub = (double *)malloc(nlanc * sizeof(double));
+  double *Z = (double *)malloc((size_t)nlanc * nlanc * sizeof(double));
+  memcpy(diag, alanc, nlanc * sizeof(double));
+  memcpy(sub, blanc, nlanc * sizeof(double));
+  if (edo_tridiag_eigh(nlanc, diag, sub, Z)) return -1;
+  edo_c64 pesoBZ;
+  if (finite_t && beta * (ei - egs) < 200) pesoBZ = vnorm2 * exp(-beta * (ei - egs)) / zeta;
+  else if (!finite_t) pesoBZ = vnorm2 / zeta;
+  else pesoBZ = 0;
+  for (int j = 0; j < nlanc; j++) {
+    double de = diag[j] - ei;
+    edo_c64 peso = pesoBZ * Z[(size_t)j * nlanc] * Z[(size_t)j * nlanc];
+    if (poles) poles[j] = isign * de;
+    if (weights) weights[j] = peso;
+    for (int i = 0; i < lmats; i++) gm[i] += peso / (I * wm[i] - isign * de);
+    for (int i = 0; i < lreal; i++) gr[i] += peso / ((wr[i] + I * eps) - isign * de);
+  }
+  free(diag); free(sub); free(Z);
+  return 0;
+}
+
 /* ---- lanc_observables: local observables of one eigenstate --------------------------------------
  * ED_OBSERVABLES.f90:94-236 (the master-only loop :120-192): for every basis state i of the sector
  * gs_weight = peso*|vec(i)|^2, impurity occupations from Bdecomp of the up / dw Fock states

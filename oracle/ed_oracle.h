@@ -162,6 +162,10 @@ int32_t edo_apply_op(int32_t ns, int32_t isector, int32_t iop, int32_t ispin, in
 int32_t edo_add_to_lanczos_gf(edo_c64 vnorm2, double ei, int32_t nlanc, const double *alanc,
                               const double *blanc, int32_t isign, double zeta, int32_t lmats,
                               const double *wm, edo_c64 *g, double *poles, edo_c64 *weights);
+int32_t edo_add_to_lanczos_gf_full(edo_c64 vnorm2, double ei, double egs, int32_t finite_t, double beta, int32_t nlanc,
+                                   const double *alanc, const double *blanc, int32_t isign, double zeta, int32_t lmats,
+                                   const double *wm, edo_c64 *gm, int32_t lreal, const double *wr, double eps, edo_c64 *gr,
+                                   double *poles, edo_c64 *weights);
 
 /* number of OpenMP threads the MPI-simulating paths will use */
 int32_t edo_num_threads(void);

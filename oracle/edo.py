@@ -151,6 +151,28 @@ def add_to_lanczos_gf(vnorm2, ei, alanc, blanc, isign, zeta, wm, g):
     return poles, weights
 
 
+def add_to_lanczos_gf_full(vnorm2, ei, egs, finite_t, beta, alanc, blanc, isign, zeta, wm, gm, wr, eps, gr):
+    """All branches of add_to_lanczos_gf_normal: T=0 / finite-T weight, Matsubara and real axis.  Accumulates into
+    gm [Lmats] and gr [Lreal] in place; returns (poles, weights)."""
+    n = len(alanc)
+    a = np.ascontiguousarray(alanc, dtype=np.float64)
+    b = np.ascontiguousarray(blanc, dtype=np.float64)
+    wm = np.ascontiguousarray(wm, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    poles = np.zeros(n)
+    weights = np.zeros(n, dtype=np.complex128)
+
+    class _Z(C.Structure):
+        _fields_ = [("re", C.c_double), ("im", C.c_double)]
+    f = lib().edo_add_to_lanczos_gf_full
+    f.argtypes = [_Z, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                  C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    z = complex(vnorm2)
+    _chk(f(_Z(z.real, z.imag), ei, egs, int(finite_t), beta, n, _p(a), _p(b), isign, zeta, wm.size, _p(wm), _p(gm),
+           wr.size, _p(wr), eps, _p(gr), _p(poles), _p(weights)))
+    return poles, weights
+
+
 def apply_op(ns, isector, iop, ispin, pos, coef, state):
     """(sum_k coef[k] * op_{pos[k]}) |state>, op = cdg (iop=+1) / c (iop=-1). Returns (jsector, out)."""
     L = lib()

@@ -1,6 +1,8 @@
 """Generates tests/golden/golden_small.npz from the CPU oracle (the reference cannot run here:
-Fortran + MPI + SciFortran absent), after checking each case against the independent
-Jordan-Wigner ED.  Re-run:  python tests/golden/make_golden.py"""
+Fortran + MPI + SciFortran absent).  The Ns = 4 cases (jw = true in the meta record) are checked against the
+independent dense Jordan-Wigner ED (oracle/jw_ed.py) at generation time, and the script refuses to write the file
+if one of them fails; the Ns = 8 cases are too large for the dense 4^Ns construction and are plain oracle dumps
+(the oracle itself is pinned on small models in tests/test_oracle_pin.py).  Re-run:  python tests/golden/make_golden.py"""
 import json
 import os
 import sys
@@ -17,11 +19,16 @@ CASES = [
     dict(key="hm2x2_nb1_54", builder="hm2x2", args=[1], nup=5, ndw=4),
     dict(key="bhz2_nb1_44", builder="bhz2", args=[1], nup=4, ndw=4),
     dict(key="bhz2_nb1_34", builder="bhz2", args=[1], nup=3, ndw=4),
+    # Ns = 4: small enough for the dense Jordan-Wigner ED -> really cross-checked below
+    dict(key="hub2x1_nb1_22", builder="hubbard_cluster", args=[2, 1, 1], nup=2, ndw=2),
+    dict(key="rand_L1O2B1_kanamori_22", builder="random_model", args=[1, 2, 1], kwargs=dict(seed=2, kanamori=True), nup=2, ndw=2),
+    dict(key="rand_L2O1B1_S2_21", builder="random_model", args=[2, 1, 1], kwargs=dict(nspin=2, seed=3), nup=2, ndw=1),
+    dict(key="rand_L1O1B3_nohf_13", builder="random_model", args=[1, 1, 3], kwargs=dict(seed=5, hfmode=False), nup=1, ndw=3),
 ]
 
 out = {}
 for c in CASES:
-    mdl = getattr(models, c["builder"])(*c["args"])
+    mdl = getattr(models, c["builder"])(*c["args"], **c.get("kwargs", {}))
     ns = mdl.ns
     c["isector"] = models.get_sector(ns, c["nup"], c["ndw"])
     orc = edo.Oracle(mdl)
@@ -41,9 +48,11 @@ for c in CASES:
     n, a, b = orc.lanc_tridiag(v, 30)
     out[k + "_alanc"], out[k + "_blanc"] = a, b
     orc.delete_hv_sector()
-    if ns <= 5:
+    c["jw"] = bool(ns <= 5)
+    if c["jw"]:
         Hs = jw_ed.sector_hamiltonian(mdl, c["nup"], c["ndw"])
-        assert np.abs(Hs @ v - out[k + "_hv"]).max() < 1e-13
+        assert np.abs(Hs @ v - out[k + "_hv"]).max() < 1e-13, k
 out["meta"] = json.dumps({"cases": CASES})
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_small.npz"), **out)
+assert sum(c["jw"] for c in CASES) >= 4
 print("written", sum(v.nbytes for k, v in out.items() if k != "meta"), "bytes")

@@ -35,3 +35,31 @@ def test_observables_from_weights_match_the_reference_loop(case):
     # sum rules: particle numbers on the impurity never exceed the sector's, weights sum to peso
     assert abs(weights_numpy(mdl, nup, ndw, vec).sum() - 1.0) < 1e-12
     assert ref["dens_up"].sum() <= nup * 0.7 + 1e-12 and ref["dens_dw"].sum() <= ndw * 0.7 + 1e-12
+
+
+def test_add_to_lanczos_gf_all_branches_host_logic(oracle_lib):
+    """add_to_lanczos_gf_normal (ED_GF_NORMAL.f90:915-975) is host arithmetic on an nlanc x nlanc tridiagonal problem:
+    the product's version (T=0 / finite-T weight, Matsubara and real axis) against the oracle's restatement."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    rng = np.random.default_rng(3)
+    n = 25
+    a, b = rng.normal(size=n), np.abs(rng.normal(size=n)) + 0.1
+    b[0] = 0.0
+    wm = np.pi / 30.0 * (2 * np.arange(1, 33) - 1)
+    wr = np.linspace(-4, 4, 41)
+    for finite_t, beta, ei, egs in [(0, 0.0, -1.3, -1.3), (1, 30.0, -1.1, -1.3), (1, 30.0, 9.0, -1.3)]:
+        for isign in (1, -1):
+            gm, gr = np.zeros(wm.size, dtype=np.complex128), np.zeros(wr.size, dtype=np.complex128)
+            om, orr = gm.copy(), gr.copy()
+            p, w = E.add_to_lanczos_gf_normal_full(0.7 + 0.1j, ei, egs, finite_t, beta, a, b, isign, 1.3, wm, gm, wr, 0.01, gr)
+            op, ow = oracle_lib.add_to_lanczos_gf_full(0.7 + 0.1j, ei, egs, finite_t, beta, a, b, isign, 1.3, wm, om, wr, 0.01, orr)
+            assert np.abs(p - op).max() < 1e-12 and np.abs(w - ow).max() < 1e-13
+            assert np.abs(gm - om).max() <= 1e-12 * max(np.abs(om).max(), 1e-30)
+            assert np.abs(gr - orr).max() <= 1e-12 * max(np.abs(orr).max(), 1e-30)
+            if finite_t and ei > 5:
+                assert np.all(gm == 0) and np.all(gr == 0)  # beta*(Ei-Egs) >= 200: the state carries no weight
+    # the T=0 entry is the same routine
+    g1, g2 = np.zeros(wm.size, dtype=np.complex128), np.zeros(wm.size, dtype=np.complex128)
+    E.add_to_lanczos_gf_normal(0.5, -1.0, a, b, 1, 1.0, wm, g1)
+    E.add_to_lanczos_gf_normal_full(0.5, -1.0, -1.0, 0, 0.0, a, b, 1, 1.0, wm, g2, np.zeros(0), 0.0, np.zeros(0, dtype=np.complex128))
+    assert np.array_equal(g1, g2)

@@ -132,13 +132,14 @@ def test_gimp_vs_exact_full_fock(oracle_lib):
 
 
 def test_golden_fixtures(oracle_lib):
-    """tests/golden/*.npz were produced by tests/golden/make_golden.py (oracle outputs, checked against
-    jw_ed at generation time); they guard the oracle against drift and feed the GPU tests."""
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py: oracle outputs; the Ns = 4 cases (meta
+    jw = true) were checked against the dense Jordan-Wigner ED when generated, and are re-checked here; the Ns = 8
+    cases are plain oracle dumps.  They guard the oracle against drift and feed the GPU tests."""
     path = os.path.join(HERE, "golden", "golden_small.npz")
     g = np.load(path)
     meta = json.loads(str(g["meta"]))
     for case in meta["cases"]:
-        mdl = getattr(models, case["builder"])(*case["args"])
+        mdl = getattr(models, case["builder"])(*case["args"], **case.get("kwargs", {}))
         orc = oracle_lib.Oracle(mdl)
         isec = case["isector"]
         key = case["key"]
@@ -150,6 +151,10 @@ def test_golden_fixtures(oracle_lib):
         v = g[key + "_v"]
         assert np.abs(orc.hxv(v) - g[key + "_hv"]).max() < 1e-13
         orc.delete_hv_sector()
+        if case.get("jw"):
+            Hs = jw_ed.sector_hamiltonian(mdl, case["nup"], case["ndw"])
+            assert np.abs(Hs @ v - g[key + "_hv"]).max() < 1e-13, key
+    assert sum(bool(c.get("jw")) for c in meta["cases"]) >= 4
 
 
 def test_observables_oracle_against_jordan_wigner_operators(oracle_lib):

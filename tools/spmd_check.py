@@ -81,6 +81,14 @@ def main():
                 # gather on rank 0 (gather_vector_MPI, ED_SETUP.f90:633-668)
                 parts = [None] * world
                 dist.all_gather_object(parts, hv)
+                # the library's own scatter_vector_MPI / gather_vector_MPI (root 0; host buffers)
+                sc = np.zeros(max(nloc, 1), dtype=np.complex128)
+                E.scatter_vector_MPI(v if rank == 0 else None, sc, 0)
+                assert np.array_equal(sc[:nloc], vloc), "scatter_vector_MPI"
+                gf = np.zeros(dim, dtype=np.complex128) if rank == 0 else None
+                E.gather_vector_MPI(hv if nloc else np.zeros(1, dtype=np.complex128), gf, 0)
+                if rank == 0:
+                    assert np.array_equal(gf, np.concatenate([p for p in parts if p.size])), "gather_vector_MPI"
                 E.delete_Hv_sector()
                 if rank == 0:
                     ond, oa, ob = ref["tri"]
