@@ -20,7 +20,8 @@ MODULE ED_HAMILTONIAN_B200
   public :: build_Hv_sector, delete_Hv_sector, vecDim_Hv_sector
   public :: b200_HxV
   public :: b200_lanc_eigh, b200_lanc_tridiag
-  public :: b200_imp_weights, b200_lanc_observables
+  public :: b200_scatter_vector, b200_gather_vector
+  public :: b200_imp_weights
 
   type, bind(C) :: cdmft_b200_model
      integer(c_int32_t) :: nlat, norb, nspin, nbath
@@ -106,6 +107,34 @@ MODULE ED_HAMILTONIAN_B200
        integer(c_int32_t) :: ndone
        integer(c_int) :: rc
      end function c_lanc_tridiag
+     function c_build_hmat(hmat) bind(C, name="cdmft_b200_build_hmat") result(rc)
+       import :: c_int, c_double_complex
+       complex(c_double_complex) :: hmat(*)
+       integer(c_int) :: rc
+     end function c_build_hmat
+     function c_scatter(vfull, vloc, root) bind(C, name="cdmft_b200_scatter_vector") result(rc)
+       import :: c_int, c_int32_t, c_double_complex
+       complex(c_double_complex) :: vfull(*), vloc(*)
+       integer(c_int32_t), value :: root
+       integer(c_int) :: rc
+     end function c_scatter
+     function c_gather(vloc, vfull, root) bind(C, name="cdmft_b200_gather_vector") result(rc)
+       import :: c_int, c_int32_t, c_double_complex
+       complex(c_double_complex) :: vloc(*), vfull(*)
+       integer(c_int32_t), value :: root
+       integer(c_int) :: rc
+     end function c_gather
+     function c_ipc_export(h) bind(C, name="cdmft_b200_ipc_export") result(rc)
+       import :: c_int, c_char
+       character(kind=c_char) :: h(128)
+       integer(c_int) :: rc
+     end function c_ipc_export
+     function c_ipc_import(all, nranks) bind(C, name="cdmft_b200_ipc_import") result(rc)
+       import :: c_int, c_int32_t, c_char
+       character(kind=c_char) :: all(*)
+       integer(c_int32_t), value :: nranks
+       integer(c_int) :: rc
+     end function c_ipc_import
      function c_imp_weights(nloc, vec, w) bind(C, name="cdmft_b200_imp_weights") result(rc)
        import :: c_int, c_int64_t, c_double, c_double_complex
        integer(c_int64_t), value :: nloc
@@ -186,12 +215,29 @@ contains
     call check(c_set_model(m), "set_model")
   end subroutine push_model
 
-  !> ED_HAMILTONIAN.f90:39-143 (the dense `Hmat` variant stays with the original module)
-  subroutine build_Hv_sector(isector)
-    integer :: isector
+  !> ED_HAMILTONIAN.f90:39-143, same signature: the optional Hmat (caller ED_DIAG.f90:199, LAPACK branch) is the
+  !> dense matrix of the sector, assembled on the device (ED_HAMILTONIAN_SPARSE_HxV.f90:112-148)
+  subroutine build_Hv_sector(isector, Hmat)
+    integer                            :: isector
+    complex(8), dimension(:,:), optional :: Hmat
     integer(c_int64_t) :: nloc
+#ifdef _MPI
+    character(kind=c_char) :: mine(128)
+    character(kind=c_char), allocatable :: all(:)
+    integer :: ierr
+#endif
     call push_model()      ! the reference re-reads the bath on every direct H*v (:59-69); once per sector here
     call check(c_build(int(isector, c_int32_t), merge(1_c_int32_t, 0_c_int32_t, ed_sparse_H), nloc), "build_Hv_sector")
+#ifdef _MPI
+    if (MpiStatus .and. MpiSize > 1) then   ! CUDA-IPC windows for the copy-engine exchange (collective)
+       allocate(all(128*MpiSize))
+       call check(c_ipc_export(mine), "ipc_export")
+       call MPI_Allgather(mine, 128, MPI_CHARACTER, all, 128, MPI_CHARACTER, MpiComm_Global, ierr)
+       call check(c_ipc_import(all, int(MpiSize, c_int32_t)), "ipc_import")
+       deallocate(all)
+    end if
+#endif
+    if (present(Hmat)) call check(c_build_hmat(Hmat), "build_Hv_sector(Hmat)")
     spHtimesV_p => b200_HxV
   end subroutine build_Hv_sector
 
@@ -201,13 +247,25 @@ contains
     spHtimesV_p => null()
   end subroutine delete_Hv_sector
 
-  !> ED_HAMILTONIAN.f90:197-221
+  !> ED_HAMILTONIAN.f90:197-221.  The reference's interface is default integer: sectors whose local dimension
+  !> does not fit (Ns = 18 on fewer than 2 ranks) stop here instead of wrapping around (ED_SETUP.f90:321 would).
   function vecDim_Hv_sector(isector) result(vecDim)
     integer :: isector, vecDim
     integer(c_int64_t) :: n
     call check(c_vecdim(int(isector, c_int32_t), n), "vecDim_Hv_sector")
+    if (n > int(huge(vecDim), c_int64_t)) stop "vecDim_Hv_sector: local dimension exceeds default integer; use more ranks"
     vecDim = int(n)
   end function vecDim_Hv_sector
+
+  !> scatter_vector_MPI / gather_vector_MPI (ED_SETUP.f90:575-668) for the active sector, root = master
+  subroutine b200_scatter_vector(v, vloc)
+    complex(8), dimension(:) :: v, vloc
+    call check(c_scatter(v, vloc, 0_c_int32_t), "scatter_vector_MPI")
+  end subroutine b200_scatter_vector
+  subroutine b200_gather_vector(vloc, v)
+    complex(8), dimension(:) :: vloc, v
+    call check(c_gather(vloc, v, 0_c_int32_t), "gather_vector_MPI")
+  end subroutine b200_gather_vector
 
   !> conforms to cc_sparse_HxV (ED_VARS_GLOBAL.f90:72-78): host arrays in, host arrays out
   subroutine b200_HxV(Nloc, v, Hv)
@@ -247,73 +305,14 @@ contains
   end subroutine b200_lanc_tridiag
 
   !> replaces the master-only O(Dim) loop of lanc_observables (ED_OBSERVABLES.f90:120-192): the device reduces
-  !> gs_weight = |state_cvec|^2 onto the impurity configurations (mu,md) of the up / dw Fock states; the caller
-  !> then runs the reference's own accumulation lines over the 4**Nimp table instead of over Dim states:
-  !>   do md=0,2**Nimp-1; do mu=0,2**Nimp-1; gs_weight=peso*W(mu,md); IbUp=Bdecomp(mu,Nimp); IbDw=Bdecomp(md,Nimp); ...
+  !> gs_weight = |state_cvec|^2 onto the impurity configurations (mu,md) of the up / dw Fock states and hands the
+  !> 4**Nimp table back.  The accumulation formulas stay where they are, in ED_OBSERVABLES: its state loop runs over
+  !> (mu,md) with gs_weight = peso*W(mu,md) instead of over the Dim basis states (INTEGRATION.md shows the edit).
   !> vec = the local shard of an eigenvector of the ACTIVE sector (build_Hv_sector(isector) first).
   subroutine b200_imp_weights(vec, W)
     complex(8), dimension(:) :: vec
     real(8), dimension(0:,0:) :: W   ! (0:2**Nimp-1, 0:2**Nimp-1) = (mu, md)
     call check(c_imp_weights(int(size(vec), c_int64_t), vec, W), "lanc_observables")
   end subroutine b200_imp_weights
-
-  !> The body of the state loop of lanc_observables (ED_OBSERVABLES.f90:120-192) for ONE eigenvector of the active
-  !> sector, with the O(Dim) part on the device: the accumulation lines below are the reference's (:155-186), run
-  !> over the (mu,md) impurity configurations with gs_weight = peso*W(mu,md) instead of over every basis state.
-  !> All arguments are accumulated (+=) like the reference's sum over state_list.
-  subroutine b200_lanc_observables(vec, peso, dens, dens_up, dens_dw, docc, magz, s2tot, sz2, n2)
-    complex(8), dimension(:)                :: vec
-    real(8)                                 :: peso
-    real(8), dimension(Nlat,Norb)           :: dens, dens_up, dens_dw, docc, magz
-    real(8), dimension(Nlat)                :: s2tot
-    real(8), dimension(Nlat,Nlat,Norb,Norb) :: sz2, n2
-    real(8), dimension(Nlat,Norb)           :: nup, ndw, sz, nt
-    real(8), allocatable                    :: W(:,:)
-    real(8)                                 :: gs_weight
-    integer                                 :: mu, md, ilat, jlat, iorb, jorb, nimp, pos
-    nimp = Nlat*Norb
-    allocate(W(0:2**nimp-1, 0:2**nimp-1))
-    call b200_imp_weights(vec, W)
-    do md = 0, 2**nimp-1
-       do mu = 0, 2**nimp-1
-          gs_weight = peso*W(mu,md)
-          if (gs_weight == 0d0) cycle
-          do ilat = 1, Nlat
-             do iorb = 1, Norb
-                pos = iorb + (ilat-1)*Norb - 1          ! imp_state_index(ilat,iorb) - 1 (ED_SETUP.f90:563-568)
-                nup(ilat,iorb) = merge(1d0, 0d0, btest(mu, pos))
-                ndw(ilat,iorb) = merge(1d0, 0d0, btest(md, pos))
-                sz(ilat,iorb)  = (nup(ilat,iorb) - ndw(ilat,iorb))/2d0
-                nt(ilat,iorb)  =  nup(ilat,iorb) + ndw(ilat,iorb)
-             end do
-          end do
-          do ilat = 1, Nlat
-             do iorb = 1, Norb
-                dens(ilat,iorb)    = dens(ilat,iorb)    + nt(ilat,iorb)*gs_weight
-                dens_up(ilat,iorb) = dens_up(ilat,iorb) + nup(ilat,iorb)*gs_weight
-                dens_dw(ilat,iorb) = dens_dw(ilat,iorb) + ndw(ilat,iorb)*gs_weight
-                docc(ilat,iorb)    = docc(ilat,iorb)    + nup(ilat,iorb)*ndw(ilat,iorb)*gs_weight
-                magz(ilat,iorb)    = magz(ilat,iorb)    + (nup(ilat,iorb)-ndw(ilat,iorb))*gs_weight
-             end do
-             s2tot(ilat) = s2tot(ilat) + (sum(sz(ilat,:)))**2*gs_weight
-          end do
-          do ilat = 1, Nlat
-             do iorb = 1, Norb
-                sz2(ilat,ilat,iorb,iorb) = sz2(ilat,ilat,iorb,iorb) + (sz(ilat,iorb)*sz(ilat,iorb))*gs_weight
-                n2(ilat,ilat,iorb,iorb)  = n2(ilat,ilat,iorb,iorb)  + (nt(ilat,iorb)*nt(ilat,iorb))*gs_weight
-                do jlat = 1, Nlat
-                   do jorb = iorb+1, Norb
-                      sz2(ilat,jlat,iorb,jorb) = sz2(ilat,jlat,iorb,jorb) + (sz(ilat,iorb)*sz(jlat,jorb))*gs_weight
-                      sz2(ilat,jlat,jorb,iorb) = sz2(ilat,jlat,jorb,iorb) + (sz(ilat,jorb)*sz(jlat,iorb))*gs_weight
-                      n2(ilat,jlat,iorb,jorb)  = n2(ilat,jlat,iorb,jorb)  + (nt(ilat,iorb)*nt(jlat,jorb))*gs_weight
-                      n2(ilat,jlat,jorb,iorb)  = n2(ilat,jlat,jorb,iorb)  + (nt(ilat,jorb)*nt(jlat,iorb))*gs_weight
-                   end do
-                end do
-             end do
-          end do
-       end do
-    end do
-    deallocate(W)
-  end subroutine b200_lanc_observables
 
 END MODULE ED_HAMILTONIAN_B200
