@@ -38,6 +38,10 @@ struct Sched {
 // (column, block): the block's rows are staged by TMA, entries whose source lies inside the block follow the
 // block's own edge-coloured schedule (relative indices), the others (hops that change the top bits) are
 // gathered from global memory / L2.  One Sched-like stream set per block, concatenated.
+#ifndef COLBLK_NW
+#define COLBLK_NW 32
+#endif
+constexpr int kColblkWarps = COLBLK_NW;  // (measured: 32 warps with 2 prefetched off-block steps beat 24 / 4 and 20 / 6)
 struct ColBlk {
   int32_t nblk = 0, nwarps = 0, fmt = 0, G = 0;
   int64_t max_rows = 0;
@@ -241,6 +245,7 @@ void free_spin_op(SpinOp &op);
 int cached_map_op(int npart, const SpinOp **out);  // lanczos.cu
 void free_map_ops();
 void lz_free_slots();  // lanczos.cu
+int scatter_gather_dims(void *vfull, void *vloc, int root, bool scatter, int64_t dimup, int64_t dimdw);  // hxv.cu
 int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
 int build_rowtile(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,
                   const std::vector<uint8_t> &code, int fmt, int64_t cap);  // rowtile.cu

@@ -987,23 +987,28 @@ int cdmft_b200_build_hmat(void *hmat) {
 // Ndw shard (shards are contiguous: rank r owns columns [off_r, off_r + q_r) of v(DimUp, DimDw)).  The reference
 // needs them around sp_lanc_tridiag (ED_GF_NORMAL.f90:214) and es_return_cvector (ED_EIGENSPACE.f90:499-569).
 // vfull is significant on the root only; host or device pointers.  Single rank / simulated ranks: plain copies.
-static int shard_bounds(int rank, int64_t *off, int64_t *cnt) {
+static int shard_bounds_of(int64_t dimup, int64_t dimdw, int rank, int64_t *off, int64_t *cnt) {
   Ctx &c = ctx();
+  const int peff = (int)std::min<int64_t>(c.nranks, dimdw);  // ED_HAMILTONIAN.f90:62-90
   *off = *cnt = 0;
-  if (rank >= c.p_eff) return 0;
-  const Split s = split_of(c.dimdw, c.p_eff, rank);
-  *off = s.off * c.dimup;
-  *cnt = s.q * c.dimup;
+  if (rank >= peff) return 0;
+  const Split s = split_of(dimdw, peff, rank);
+  *off = s.off * dimup;
+  *cnt = s.q * dimup;
   return 0;
 }
-static int scatter_gather(void *vfull, void *vloc, int root, bool scatter) {
+}  // extern "C"
+namespace cb {
+// scatter (root's full vector -> shards) / gather of a vector of ANY sector (dimup x dimdw), SPMD or not
+int scatter_gather_dims(void *vfull, void *vloc, int root, bool scatter, int64_t dimup, int64_t dimdw) {
   Ctx &c = ctx();
-  if (!c.hstatus) return fail("%s: Hsector NOT set", scatter ? "scatter_vector" : "gather_vector");
+  const int64_t dim = dimup * dimdw;
+  auto shard_bounds = [&](int rank, int64_t *off, int64_t *cnt) { return shard_bounds_of(dimup, dimdw, rank, off, cnt); };
   const bool spmd = c.spmd && c.nranks > 1;
   if (root < 0 || root >= (spmd ? c.nranks : 1)) return fail("scatter/gather_vector: bad root %d", root);
   if (!spmd) {  // one process holds every shard back to back = the full vector
-    if (vfull == vloc || c.dim == 0) return 0;
-    CB_CUDA(cudaMemcpyAsync(scatter ? vloc : vfull, scatter ? vfull : vloc, (size_t)c.dim * 16, cudaMemcpyDefault, c.stream));
+    if (vfull == vloc || dim == 0) return 0;
+    CB_CUDA(cudaMemcpyAsync(scatter ? vloc : vfull, scatter ? vfull : vloc, (size_t)dim * 16, cudaMemcpyDefault, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
   }
@@ -1018,8 +1023,8 @@ static int scatter_gather(void *vfull, void *vloc, int root, bool scatter) {
     if (me_root) {
       if (full_dev) dfull = (double2 *)vfull;
       else {
-        CB_CHECK(dev_alloc(&dfull, c.dim));
-        if (scatter) CB_CUDA(cudaMemcpyAsync(dfull, vfull, (size_t)c.dim * 16, cudaMemcpyHostToDevice, c.stream));
+        CB_CHECK(dev_alloc(&dfull, dim));
+        if (scatter) CB_CUDA(cudaMemcpyAsync(dfull, vfull, (size_t)dim * 16, cudaMemcpyHostToDevice, c.stream));
       }
     }
     if (mcnt > 0) {
@@ -1040,7 +1045,7 @@ static int scatter_gather(void *vfull, void *vloc, int root, bool scatter) {
       CB_CHECK(nccl_all_to_all(dloc, dfull, cs.data(), os.data(), cr.data(), orr.data()));
     }
     if (scatter && mcnt > 0 && !loc_dev) CB_CUDA(cudaMemcpyAsync(vloc, dloc, (size_t)mcnt * 16, cudaMemcpyDeviceToHost, c.stream));
-    if (!scatter && me_root && !full_dev) CB_CUDA(cudaMemcpyAsync(vfull, dfull, (size_t)c.dim * 16, cudaMemcpyDeviceToHost, c.stream));
+    if (!scatter && me_root && !full_dev) CB_CUDA(cudaMemcpyAsync(vfull, dfull, (size_t)dim * 16, cudaMemcpyDeviceToHost, c.stream));
     CB_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
   };
@@ -1049,13 +1054,19 @@ static int scatter_gather(void *vfull, void *vloc, int root, bool scatter) {
   if (mcnt > 0 && !loc_dev && dloc) cudaFree(dloc);
   return rc;
 }
+}  // namespace cb
+extern "C" {
 int cdmft_b200_scatter_vector(const void *vfull, void *vloc, int32_t root) {
   CB_REQUIRE_INIT();
-  return scatter_gather((void *)vfull, vloc, root, true);
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("scatter_vector: Hsector NOT set");
+  return scatter_gather_dims((void *)vfull, vloc, root, true, c.dimup, c.dimdw);
 }
 int cdmft_b200_gather_vector(const void *vloc, void *vfull, int32_t root) {
   CB_REQUIRE_INIT();
-  return scatter_gather(vfull, (void *)vloc, root, false);
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("gather_vector: Hsector NOT set");
+  return scatter_gather_dims(vfull, (void *)vloc, root, false, c.dimup, c.dimdw);
 }
 
 }  // extern "C"

@@ -313,10 +313,16 @@ __device__ __forceinline__ void colblk_off_apply(T &acc, uint32_t w, T x, const 
   }
 }
 
+#ifndef COLBLK_KP
+#define COLBLK_KP 2
+#endif
+constexpr int kColblkKP = COLBLK_KP;  // off-block steps prefetched per task (the rest, if any, is loaded in place)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(1024, 1) k_colblk(int64_t n, int64_t ncols, const T *__restrict__ v, T *__restrict__ out,
-                                                     ColBlkArgs a, DiagArgs dg) {
+__global__ void __launch_bounds__(kColblkWarps * 32, 1) k_colblk(int64_t n, int64_t ncols, const T *__restrict__ v, T *__restrict__ out,
+                                                                  ColBlkArgs a, DiagArgs dg) {
   constexpr int G = sizeof(T) == 16 ? 8 : 16;
+  constexpr int KP = kColblkKP;
+  constexpr uint32_t NONE = MODE >= 2 ? 0xFFFFFFFFu : 0u;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bar = (uint64_t *)smem_raw;
   double2 *coef = (double2 *)(smem_raw + 128);
@@ -357,51 +363,92 @@ __global__ void __launch_bounds__(1024, 1) k_colblk(int64_t n, int64_t ncols, co
       dtab[mu] = val;
     }
     const int t0 = bd.z + __ldg(a.tbase + b * (a.nwarps + 1) + warp), t1 = bd.z + __ldg(a.tbase + b * (a.nwarps + 1) + warp + 1);
-    const uint4 *wp = (const uint4 *)a.words + ((int64_t)bd.w + __ldg(a.qbase + b * (a.nwarps + 1) + warp)) * 32 + lane;
+    using WQ = typename std::conditional<MODE == 3, uint32_t, uint4>::type;  // one unit of a lane: 2 or 4 steps
+    const WQ *wp = (const WQ *)a.words + ((int64_t)bd.w + __ldg(a.qbase + b * (a.nwarps + 1) + warp)) * 32 + lane;
     const uint4 *mp = a.meta + (int64_t)t0 * 32 + lane;
-    uint4 wa = __ldg(wp), wb = __ldg(wp + 32);
+    WQ wa = __ldg(wp), wb = __ldg(wp + 32);
+    WQ wc = wa, wd = wa;
+    if constexpr (MODE == 3) { wc = __ldg(wp + 64); wd = __ldg(wp + 96); }
     uint4 m = t0 < t1 ? __ldg(mp) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    // Off-block sources (hops that change the top bits) are scattered gathers from the column in global memory / L2.
+    // Nothing of them depends on the staged block, and a load that waits on a load would stall the warp twice: the
+    // operator words of task t+1 are requested during task t, the gathers of task t are issued at its top -- for the
+    // first task while the block is still in flight -- and consumed after its shared-memory loop.
+    uint2 to = t0 < t1 ? __ldg(a.toff + t0) : make_uint2(0u, 0u);
+    uint32_t pw[KP];
+#pragma unroll
+    for (int k = 0; k < KP; k++) pw[k] = k < (int)to.y ? __ldg(a.woff + ((int64_t)to.x + k) * 32 + lane) : NONE;
     mbar_wait(bar, phase);
     phase ^= 1u;
     __syncthreads();
     T *oc = out + c * n + g0;
     for (int t = t0; t < t1; t++) {
       uint4 mnext = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-      if (t + 1 < t1) mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
-      const uint2 to = __ldg(a.toff + t);
+      uint2 tonext = make_uint2(0u, 0u);
+      if (t + 1 < t1) {
+        mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
+        tonext = __ldg(a.toff + t + 1);
+      }
       const int nquad = (int)(m.w >> 16);
       const bool valid = m.z != 0xFFFFFFFFu;
+      const int noff = (int)to.y;
+      T px[KP];
+      uint32_t pc[KP];  // the words of this task (their low bits decode the coefficient)
+#pragma unroll
+      for (int k = 0; k < KP; k++) {
+        pc[k] = pw[k];
+        px[k] = colblk_off_load<T, MODE>(pc[k], vc);
+      }
+#pragma unroll
+      for (int k = 0; k < KP; k++) pw[k] = k < (int)tonext.y ? __ldg(a.woff + ((int64_t)tonext.x + k) * 32 + lane) : NONE;
       T acc;
       colres_zero(acc);
       if (dg.enabled && valid)
         acc = colres_scale(__hiloint2double((int)m.y, (int)m.x) + dtab[m.w & 0xFFFFu], xs[m.z]);
-      {  // off-block sources (hops that change the top bits): scattered gathers from the column in global memory / L2
-        const uint32_t *wo = a.woff + (int64_t)to.x * 32 + lane;
-        const int noff = (int)to.y;
-        int k = 0;
-        for (; k + 2 <= noff; k += 2) {
-          const uint32_t w0 = __ldg(wo + k * 32), w1 = __ldg(wo + k * 32 + 32);
-          const T x0 = colblk_off_load<T, MODE>(w0, vc), x1 = colblk_off_load<T, MODE>(w1, vc);
-          colblk_off_apply<T, MODE>(acc, w0, x0, coef_b, a.m0, a.m1, a.m2, a.m3);
-          colblk_off_apply<T, MODE>(acc, w1, x1, coef_b, a.m0, a.m1, a.m2, a.m3);
+      if constexpr (MODE == 3) {
+        // 16-bit words: one 4-byte load per two steps, four loads in flight (as in k_colres)
+        for (int kq = 0; kq < nquad; kq++) {
+          const uint32_t w = wa;
+          wp += 32;
+          wa = wb; wb = wc; wc = wd;
+          wd = __ldg(wp + 96);
+          colres_step16x2<T>(acc, w, xs_b, a.m0, a.m1);
         }
-        if (k < noff) {
-          const uint32_t w0 = __ldg(wo + k * 32);
-          colblk_off_apply<T, MODE>(acc, w0, colblk_off_load<T, MODE>(w0, vc), coef_b, a.m0, a.m1, a.m2, a.m3);
+      } else {
+        // two operator loads in flight in registers that are never moved (a move would wait for the load it copies)
+        auto quad = [&](const uint4 w) {
+          colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+          colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+        };
+        int kq = 0;
+        for (; kq + 2 <= nquad; kq += 2) {
+          const uint4 w0 = wa;
+          wa = __ldg(wp + 64);
+          quad(w0);
+          const uint4 w1 = wb;
+          wb = __ldg(wp + 96);
+          wp += 64;
+          quad(w1);
+        }
+        if (kq < nquad) {
+          const uint4 w0 = wa;
+          wa = wb;
+          wb = __ldg(wp + 64);
+          wp += 32;
+          quad(w0);
         }
       }
-      for (int kq = 0; kq < nquad; kq++) {
-        const uint4 w = wa;
-        wp += 32;
-        wa = wb;
-        wb = __ldg(wp + 32);
-        colres_step<T, MODE>(acc, w.x, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
-        colres_step<T, MODE>(acc, w.y, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
-        colres_step<T, MODE>(acc, w.z, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
-        colres_step<T, MODE>(acc, w.w, xs_b, coef_b, a.m0, a.m1, a.m2, a.m3);
+#pragma unroll
+      for (int k = 0; k < KP; k++) colblk_off_apply<T, MODE>(acc, pc[k], px[k], coef_b, a.m0, a.m1, a.m2, a.m3);
+      for (int k = KP; k < noff; k++) {  // more off-block steps than prefetch slots
+        const uint32_t w0 = __ldg(a.woff + ((int64_t)to.x + k) * 32 + lane);
+        colblk_off_apply<T, MODE>(acc, w0, colblk_off_load<T, MODE>(w0, vc), coef_b, a.m0, a.m1, a.m2, a.m3);
       }
       if (valid) oc[m.z] = acc;
       m = mnext;
+      to = tonext;
     }
     __syncthreads();  // every gather of this block is done before the next bulk copy lands
   }
@@ -498,13 +545,14 @@ inline int launch_colblk(const SpinOp &s, int64_t ncols, const T *v, T *out, con
   a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1]; a.m2 = s.sc_mag[2]; a.m3 = s.sc_mag[3];
   a.nblk = cb.nblk; a.nwarps = cb.nwarps;
   void (*kern)(int64_t, int64_t, const T *, T *, ColBlkArgs, DiagArgs) =
-      cb.fmt == 3 ? k_colblk<T, 4> : (cb.fmt == 1 ? k_colblk<T, 2> : (c.real_h ? k_colblk<T, 1> : k_colblk<T, 0>));
+      cb.fmt == 3 ? k_colblk<T, 4> : (cb.fmt == 2 ? k_colblk<T, 3> : (cb.fmt == 1 ? k_colblk<T, 2> : (c.real_h ? k_colblk<T, 1> : k_colblk<T, 0>)));
   static std::map<const void *, size_t> max_smem;
   size_t &ms = max_smem[(const void *)kern];
   if (smem > ms) {
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ms = smem;
   }
+  if (cb.nwarps != kColblkWarps) return fail("internal: block-split schedule dealt for %d warps", cb.nwarps);
   const int threads = cb.nwarps * 32;
   const int64_t grid = std::min<int64_t>(ncols * cb.nblk, (int64_t)c.sm_count);
   kern<<<(unsigned)grid, threads, smem, c.stream>>>(s.n, ncols, v, out, a, dg);

@@ -761,8 +761,10 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   if (ispin != 1 && ispin != 2) return fail("apply_op: ispin must be 1 or 2");
   // SPMD: the vector is sharded along Ndw, so a spin-UP operator maps every column onto the same column of the
   // target sector (same DimDw, same split): each rank transforms its own shard, no communication.  Spin-down
-  // operators change the column split; the reference gathers on the master for those (ED_EIGENSPACE.f90:499-569).
-  if (c.spmd && ispin != 1) return fail("apply_op: spin-down operators on a sharded vector are not supported (gather the state first)");
+  // operators change the number of columns and with it the split: the state is gathered on rank 0, transformed
+  // there and scattered with the target sector's split -- the reference's own route (es_return_cvector gathers on
+  // the master, ED_EIGENSPACE.f90:499-569; scatter_vector_MPI before sp_lanc_tridiag, ED_GF_NORMAL.f90:214).
+  const bool spmd_dw = c.spmd && c.nranks > 1 && ispin != 1;
   const int ns = c.ns;
   for (int k = 0; k < nops; k++)  // validate everything before any resource exists
     if (pos[k] < 1 || pos[k] > ns) return fail("apply_op: pos out of range");
@@ -773,6 +775,37 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   int64_t idimup, idimdw, idim, jdimup, jdimdw, jdim;
   CB_CHECK(cdmft_b200_get_sector_dims(isector, &idimup, &idimdw, &idim));
   CB_CHECK(cdmft_b200_get_sector_dims(1 + jnup * (ns + 1) + jndw, &jdimup, &jdimdw, &jdim));
+  if (spmd_dw) {
+    // gather (source sector split) -> full-vector transform on rank 0 -> scatter (target sector split)
+    const bool root = c.rank == 0;
+    double2 *gfull = nullptr, *ofull = nullptr;
+    auto body2 = [&]() -> int {
+      if (root) {
+        CB_CHECK(dev_alloc(&gfull, idim));
+        CB_CHECK(dev_alloc(&ofull, jdim));
+      }
+      CB_CHECK(scatter_gather_dims(gfull, (void *)state, 0, false, idimup, idimdw));
+      if (root) {
+        const SpinOp *src = nullptr, *dst = nullptr;
+        CB_CHECK(cached_map_op(ndw, &src));
+        CB_CHECK(cached_map_op(jndw, &dst));
+        CB_CUDA(cudaMemsetAsync(ofull, 0, jdim * 16, c.stream));
+        for (int k = 0; k < nops; k++) {
+          if (idim == 0) continue;
+          k_apply_op<<<(unsigned)((idim + 255) / 256), 256, 0, c.stream>>>(idim, idimup, jdimup, ispin, iop, pos[k] - 1, src->map, dst->lin_lo,
+                                                                            dst->lin_hi, ns / 2, make_double2(coef[2 * k], coef[2 * k + 1]),
+                                                                            gfull, ofull);
+          c.launches++;
+        }
+      }
+      CB_CHECK(scatter_gather_dims(ofull, out, 0, true, jdimup, jdimdw));
+      return 0;
+    };
+    const int rc2 = body2();
+    if (gfull) cudaFree(gfull);
+    if (ofull) cudaFree(ofull);
+    return rc2;
+  }
   if (c.spmd) {  // local shard: this rank's columns (ED_HAMILTONIAN.f90:92-105 with P_eff = min(P, DimDw))
     const int peff = (int)std::min<int64_t>(c.nranks, idimdw);
     const int64_t q = c.rank < peff ? split_of(idimdw, peff, c.rank).q : 0;

@@ -391,8 +391,16 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
   std::vector<int32_t> tbase, qbase;
   std::vector<uint32_t> meta, words, woff;
   std::vector<uint2> toff;
-  const int nwarps = 32;
-  const bool fastw = fmt == 1 || fmt == 3;  // fmt 2 (16-bit) is not used here
+  const int nwarps = kColblkWarps;
+  const bool fastw = fmt == 1 || fmt == 3;
+  // in-block words: 16 bits (sign | class | row relative to the block) when the two-magnitude decode applies and the
+  // largest block fits 14-bit row numbers -- half the operator traffic of the 32-bit words; the off-block words stay 32 bits
+  int fmt_in = fmt;
+  {
+    int64_t mx = 0;
+    for (int k = 0; k <= t; k++) mx = std::max(mx, binom64(ns - t, op.npart - k));
+    if (fmt == 1 && G == 8 && mx + 32 <= (1 << 14) && !host_out) fmt_in = 2;
+  }
   const uint32_t NONE = fastw ? 0xFFFFFFFFu : 0u;
   std::vector<int32_t> bstart;  // first row of every block + the end
   {
@@ -421,7 +429,7 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
       rp[i + 1] = (int32_t)cl.size();
     }
     SchedHost sh;
-    build_schedule_host(ng, rp, cl, cd, G, fmt, natural, nwarps, f_row ? f_row + g0 : nullptr, mu_row ? mu_row + g0 : nullptr, sh);
+    build_schedule_host(ng, rp, cl, cd, G, fmt_in, natural, nwarps, f_row ? f_row + g0 : nullptr, mu_row ? mu_row + g0 : nullptr, sh);
     blk.push_back(make_int4((int)g0, (int)ng, (int)task0, (int)unit0));
     tbase.insert(tbase.end(), sh.tbase.begin(), sh.tbase.end());
     qbase.insert(qbase.end(), sh.qbase.begin(), sh.qbase.end());
@@ -473,7 +481,7 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
       }
     }
     task0 += sh.ntask;
-    unit0 += (int64_t)(sh.words.size() / (32 * 4));  // fmt 0/1/3: one uint4 per unit and lane (slack included)
+    unit0 += (int64_t)(sh.words.size() / (32 * (fmt_in == 2 ? 1 : 4)));  // one uint4 (uint32 for 16-bit words) per unit and lane, slack included
   }
   if (start != op.n) return fail("internal: column blocks do not cover the sector");
   woff.resize(woff.size() + 64, NONE);
@@ -482,7 +490,7 @@ static int build_colblk(SpinOp &op, ColBlk &cb, int ns, const std::vector<int32_
     host_out->woff = woff; host_out->toff = toff; host_out->nwarps = nwarps; host_out->max_rows = mxrows;
     return 0;
   }
-  cb.nblk = (int32_t)blk.size(); cb.nwarps = nwarps; cb.fmt = fmt; cb.G = G; cb.max_rows = mxrows;
+  cb.nblk = (int32_t)blk.size(); cb.nwarps = nwarps; cb.fmt = fmt_in; cb.G = G; cb.max_rows = mxrows;
   cb.even_blocks = true;
   for (auto &q : blk) cb.even_blocks = cb.even_blocks && !(q.x & 1) && !(q.y & 1);
   CB_CHECK(dev_alloc(&cb.blk, (int64_t)blk.size()));

@@ -170,9 +170,10 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
 /* out = sum_k coef[k] * op(pos[k]) |state>  with op = c^+ (iop=+1) or c (iop=-1) acting on spin
  * ispin (1 = up, 2 = dw) of a vector living in sector `isector`; the result lives in
  * getCDGsector/getCsector(isector) (ED_SETUP.f90:377-418; loops ED_GF_NORMAL.f90:180-194,
- * 244-258, 590-620).  state[dim(isector)], out[dim(jsector)] host or device.  SPMD: spin-up operators (all the
- * reference applies when Nspin=1) act shard by shard -- state / out are the local shards, the Ndw split is the
- * same in both sectors; spin-down operators on a sharded vector return an error (gather first).
+ * 244-258, 590-620).  state[dim(isector)], out[dim(jsector)] host or device.  SPMD: state / out are the local
+ * shards of the two sectors.  Spin-up operators (all the reference applies when Nspin=1) act shard by shard -- the
+ * Ndw split is the same in both sectors; spin-down operators change the split: the state is gathered on rank 0,
+ * transformed there and scattered with the target sector's split (collective; out needs vecDim(jsector) elements).
  * pos is the 1-based orbital position imp_state_index(ilat,iorb); coef complex interleaved. */
 int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nops, const int32_t *pos,
                         const double *coef, const void *state, void *out, int32_t *jsector);

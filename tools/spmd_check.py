@@ -52,7 +52,8 @@ def main():
                 orc = edo.Oracle(mdl)
                 orc.build_hv_sector(isec, edo.SPARSE_MPI if sparse else edo.DIRECT_MPI, world)
                 ref = dict(hv=orc.hxv(v), tri=orc.lanc_tridiag(v, 30), trir=orc.lanc_tridiag(vreal, 30),
-                           cop=edo.apply_op(ns, isec, +1, 1, [1], [1.0 + 0.0j], v), p_eff=orc.active_ranks())
+                           cop=edo.apply_op(ns, isec, +1, 1, [1], [1.0 + 0.0j], v),
+                           copd=edo.apply_op(ns, isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], v), p_eff=orc.active_ranks())
                 orc.delete_hv_sector()
             for mode in SEL:
                 use_ipc, chunks = MODES[mode]
@@ -78,6 +79,10 @@ def main():
                 jsec, cv = E.apply_op(isec, +1, 1, [1], [1.0 + 0.0j], vloc)
                 cparts = [None] * world
                 dist.all_gather_object(cparts, cv if jsec else np.zeros(0, dtype=np.complex128))
+                # c_{2,dw}: a spin-DOWN operator changes the column split (gather -> transform -> scatter inside the library)
+                jsecd, cvd = E.apply_op(isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], vloc)
+                dparts = [None] * world
+                dist.all_gather_object(dparts, cvd if jsecd else np.zeros(0, dtype=np.complex128))
                 # gather on rank 0 (gather_vector_MPI, ED_SETUP.f90:633-668)
                 parts = [None] * world
                 dist.all_gather_object(parts, hv)
@@ -102,6 +107,9 @@ def main():
                     ojsec, ocv = ref["cop"]
                     gotc = np.concatenate([p for p in cparts if p is not None and p.size] or [np.zeros(0, dtype=np.complex128)])
                     okc = (ojsec == jsec) and (ojsec == 0 or (gotc.size == ocv.size and np.abs(gotc - ocv).max() < 1e-14))
+                    ojd, ocd = ref["copd"]
+                    gotd = np.concatenate([p for p in dparts if p is not None and p.size] or [np.zeros(0, dtype=np.complex128)])
+                    okc = okc and (ojd == jsecd) and (ojd == 0 or (gotd.size == ocd.size and np.abs(gotd - ocd).max() < 1e-14))
                     good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == ref["p_eff"] and nd == ond and ndr == ondr and okc
                     ok &= bool(good)
                     print(f"{mdl.name} sector({nup},{ndw}) sparse={sparse} P={world} p_eff={p_eff} dim={dim} backend={mode} "
