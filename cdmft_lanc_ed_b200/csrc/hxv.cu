@@ -246,6 +246,75 @@ __global__ void __launch_bounds__(256) k_copy_block(const double2 *__restrict__ 
   }
 }
 
+// Multi-destination tiled transpose: the rows r (contiguous index of src) are partitioned into up to 16 segments
+// [b[p], b[p+1]) -- one per destination rank -- and every segment has its own destination:
+//   dst_p[(dcol_off_p + c) + (r - b[p]) * ld_p] (=|+=) src[r + c*ld_src]        r in segment p, c in [0, nc)
+// One launch packs every block of a distributed transpose (and writes the own block in place), instead of one
+// small launch per rank: at 8 ranks the product is otherwise bound by the launch rate, not by any kernel.
+constexpr int kMaxSeg = 16;
+struct XposeSeg {
+  double2 *dst;
+  int64_t ld, dcol_off;
+  int32_t accum, pad;
+};
+struct XposeArgs {
+  int64_t b[kMaxSeg + 1];
+  XposeSeg seg[kMaxSeg];
+  int nseg;
+};
+__global__ void __launch_bounds__(256) k_xpose_multi(const double2 *__restrict__ src, int64_t ld_src, int64_t nr, int64_t nc, XposeArgs a) {
+  __shared__ double2 tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int64_t r = r0 + tx, c = c0 + ty + k;
+    if (r < nr && c < nc) tile[ty + k][tx] = src[r + c * ld_src];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int64_t c = c0 + tx, r = r0 + ty + k;
+    if (r < nr && c < nc) {
+      int p = 0;
+      while (p + 1 < a.nseg && r >= a.b[p + 1]) p++;
+      double2 x = tile[tx][ty + k];
+      double2 *d = a.seg[p].dst + (a.seg[p].dcol_off + c) + (r - a.b[p]) * a.seg[p].ld;
+      if (a.seg[p].accum) { const double2 o = *d; x.x += o.x; x.y += o.y; }
+      *d = x;
+    }
+  }
+}
+// Fused unpack of the way back: hv(i, r) += the element sender p packed for it, for every row i outside my own
+// up-range.  The receive window holds, per sender p and chunk ch of its up-rows, a block [i_chunk + r * q_chunk]
+// at q_dw * (up_off(p) + chunk_off).  ub = up-split boundaries (nseg + 1), nch = chunks per sender.
+struct UnpackArgs {
+  int64_t ub[kMaxSeg + 1];
+  int nseg, me, nch_opt;
+};
+__global__ void __launch_bounds__(256) k_unpack_multi(const double2 *__restrict__ recv, double2 *__restrict__ hv, int64_t DU, int64_t qdw,
+                                                      UnpackArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (i >= DU || r >= qdw) return;
+  int p = 0;
+  while (p + 1 < a.nseg && i >= a.ub[p + 1]) p++;
+  if (p == a.me) return;
+  const int64_t uoff = a.ub[p], uq = a.ub[p + 1] - a.ub[p];
+  const int64_t nch = uq < a.nch_opt ? (uq > 1 ? uq : 1) : a.nch_opt;  // = max(1, min(xchg_chunks, uq)) of the sender
+  // split_of(uq, nch, ch): the first (uq mod nch) chunks hold one more row
+  const int64_t q = uq / nch, rem = uq % nch, il = i - uoff;
+  int64_t ch, coff, cq;
+  if (il < rem * (q + 1)) { ch = il / (q + 1); coff = ch * (q + 1); cq = q + 1; }
+  else { ch = rem + (il - rem * (q + 1)) / (q > 0 ? q : 1); coff = ch * q + rem; cq = q; }
+  const double2 x = recv[qdw * (uoff + coff) + (il - coff) + r * cq];
+  double2 *d = hv + i + r * DU;
+  double2 o = *d;
+  o.x += x.x;
+  o.y += x.y;
+  *d = o;
+}
+
 // ------------------------------------------------------------------------------------
 OpArgs op_args(const SpinOp &s) {
   Ctx &c = ctx();
@@ -554,12 +623,21 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
     int64_t so = 0;
     for (int p = 0; p < P; p++) { os[p] = so; so += usplit(p).q * me.dw.q; }
   }
+  if (P > kMaxSeg) return fail("copy-engine exchange: more than %d ranks", kMaxSeg);
   prof_begin(2);
-  for (int k = 0; k < P; k++) {
-    const int p = (me.rank + k) % P;
-    const Split pu = usplit(p);
-    if (p == me.rank) transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.vt, c.dimdw, me.dw.off);
-    else transpose_block<false>(v, DU, pu.off, pu.q, me.dw.q, me.sendbuf + os[p], me.dw.q, 0);
+  if (me.dw.q > 0 && DU > 0) {  // one launch: every destination's block, transposed (the own block straight into vt)
+    XposeArgs xa{};
+    xa.nseg = P;
+    for (int p = 0; p < P; p++) {
+      const Split pu = usplit(p);
+      xa.b[p] = pu.off;
+      xa.b[p + 1] = pu.off + pu.q;
+      if (p == me.rank) xa.seg[p] = XposeSeg{me.vt, c.dimdw, me.dw.off, 0, 0};
+      else xa.seg[p] = XposeSeg{me.sendbuf + os[p], me.dw.q, 0, 0, 0};
+    }
+    dim3 grid((unsigned)((DU + 31) / 32), (unsigned)((me.dw.q + 31) / 32));
+    k_xpose_multi<<<grid, 256, 0, S>>>(v, DU, DU, me.dw.q, xa);
+    c.launches++;
   }
   prof_end();
   CB_CUDA(cudaEventRecord(c.ev_pack, S));
@@ -590,12 +668,19 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
     if (cs.q <= 0) continue;
     CB_CHECK(colpass(c.dw, cs.q, me.vt + cs.off * c.dimdw, me.hvt + cs.off * c.dimdw, nodiag));
     prof_begin(2);
-    for (int k = 0; k < P; k++) {
-      const int p = (me.rank + k) % P;
-      const Split pd = split_of(c.dimdw, P, p);
-      // block: p's columns (rows of hvt) x this chunk of my up-rows, transposed: [iup_chunk + idw_p * cs.q]
-      if (p == me.rank) transpose_block<true>(me.hvt + cs.off * c.dimdw, c.dimdw, pd.off, pd.q, cs.q, hv, DU, me_up.off + cs.off);
-      else transpose_block<false>(me.hvt + cs.off * c.dimdw, c.dimdw, pd.off, pd.q, cs.q, me.sendbuf + ob[p] + pd.q * cs.off, cs.q, 0);
+    {  // one launch: p's columns (rows of hvt) x this chunk of my up-rows, transposed [iup_chunk + idw_p * cs.q]; own block += into hv
+      XposeArgs xa{};
+      xa.nseg = P;
+      for (int p = 0; p < P; p++) {
+        const Split pd = split_of(c.dimdw, P, p);
+        xa.b[p] = pd.off;
+        xa.b[p + 1] = pd.off + pd.q;
+        if (p == me.rank) xa.seg[p] = XposeSeg{hv, DU, me_up.off + cs.off, 1, 0};
+        else xa.seg[p] = XposeSeg{me.sendbuf + ob[p] + pd.q * cs.off, cs.q, 0, 0, 0};
+      }
+      dim3 grid((unsigned)((c.dimdw + 31) / 32), (unsigned)((cs.q + 31) / 32));
+      k_xpose_multi<<<grid, 256, 0, S>>>(me.hvt + cs.off * c.dimdw, c.dimdw, c.dimdw, cs.q, xa);
+      c.launches++;
     }
     prof_end();
     CB_CUDA(cudaEventRecord(c.ev_pack, S));
@@ -615,15 +700,14 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
   CB_CHECK(nccl_barrier());  // every receive window is complete
   prof_end();
   prof_begin(2);
-  for (int p = 0; p < P; p++) {
-    if (p == me.rank) continue;
-    const Split pu = usplit(p);
-    // sender p's block: its up-rows x my columns, chunk by chunk [iup_chunk + idw * cs.q]
-    const int nchp = (int)std::max<int64_t>(1, std::min<int64_t>(c.opt.xchg_chunks, pu.q));
-    for (int ch = 0; ch < nchp; ch++) {
-      const Split cs = split_of(pu.q, nchp, ch);
-      copy_block<true>(me.recvbuf + me.dw.q * (pu.off + cs.off), me.dw.q, cs.q, hv, DU, pu.off + cs.off);
-    }
+  if (me.dw.q > 0 && DU > 0) {  // one launch adds every sender's blocks to Hv
+    UnpackArgs ua{};
+    ua.nseg = P; ua.me = me.rank; ua.nch_opt = (int)std::max<int64_t>(1, c.opt.xchg_chunks);
+    for (int p = 0; p < P; p++) { ua.ub[p] = usplit(p).off; ua.ub[p + 1] = usplit(p).off + usplit(p).q; }
+    if (me.dw.q > 65535) return fail("copy-engine exchange: more than 65535 local columns");
+    dim3 grid((unsigned)((DU + 255) / 256), (unsigned)me.dw.q);
+    k_unpack_multi<<<grid, 256, 0, S>>>(me.recvbuf, hv, DU, me.dw.q, ua);
+    c.launches++;
   }
   prof_end();
   return 0;
