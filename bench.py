@@ -185,7 +185,7 @@ def _config(workload, ngpus, sparse):
 # ---------------------------------------------------------------------------------------------
 SEED = 20261018          # counter-based synthetic vector (cdmft_lanc_ed_b200/synth.py): v(i) depends on the GLOBAL index only
 NVLINK_GBS = 900.0       # NVLink 5 per direction and GPU (B200_PROFILING.md)
-KINDS = {0: "column_pass", 1: "row_pass", 2: "transpose_pack_unpack", 3: "exchange_exposed"}
+KINDS = {0: "column_pass", 1: "row_pass", 2: "transpose_pack_unpack", 3: "exchange_exposed", 6: "exchange_exposed_back", 5: "barrier"}
 
 
 def run_ours(args):
@@ -324,8 +324,9 @@ def run_ours(args):
         return {"bytes_out_per_gpu_per_hxv": out_bytes, "peak_GBps_per_direction": NVLINK_GBS,
                 "floor_ms": out_bytes / (NVLINK_GBS * 1e9) * 1e3,
                 "frac_of_step": out_bytes / (ms_step * 1e-3) / 1e9 / NVLINK_GBS,
-                "exposed_exchange_ms": (kern.get("exchange_exposed") or {}).get("ms_per_step"),
-                "note": "copy-engine exchange: the DMA copies overlap the column passes; exposed = what the compute stream still waits for (incl. 2 barriers)"}
+                "exposed_exchange_ms": ((kern.get("exchange_exposed") or {}).get("ms_per_step") or 0.0) + ((kern.get("exchange_exposed_back") or {}).get("ms_per_step") or 0.0),
+                "barrier_ms": (kern.get("barrier") or {}).get("ms_per_step"),
+                "note": "copy-engine exchange: the DMA copies overlap the column passes; exposed = what the compute stream still waits for its own outgoing copies; barrier = the two stream-ordered barriers per product, waiting for the slowest rank included"}
 
     def gs_lanczos(sec, niter, tol, fixed=None):
         """sp_lanc_eigh semantics from the constant start vector; warm call reported (the first call allocates)"""

@@ -96,6 +96,7 @@ struct SpinOp {
   int32_t ncoef = 0;
   // column-resident kernels: schedules for 16-byte (sc8) and 8-byte (sc16) vector elements
   Sched sc8, sc16;
+  Sched sc16x2;                  // 8-byte elements, dealt for 32 warps: the two-column kernel k_colres2 (hxv_real.cu)
   ColBlk cb8, cb16;
   RowRes rr;
   bool sc_fast = false;          // real H with <= 2 distinct |coefficients|: sign and class bits instead of table ids
@@ -137,7 +138,9 @@ struct Options {
   int64_t row_slab = 128;       // rows per slab of the row pass (slab x all columns stays in L2)
   int64_t use_ipc = 1;          // SPMD with peer windows (ipc_import): 1 = copy-engine exchange (default), 2 = transposing kernels that
                                 // store into peer memory, 0 = NCCL send/recv
-  int64_t xchg_chunks = 4;      // copy-engine exchange: chunks of the Hdw pass pipelined against the way back
+  int64_t colres_pair = 1;      // real Krylov vectors: two columns per pass of the column-resident kernel (k_colres2)
+  int64_t xchg_split = 1;       // copy-engine exchange: DMA streams per peer (each copy cut into this many pieces)
+  int64_t xchg_chunks = 0;      // copy-engine exchange: chunks of the Hdw pass pipelined against the way back (0 = auto: 4 with one peer, 2 with more)
   int64_t row_rb = 2;           // row chunks per thread in the generic SPARSE row pass (1 = one row per thread)
   int64_t fast4 = 1;            // sign/class/phase decode for purely real-or-imaginary coefficients
   int64_t fuse_dot = 1;         // Krylov drivers: Re<u,Hu> reduced inside the last pass of H x v

@@ -596,6 +596,15 @@ int hxv_device(const double2 *v, double2 *hv) {
 // v / hv: this rank's shard, 16-byte elements (complex, or the paired-row view of a real vector), DU rows.
 // ------------------------------------------------------------------------------------
 int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final);  // hxv_real.cu
+// chunks of the Hdw pass pipelined against the way back.  A peer-to-peer DMA copy carries ~20 us of fixed cost
+// (measured on the B200 box, tools/p2p_bw.py: 8 MB 280 GB/s, 40 MB 566, 83 MB 664, 331 MB 745, 1 GB 772), and
+// copies to different peers do not run faster side by side, so small blocks are expensive: 4 chunks with one
+// peer (K3: 83-MB blocks), 2 with more (K3 at 8 ranks: 20-MB blocks).  Option xchg_chunks > 0 overrides.
+static int64_t xchg_chunks_eff() {
+  Ctx &c = ctx();
+  if (c.opt.xchg_chunks > 0) return c.opt.xchg_chunks;
+  return c.p_eff <= 2 ? 4 : 2;
+}
 static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU) {
   Ctx &c = ctx();
   RankState &me = c.rk[0];
@@ -603,10 +612,11 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
   auto usplit = [&](int p) { return split_of(DU, P, p); };
   const Split me_up = usplit(me.rank);
   cudaStream_t S = c.stream;
-  if ((int)c.peer_stream.size() < P) {
+  const int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(c.opt.xchg_split, 4));  // DMA streams per peer
+  if ((int)c.peer_stream.size() < P * nsplit) {
     int lo = 0, hi = 0;
     CB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    while ((int)c.peer_stream.size() < P) {
+    while ((int)c.peer_stream.size() < P * nsplit) {
       cudaStream_t st;
       cudaEvent_t ev;
       CB_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
@@ -614,7 +624,7 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
       c.peer_stream.push_back(st);
       c.peer_done.push_back(ev);
     }
-    CB_CUDA(cudaEventCreateWithFlags(&c.ev_pack, cudaEventDisableTiming));
+    if (!c.ev_pack) CB_CUDA(cudaEventCreateWithFlags(&c.ev_pack, cudaEventDisableTiming));
   }
   DiagArgs nodiag{};
   // ---- way out: pack (transposing), DMA into the owners' vt, diag + Hup meanwhile
@@ -645,19 +655,28 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
     const int p = (me.rank + k) % P;  // staggered: at step k every rank targets a different GPU
     const Split pu = usplit(p);
     if (pu.q <= 0 || me.dw.q <= 0) continue;
-    CB_CUDA(cudaStreamWaitEvent(c.peer_stream[p], c.ev_pack, 0));
-    CB_CUDA(cudaMemcpy2DAsync(c.peer_vt[p] + me.dw.off, (size_t)c.dimdw * 16, me.sendbuf + os[p], (size_t)me.dw.q * 16,
-                              (size_t)me.dw.q * 16, (size_t)pu.q, cudaMemcpyDeviceToDevice, c.peer_stream[p]));
-    CB_CUDA(cudaEventRecord(c.peer_done[p], c.peer_stream[p]));
+    for (int j = 0; j < nsplit; j++) {  // rows [r.off, r.off + r.q) of the block on stream j of this peer
+      const Split r = split_of(pu.q, nsplit, j);
+      if (r.q <= 0) continue;
+      cudaStream_t st = c.peer_stream[p * nsplit + j];
+      CB_CUDA(cudaStreamWaitEvent(st, c.ev_pack, 0));
+      CB_CUDA(cudaMemcpy2DAsync(c.peer_vt[p] + me.dw.off + r.off * c.dimdw, (size_t)c.dimdw * 16, me.sendbuf + os[p] + r.off * me.dw.q,
+                                (size_t)me.dw.q * 16, (size_t)me.dw.q * 16, (size_t)r.q, cudaMemcpyDeviceToDevice, st));
+      CB_CUDA(cudaEventRecord(c.peer_done[p * nsplit + j], st));
+    }
   }
   if (pairs) CB_CHECK(colpass_real(c.up, me.dw.q, (const double *)v, (double *)hv, diag_args(me.dw.off), false, false));
   else CB_CHECK(colpass(c.up, me.dw.q, v, hv, diag_args(me.dw.off)));
-  prof_begin(3);  // what is left of the exchange after the overlap + the barrier
-  for (int k = 1; k < P; k++) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[(me.rank + k) % P], 0));
-  CB_CHECK(nccl_barrier());  // all blocks of every vt have landed
+  prof_begin(3);  // what is left of my outgoing DMA copies (way out) after the overlap with the column pass
+  for (int k = 1; k < P; k++)
+    for (int j = 0; j < nsplit; j++)
+      if (split_of(usplit((me.rank + k) % P).q, nsplit, j).q > 0) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[((me.rank + k) % P) * nsplit + j], 0));
+  prof_end();
+  prof_begin(5);  // barrier: all blocks of every vt have landed (includes waiting for the slowest rank)
+  CB_CHECK(nccl_barrier());
   prof_end();
   // ---- Hdw on vt in chunks of my up-rows; way back pipelined behind the chunks
-  const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(c.opt.xchg_chunks, me_up.q));
+  const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(xchg_chunks_eff(), me_up.q));
   std::vector<int64_t> ob(P, 0);  // receive-window layout of peer p: block of sender s at q_dw(p) * up_off(s)
   {
     int64_t so = 0;
@@ -688,21 +707,31 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
       const int p = (me.rank + k) % P;
       const Split pd = split_of(c.dimdw, P, p);
       if (pd.q <= 0) continue;
-      CB_CUDA(cudaStreamWaitEvent(c.peer_stream[p], c.ev_pack, 0));
       // into p's window: sender block at q_dw(p) * up_off(me), inside it this chunk at q_dw(p) * cs.off
-      CB_CUDA(cudaMemcpyAsync(c.peer_recv[p] + pd.q * (me_up.off + cs.off), me.sendbuf + ob[p] + pd.q * cs.off,
-                              (size_t)pd.q * cs.q * 16, cudaMemcpyDeviceToDevice, c.peer_stream[p]));
-      if (ch == nch - 1) CB_CUDA(cudaEventRecord(c.peer_done[p], c.peer_stream[p]));
+      const int64_t tot = pd.q * cs.q;
+      for (int j = 0; j < nsplit; j++) {
+        const Split r = split_of(tot, nsplit, j);
+        cudaStream_t st = c.peer_stream[p * nsplit + j];
+        CB_CUDA(cudaStreamWaitEvent(st, c.ev_pack, 0));
+        if (r.q > 0)
+          CB_CUDA(cudaMemcpyAsync(c.peer_recv[p] + pd.q * (me_up.off + cs.off) + r.off, me.sendbuf + ob[p] + pd.q * cs.off + r.off,
+                                  (size_t)r.q * 16, cudaMemcpyDeviceToDevice, st));
+        if (ch == nch - 1) CB_CUDA(cudaEventRecord(c.peer_done[p * nsplit + j], st));
+      }
     }
   }
-  prof_begin(3);
-  for (int k = 1; k < P; k++) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[(me.rank + k) % P], 0));
-  CB_CHECK(nccl_barrier());  // every receive window is complete
+  prof_begin(6);  // what is left of the way back
+  for (int k = 1; k < P; k++)
+    for (int j = 0; j < nsplit; j++)
+      if (split_of(c.dimdw, P, (me.rank + k) % P).q > 0) CB_CUDA(cudaStreamWaitEvent(S, c.peer_done[((me.rank + k) % P) * nsplit + j], 0));
+  prof_end();
+  prof_begin(5);  // every receive window is complete
+  CB_CHECK(nccl_barrier());
   prof_end();
   prof_begin(2);
   if (me.dw.q > 0 && DU > 0) {  // one launch adds every sender's blocks to Hv
     UnpackArgs ua{};
-    ua.nseg = P; ua.me = me.rank; ua.nch_opt = (int)std::max<int64_t>(1, c.opt.xchg_chunks);
+    ua.nseg = P; ua.me = me.rank; ua.nch_opt = (int)std::max<int64_t>(1, xchg_chunks_eff());
     for (int p = 0; p < P; p++) { ua.ub[p] = usplit(p).off; ua.ub[p + 1] = usplit(p).off + usplit(p).q; }
     if (me.dw.q > 65535) return fail("copy-engine exchange: more than 65535 local columns");
     dim3 grid((unsigned)((DU + 255) / 256), (unsigned)me.dw.q);

@@ -98,6 +98,177 @@ __global__ void __launch_bounds__(256) k_rowpass_r(int64_t n /*rows*/, int64_t n
   out[i + c * n] += acc0 + acc1;
 }
 
+// ------------------------------------------------------------------------------------
+// Column-resident pass on TWO real columns at a time (real Krylov vectors, fast decodes).  The one-column kernel
+// k_colres<double> is bound by instruction issue, not by shared-memory bandwidth: every 8-byte gather carries the
+// whole decode of its operator word.  Two columns (c, c+1) resident side by side -- exactly the footprint of one
+// complex column -- share the decode, the operator stream and the metadata: per step one word, two LDS.64 at the
+// same offset of the two planes, two FMAs.  Same edge-coloured schedule (G = 16), dealt for 32 warps.
+// ------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_colres2(int64_t n, int64_t ncols, const double *__restrict__ v, double *__restrict__ out,
+                                                      ColResArgs a, DiagArgs dg) {
+  constexpr int G = 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [0,8) mbarrier | two diagonal tables [2^nimp doubles each] | plane 0 | plane 1 (column + G zero elements each)
+  uint64_t *bar = (uint64_t *)smem_raw;
+  const int ndt = dg.enabled ? (1 << dg.nimp) : 0;
+  double *dtab0 = (double *)(smem_raw + 128);
+  double *dtab1 = dtab0 + ndt;
+  const int64_t npad = (n + G - 1) / G * G;
+  const uint32_t pstride = (uint32_t)((npad + G) * 8);  // bytes between the planes
+  double *xs0 = (double *)(smem_raw + 128 + (((size_t)ndt * 16 + 127) & ~(size_t)127));
+  double *xs1 = (double *)((char *)xs0 + pstride);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  for (int64_t k = n + threadIdx.x; k < npad + G; k += blockDim.x) { xs0[k] = 0.0; xs1[k] = 0.0; }  // idle lanes gather these
+  const int t0 = __ldg(a.tbase + warp), t1 = __ldg(a.tbase + warp + 1);
+  const int64_t q0 = __ldg(a.qbase + warp);
+  const uint4 *mp = a.meta + (int64_t)t0 * 32 + lane;
+  using WQ = typename std::conditional<MODE == 3, uint32_t, uint4>::type;
+  const WQ *wbase = (const WQ *)a.words + q0 * 32 + lane;
+  __syncthreads();
+  const uint32_t bytes = (uint32_t)(n * 8);
+  const char *xs_b = (const char *)xs0;
+  uint32_t phase = 0;
+  double dsum = 0.0;
+  const int64_t npairs = (ncols + 1) / 2;
+  auto step = [&](double &acc0, double &acc1, uint32_t off, double h) {
+    acc0 = fma(h, *(const double *)(xs_b + off), acc0);
+    acc1 = fma(h, *(const double *)(xs_b + off + pstride), acc1);
+  };
+  for (int64_t cp = blockIdx.x; cp < npairs; cp += gridDim.x) {
+    const int64_t c0 = 2 * cp;
+    const bool two = c0 + 1 < ncols;
+    const int64_t c1 = two ? c0 + 1 : c0;  // odd tail: the second plane repeats the column, its results are dropped
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, 2 * bytes);
+      for (int pl = 0; pl < 2; pl++) {
+        const char *src = (const char *)(v + (pl ? c1 : c0) * n);
+        char *dst = (char *)(pl ? xs1 : xs0);
+        for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
+      }
+    }
+    for (int mu = threadIdx.x; mu < 2 * ndt; mu += blockDim.x) {  // diagonal of both columns per impurity configuration of the row
+      const int64_t cg = dg.coloff + (mu < ndt ? c0 : c1);
+      const int m = mu < ndt ? mu : mu - ndt;
+      double val = __ldg(dg.f_col + cg);
+      uint32_t md = (uint32_t)__ldg(dg.map_col + cg) & ((1u << dg.nimp) - 1u);
+      while (md) {
+        const int b = __ffs(md) - 1;
+        md &= md - 1;
+        val += __ldg(dg.cross_tab + ((int64_t)b << dg.nimp) + m);
+      }
+      dtab0[mu] = val;  // dtab1 = dtab0 + ndt
+    }
+    const WQ *wp = wbase;
+    WQ wa = __ldg(wp), wb = __ldg(wp + 32);
+    WQ wc = wa, wd = wa;
+    if constexpr (MODE == 3) { wc = __ldg(wp + 64); wd = __ldg(wp + 96); }
+    uint4 m = t0 < t1 ? __ldg(mp) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    __syncthreads();
+    double *o0 = out + c0 * n, *o1 = out + c1 * n;
+    for (int t = t0; t < t1; t++) {
+      uint4 mnext = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+      if (t + 1 < t1) mnext = __ldg(mp + (int64_t)(t + 1 - t0) * 32);
+      const int nquad = (int)(m.w >> 16);
+      const bool valid = m.z != 0xFFFFFFFFu;
+      double acc0 = 0.0, acc1 = 0.0, y0 = 0.0, y1 = 0.0;
+      if (a.accum && valid) { y0 = o0[m.z]; y1 = o1[m.z]; }  // requested first, needed last
+      if (dg.enabled && valid) {
+        const double fr = __hiloint2double((int)m.y, (int)m.x);
+        acc0 = (fr + dtab0[m.w & 0xFFFFu]) * xs0[m.z];
+        acc1 = (fr + dtab1[m.w & 0xFFFFu]) * xs1[m.z];
+      }
+      for (int kq = 0; kq < nquad; kq++) {
+        const WQ w = wa;
+        wp += 32;
+        if constexpr (MODE == 3) {
+          // two 16-bit words (negative << 15 | class << 14 | source row) per register
+          wa = wb; wb = wc; wc = wd;
+          wd = __ldg(wp + 96);
+          step(acc0, acc1, (w << 3) & 0x1FFF8u, colres_signed((w & 0x4000u) ? a.m1 : a.m0, (w << 16) & 0x80000000u));
+          step(acc0, acc1, (w >> 13) & 0x1FFF8u, colres_signed((w & 0x40000000u) ? a.m1 : a.m0, w & 0x80000000u));
+        } else {
+          // 32-bit words: negative << 31 | byte offset | class
+          wa = wb;
+          wb = __ldg(wp + 32);
+          step(acc0, acc1, w.x & 0x7FFFFFF8u, colres_signed((w.x & 1u) ? a.m1 : a.m0, w.x & 0x80000000u));
+          step(acc0, acc1, w.y & 0x7FFFFFF8u, colres_signed((w.y & 1u) ? a.m1 : a.m0, w.y & 0x80000000u));
+          step(acc0, acc1, w.z & 0x7FFFFFF8u, colres_signed((w.z & 1u) ? a.m1 : a.m0, w.z & 0x80000000u));
+          step(acc0, acc1, w.w & 0x7FFFFFF8u, colres_signed((w.w & 1u) ? a.m1 : a.m0, w.w & 0x80000000u));
+        }
+      }
+      if (valid) {
+        acc0 += y0;
+        acc1 += y1;
+        o0[m.z] = acc0;
+        if (two) o1[m.z] = acc1;
+        if (a.dot_partial) dsum += xs0[m.z] * acc0 + (two ? xs1[m.z] * acc1 : 0.0);
+      }
+      m = mnext;
+    }
+    __syncthreads();  // every gather of this pair is done before the next bulk copies land
+  }
+  if (a.dot_partial) {  // fixed summation order: lanes -> warps -> CTA, one partial per CTA
+    __shared__ double wsum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+    if (lane == 0) wsum[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += wsum[w];
+      a.dot_partial[blockIdx.x] = tot;
+    }
+  }
+}
+
+static size_t colres2_smem(int64_t n, int nimp_diag) {
+  const size_t ndt = nimp_diag >= 0 ? ((size_t)1 << nimp_diag) : 0;
+  const int64_t npad = (n + 15) / 16 * 16;
+  return 128 + ((ndt * 16 + 127) & ~(size_t)127) + 2 * (size_t)(npad + 16) * 8;
+}
+// kColresNA when the two-column kernel does not apply
+static int launch_colres2(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final) {
+  Ctx &c = ctx();
+  const Sched &sc = s.sc16x2;
+  if (!c.opt.colres_pair || c.opt.colpass_variant != 6 || c.opt.colres_rows > 0) return kColresNA;
+  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0 || (sc.fmt != 1 && sc.fmt != 2)) return kColresNA;
+  if ((s.n & 1) || !c.real_h || ncols < 2) return kColresNA;
+  if (dg.enabled && dg.f_row != s.f) return kColresNA;
+  const size_t smem = colres2_smem(s.n, dg.enabled ? dg.nimp : -1);
+  if (smem > 232448) return kColresNA;
+  ColResArgs a{};
+  a.accum = accum ? 1 : 0;
+  a.tbase = sc.tbase; a.qbase = sc.qbase; a.meta = (const uint4 *)sc.meta; a.words = sc.words;
+  a.m0 = s.sc_mag[0]; a.m1 = s.sc_mag[1];
+  void (*kern)(int64_t, int64_t, const double *, double *, ColResArgs, DiagArgs) = sc.fmt == 2 ? k_colres2<3> : k_colres2<2>;
+  static std::map<const void *, size_t> max_smem;
+  size_t &ms = max_smem[(const void *)kern];
+  if (smem > ms) {
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ms = smem;
+  }
+  if (sc.nwarps != 32) return kColresNA;
+  const int64_t grid = std::min<int64_t>((ncols + 1) / 2, (int64_t)c.sm_count);
+  if (final && c.dot_request) {
+    if (c.dot_cap < grid) {
+      dev_free(c.dot_partial);
+      CB_CHECK(dev_alloc(&c.dot_partial, grid));
+      c.dot_cap = grid;
+    }
+    a.dot_partial = c.dot_partial;
+    c.dot_npartial = grid;
+    c.dot_done = true;
+  }
+  kern<<<(unsigned)grid, 1024, smem, c.stream>>>(s.n, ncols, v, out, a, dg);
+  c.launches++;
+  return 0;
+}
+
 // diag + Hup on a real vector: column-resident kernel when a column fits in shared memory, else the generic one
 int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final) {
   Ctx &c = ctx();
@@ -107,6 +278,7 @@ int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, c
   int rc = kColresNA;
   if (c.opt.colpass_variant == 6) {
     if (c.opt.colres_rows > 0 && !accum) rc = launch_colblk<double>(s, ncols, v, out, dg);
+    if (rc == kColresNA) rc = launch_colres2(s, ncols, v, out, dg, accum, final);
     if (rc == kColresNA) rc = launch_colres<double>(s, ncols, v, out, dg, accum, final);
     if (rc == kColresNA && !accum) rc = launch_colblk<double>(s, ncols, v, out, dg);
   }

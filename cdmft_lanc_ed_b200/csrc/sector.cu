@@ -678,6 +678,10 @@ int build_spin_op(SpinOp &op, int32_t npart, const std::vector<Term> &terms, con
           const int nw = (size_t)op.n * 8 * 2 + 8192 <= 232448 ? 16 : 32;
           build_schedule_host(op.n, hrp, hcol, code, 16, fmt, natural, nw, hf.data(), hmu.data(), sh);
           CB_CHECK(upload_schedule(op.sc16, sh));
+          if ((fmt == 1 || fmt == 2) && !(op.n & 1) && (size_t)(op.n + 32) * 16 + 4096 <= 232448) {  // two columns side by side
+            if (nw != 32) build_schedule_host(op.n, hrp, hcol, code, 16, fmt, natural, 32, hf.data(), hmu.data(), sh);
+            CB_CHECK(upload_schedule(op.sc16x2, sh));
+          }
         }
       }
       // block-split schedules: columns larger than shared memory (or forced small blocks for the tests)
@@ -726,7 +730,7 @@ void free_spin_op(SpinOp &op) {
   for (ColBlk *cb : {&op.cb8, &op.cb16}) {
     dev_free(cb->blk); dev_free(cb->tbase); dev_free(cb->qbase); dev_free(cb->meta); dev_free(cb->words); dev_free(cb->toff); dev_free(cb->woff);
   }
-  for (Sched *sc : {&op.sc8, &op.sc16}) { dev_free(sc->tbase); dev_free(sc->qbase); dev_free(sc->meta); dev_free(sc->words); }
+  for (Sched *sc : {&op.sc8, &op.sc16, &op.sc16x2}) { dev_free(sc->tbase); dev_free(sc->qbase); dev_free(sc->meta); dev_free(sc->words); }
   op = SpinOp();
 }
 

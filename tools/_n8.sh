@@ -1,0 +1,10 @@
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+for o in "xchg_chunks=2" "use_ipc=0"; do
+timeout 200 $TR bench.py --gpus 8 --steps 10 --warmup 3 --no-e2e --no-sub --no-lanczos --opt $o > gpurun_out/r2o_n8_$o.json 2> gpurun_out/r2o_n8_$o.err
+python - <<P
+import json
+for line in open("gpurun_out/r2o_n8_$o.json"):
+    if line.startswith("{"):
+        d=json.loads(line); print("$o", round(d["ms_per_step"],3), d["gpu_launches"], {k:round(v["ms_per_step"],3) for k,v in d["kernels"].items()})
+P
+done
