@@ -138,6 +138,7 @@ struct Options {
   int64_t row_slab = 128;       // rows per slab of the row pass (slab x all columns stays in L2)
   int64_t use_ipc = 1;          // SPMD with peer windows (ipc_import): 1 = copy-engine exchange (default), 2 = transposing kernels that
                                 // store into peer memory, 0 = NCCL send/recv
+  int64_t direct_tables = 1;    // DIRECT mode (ed_sparse_H = F): 1 = per-spin operator tables + the table kernels, 0 = matrix-free kernels
   int64_t colres_pair = 1;      // real Krylov vectors: two columns per pass of the column-resident kernel (k_colres2)
   int64_t xchg_split = 1;       // copy-engine exchange: DMA streams per peer (each copy cut into this many pieces)
   int64_t xchg_chunks = 0;      // copy-engine exchange: chunks of the Hdw pass pipelined against the way back (0 = auto: 4 with one peer, 2 with more)
@@ -181,6 +182,7 @@ struct Ctx {
   // active sector
   bool hstatus = false;
   int32_t hsector = 0, mode = CDMFT_B200_SPARSE;
+  bool tables = true;  // per-spin operator tables (CSR, schedules) exist for the active sector
   int64_t dim = 0, dimup = 0, dimdw = 0;
   int p_eff = 1;  // min(P, DimDw)
   SpinOp up, dw;
@@ -222,6 +224,7 @@ struct Ctx {
 };
 
 Ctx &ctx();
+inline bool use_tables() { return ctx().tables; }
 void prof_begin(int kind);
 void prof_end();
 int fail(const char *fmt, ...);

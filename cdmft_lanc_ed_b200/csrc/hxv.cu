@@ -332,7 +332,7 @@ static int launch_colpass(const SpinOp &s, int64_t ncols, const double2 *v, doub
   dim3 grid((unsigned)((s.n + 255) / 256), (unsigned)((ncols + CB - 1) / CB));
   if (grid.y > 65535) return fail("colpass: too many column groups (%u)", grid.y);
   OpArgs op = op_args(s);
-  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  const bool direct = !use_tables();  // matrix-free kernels
   if (c.real_h) {
     if (direct) k_colpass<true, true, CB><<<grid, 256, 0, c.stream>>>(s.n, ncols, v, out, op, dg);
     else k_colpass<true, false, CB><<<grid, 256, 0, c.stream>>>(s.n, ncols, v, out, op, dg);
@@ -398,7 +398,7 @@ static int rowpass_impl(const SpinOp &s, int64_t nrows, const double2 *v, double
   dim3 grid((unsigned)s.n, (unsigned)((nrows + 255) / 256));
   if (grid.y > 65535) return fail("rowpass: too many row chunks");
   OpArgs op = op_args(s);
-  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  const bool direct = !use_tables();  // matrix-free kernels
   if (!direct && (c.opt.row_rb > 1 || c.opt.row_slab != 256)) {
     // RB row chunks per thread; the slab of rows one grid.y index sweeps (threads*RB rows x all columns) must stay
     // L2-resident: 128 rows x 12870 columns x 16 B = 26 MB at K3 -> threads = row_slab / RB, at most 256

@@ -469,7 +469,7 @@ inline bool colres_applicable(const SpinOp &s, const DiagArgs &dg) {
   Ctx &c = ctx();
   const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
   if (c.opt.colpass_variant != 6 || c.opt.colres_rows > 0) return false;
-  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return false;
+  if (!use_tables() || !sc.words || sc.ntask <= 0) return false;
   if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return false;  // bulk copies need 16-byte aligned columns
   if (colres_smem(s.n, (int)sizeof(T), dg.enabled ? dg.nimp : -1) > 232448) return false;
   if (dg.enabled && dg.f_row != s.f) return false;  // the schedule carries the operator's own row diagonal
@@ -483,7 +483,7 @@ inline int launch_colres(const SpinOp &s, int64_t ncols, const T *v, T *out, con
                          bool final = false) {
   Ctx &c = ctx();
   const Sched &sc = sizeof(T) == 16 ? s.sc8 : s.sc16;
-  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0) return kColresNA;
+  if (!use_tables() || !sc.words || sc.ntask <= 0) return kColresNA;
   if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h)) return kColresNA;  // bulk copies need 16-byte aligned columns
   const size_t smem = colres_smem(s.n, (int)sizeof(T), dg.enabled ? dg.nimp : -1);
   if (smem > 232448) return kColresNA;
@@ -534,7 +534,7 @@ template <typename T>
 inline int launch_colblk(const SpinOp &s, int64_t ncols, const T *v, T *out, const DiagArgs &dg) {
   Ctx &c = ctx();
   const ColBlk &cb = sizeof(T) == 16 ? s.cb8 : s.cb16;
-  if (c.mode != CDMFT_B200_SPARSE || !cb.words || cb.nblk <= 0) return kColresNA;
+  if (!use_tables() || !cb.words || cb.nblk <= 0) return kColresNA;
   if (sizeof(T) == 8 && ((s.n & 1) || !c.real_h || !cb.even_blocks)) return kColresNA;  // 16-byte aligned bulk copies
   if (dg.enabled && dg.f_row != s.f) return kColresNA;
   const size_t smem = colres_smem(cb.max_rows, (int)sizeof(T), dg.enabled ? dg.nimp : -1);

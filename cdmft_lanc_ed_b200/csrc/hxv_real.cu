@@ -236,7 +236,7 @@ static int launch_colres2(const SpinOp &s, int64_t ncols, const double *v, doubl
   Ctx &c = ctx();
   const Sched &sc = s.sc16x2;
   if (!c.opt.colres_pair || c.opt.colpass_variant != 6 || c.opt.colres_rows > 0) return kColresNA;
-  if (c.mode != CDMFT_B200_SPARSE || !sc.words || sc.ntask <= 0 || (sc.fmt != 1 && sc.fmt != 2)) return kColresNA;
+  if (!use_tables() || !sc.words || sc.ntask <= 0 || (sc.fmt != 1 && sc.fmt != 2)) return kColresNA;
   if ((s.n & 1) || !c.real_h || ncols < 2) return kColresNA;
   if (dg.enabled && dg.f_row != s.f) return kColresNA;
   const size_t smem = colres2_smem(s.n, dg.enabled ? dg.nimp : -1);
@@ -273,7 +273,7 @@ static int launch_colres2(const SpinOp &s, int64_t ncols, const double *v, doubl
 int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final) {
   Ctx &c = ctx();
   if (ncols <= 0 || s.n <= 0) return 0;
-  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  const bool direct = !use_tables();  // matrix-free kernels
   prof_begin(0);
   int rc = kColresNA;
   if (c.opt.colpass_variant == 6) {
@@ -303,7 +303,7 @@ int hxv_device_real(const double *v, double *hv) {
   Ctx &c = ctx();
   if (!c.real_h || c.jhflag) return fail("hxv_device_real: not applicable");
   if (c.spmd || c.sim || c.opt.force_sharded) return hxv_sharded_real(v, hv);
-  const bool direct = c.mode == CDMFT_B200_DIRECT;
+  const bool direct = !use_tables();  // matrix-free kernels
   // preferred order (see hxv_local_terms): tile-resident row pass writes hv, column-resident pass accumulates
   if (!direct && !(c.dimup & 1) && rowtile_applicable(c.dw) && colres_applicable<double>(c.up, diag_args(0))) {
     CB_CHECK(rowpass_real_as_pairs(c.dimup, v, hv, false));

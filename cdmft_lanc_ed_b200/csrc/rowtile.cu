@@ -452,7 +452,7 @@ int64_t rowtile_cap() { return ((int64_t)(kRowTileSmemMax - 128 - 2048) / 128 - 
 
 bool rowtile_applicable(const SpinOp &s) {
   Ctx &c = ctx();
-  return c.mode == CDMFT_B200_SPARSE && c.opt.rowpass_variant == 4 && s.rr.win && s.rr.ntask > 0 &&
+  return use_tables() && c.opt.rowpass_variant == 4 && s.rr.win && s.rr.ntask > 0 &&
          rowtile_smem(s.rr.max_block) <= kRowTileSmemMax;
 }
 

@@ -365,6 +365,7 @@ int cdmft_b200_set_option(const char *key, int64_t value) {
   else if (k == "xchg_chunks") c.opt.xchg_chunks = value;
   else if (k == "xchg_split") c.opt.xchg_split = value;
   else if (k == "colres_pair") c.opt.colres_pair = value;
+  else if (k == "direct_tables") c.opt.direct_tables = value;
   else if (k == "force_sharded") c.opt.force_sharded = value;
   else if (k == "col_batch") c.opt.col_batch = value;
   else if (k == "row_slab") c.opt.row_slab = value;

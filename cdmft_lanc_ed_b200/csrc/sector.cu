@@ -843,8 +843,12 @@ int cdmft_b200_build_hv_sector(int32_t isector, int32_t mode, int64_t *nloc) {
   CB_CUDA(cudaSetDevice(c.device));
   c.hsector = isector;
   c.mode = mode;
-  CB_CHECK(build_spin_op(c.up, nup, c.terms_up, c.e_up, c.const0, mode == CDMFT_B200_SPARSE));
-  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, mode == CDMFT_B200_SPARSE));
+  // ed_sparse_H = F (DIRECT): the reference recomputes every hop instead of storing spH0d / spH0nd / spH0ups / spH0dws.
+  // Nothing O(Dim) is ever stored here in either mode; the per-spin operator tables (O(Dim_sigma), < 1 MB at Ns = 16) are
+  // built in DIRECT mode too unless option direct_tables = 0 asks for the matrix-free (on-the-fly bit-hopping) kernels.
+  c.tables = mode == CDMFT_B200_SPARSE || c.opt.direct_tables != 0;
+  CB_CHECK(build_spin_op(c.up, nup, c.terms_up, c.e_up, c.const0, c.tables));
+  CB_CHECK(build_spin_op(c.dw, ndw, c.terms_dw, c.e_dw, 0.0, c.tables));
   c.dimup = c.up.n; c.dimdw = c.dw.n; c.dim = c.dimup * c.dimdw;
   c.p_eff = (int)std::min<int64_t>(c.nranks, c.dimdw);
   c.rk.clear();

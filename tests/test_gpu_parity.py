@@ -100,6 +100,42 @@ def test_hxv_matches_oracle(ed, oracle_lib, name, sparse):
         orc.delete_hv_sector()
 
 
+@pytest.mark.parametrize("name", ["hm2x2_nb2", "bhz2_nb1", "rand_c_L2O2B1_S2", "rand_r_L3O1B1", "rand_kanamori_L2O2B1"])
+def test_direct_mode_matrix_free_kernels(oracle_lib, name):
+    """ed_sparse_H = F with option direct_tables = 0: the matrix-free (on-the-fly bit-hopping) kernels of the DIRECT
+    mode -- every hop recomputed from the Fock states, nothing stored -- on one rank and on simulated ranks, complex
+    and real Krylov vectors, against the oracle's directMatVec restatements.  (By default DIRECT mode builds the
+    per-spin operator tables, O(Dim_sigma) memory, and runs the same kernels as SPARSE mode; the other tests cover that.)"""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    mdl = MODELS[name]()
+    orc = oracle_lib.Oracle(mdl)
+    ns = mdl.ns
+    for P in (1, 3):
+        if P == 1:
+            E.ed_init(0)
+        else:
+            E.ed_init_sim(P, 0)
+        try:
+            E.set_option("direct_tables", 0)
+            E.ed_set_model(mdl)
+            for (nup, ndw) in [(ns // 2, ns // 2), (ns // 2 + 1, ns // 2 - 1), (1, ns - 1)]:
+                isec = models.get_sector(ns, nup, ndw)
+                n = E.build_Hv_sector(isec, False)
+                orc.build_hv_sector(isec, oracle_lib.DIRECT_SERIAL if P == 1 else oracle_lib.DIRECT_MPI, P)
+                v = _rand_vec(n, seed=3 + nup)
+                assert _relerr(E.hxv(v), orc.hxv(v)) < RTOL, (name, P, nup, ndw)
+                if n > 50:
+                    vr = _rand_vec(n, seed=8, real=True)
+                    nd, a, b = E.sp_lanc_tridiag(vr, 12)
+                    ond, oa, ob = orc.lanc_tridiag(vr, 12)
+                    k = min(nd, ond, 8)
+                    assert np.abs(a[:k] - oa[:k]).max() <= 1e-9 * np.abs(oa[:k]).max(), (name, P, nup, ndw)
+                E.delete_Hv_sector()
+                orc.delete_hv_sector()
+        finally:
+            E.ed_finalize()
+
+
 def test_hxv_direct_quirk_bathdiag(ed, oracle_lib):
     """direct/HxV_local.f90:83-84 loops ilat=1..Norb over the bath diagonal; reproduce on request."""
     mdl = models.hm2x2(2)
