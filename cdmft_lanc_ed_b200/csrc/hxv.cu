@@ -598,12 +598,16 @@ int hxv_device(const double2 *v, double2 *hv) {
 int colpass_real(const SpinOp &s, int64_t ncols, const double *v, double *out, const DiagArgs &dg, bool accum, bool final);  // hxv_real.cu
 // chunks of the Hdw pass pipelined against the way back.  A peer-to-peer DMA copy carries ~20 us of fixed cost
 // (measured on the B200 box, tools/p2p_bw.py: 8 MB 280 GB/s, 40 MB 566, 83 MB 664, 331 MB 745, 1 GB 772), and
-// copies to different peers do not run faster side by side, so small blocks are expensive: 4 chunks with one
-// peer (K3: 83-MB blocks), 2 with more (K3 at 8 ranks: 20-MB blocks).  Option xchg_chunks > 0 overrides.
-static int64_t xchg_chunks_eff() {
+// copies to different peers do not run faster side by side, so small blocks are expensive, while large ones leave a
+// long unhidden tail: about 96 MB per copy, between 2 and 6 chunks (K3: 4 chunks at 2 ranks, 2 at 8; K5 at 8 ranks: 6;
+// measured: K3/8 ranks 2.01 | 2.04 | 2.21 ms with 2 | 4 | 8 chunks, K5 32.0 | 30.1 ms with 2 | 4).
+// Option xchg_chunks > 0 overrides.  Every rank computes the same number (it enters the receive-window layout).
+static int64_t xchg_chunks_eff(int64_t DU) {
   Ctx &c = ctx();
   if (c.opt.xchg_chunks > 0) return c.opt.xchg_chunks;
-  return c.p_eff <= 2 ? 4 : 2;
+  const int P = c.p_eff;
+  const int64_t block_bytes = (c.dimdw / P + 1) * (DU / P + 1) * 16;  // one sender -> one receiver, one direction
+  return std::max<int64_t>(2, std::min<int64_t>(6, (block_bytes + (96ll << 20) - 1) / (96ll << 20)));
 }
 static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU) {
   Ctx &c = ctx();
@@ -676,7 +680,7 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
   CB_CHECK(nccl_barrier());
   prof_end();
   // ---- Hdw on vt in chunks of my up-rows; way back pipelined behind the chunks
-  const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(xchg_chunks_eff(), me_up.q));
+  const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(xchg_chunks_eff(DU), me_up.q));
   std::vector<int64_t> ob(P, 0);  // receive-window layout of peer p: block of sender s at q_dw(p) * up_off(s)
   {
     int64_t so = 0;
@@ -731,7 +735,7 @@ static int hxv_sharded_ce(const double2 *v, double2 *hv, bool pairs, int64_t DU)
   prof_begin(2);
   if (me.dw.q > 0 && DU > 0) {  // one launch adds every sender's blocks to Hv
     UnpackArgs ua{};
-    ua.nseg = P; ua.me = me.rank; ua.nch_opt = (int)std::max<int64_t>(1, xchg_chunks_eff());
+    ua.nseg = P; ua.me = me.rank; ua.nch_opt = (int)std::max<int64_t>(1, xchg_chunks_eff(DU));
     for (int p = 0; p < P; p++) { ua.ub[p] = usplit(p).off; ua.ub[p + 1] = usplit(p).off + usplit(p).q; }
     if (me.dw.q > 65535) return fail("copy-engine exchange: more than 65535 local columns");
     dim3 grid((unsigned)((DU + 255) / 256), (unsigned)me.dw.q);
