@@ -186,6 +186,10 @@ struct Ctx {
   int64_t dim = 0, dimup = 0, dimdw = 0;
   int p_eff = 1;  // min(P, DimDw)
   SpinOp up, dw;
+  // impurity-only hopping operators of the active sector (cdmft_b200_imp_kinetic: <E0> of lanc_local_energy); built on
+  // first use, swapped into up / dw for one product with kin_only set
+  SpinOp kin_up, kin_dw;
+  bool kin_built = false, kin_only = false;
   std::map<int, SpinOp *> map_ops;  // map-only SpinOps per particle number (apply_op), valid for the current model
   std::vector<RankState> rk;
   // CUDA-IPC peer windows (SPMD, optional): peers' vt and recvbuf mapped into this process so the

@@ -475,7 +475,7 @@ static void copy_block(const double2 *src, int64_t nr, int64_t nc, double2 *dst,
 DiagArgs diag_args(int64_t coloff) {
   Ctx &c = ctx();
   DiagArgs d{};
-  d.enabled = 1;
+  d.enabled = c.kin_only ? 0 : 1;  // kin_only: the operator is the bare hopping part (cdmft_b200_imp_kinetic)
   d.f_row = c.up.f; d.f_col = c.dw.f;
   d.map_row = c.up.map; d.map_col = c.dw.map;
   d.cross_tab = c.cross_tab;

@@ -842,6 +842,53 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   return rc;
 }
 
+// <vec| K |vec> for K = the impurity block of the hopping part of H (off-diagonal impHloc, both spins): the only piece of
+// lanc_local_energy (ED_OBSERVABLES.f90:246-460) that is not a function of the impurity occupations -- the reference
+// accumulates impHloc(is,js) sg1 sg2 vec(i) conjg(vec(j)) over the hops |j> = c^+_is c_js |i> (:305-345).  One product
+// with the restricted operator through the regular H x v path (any layout: single rank, simulated ranks, SPMD), then
+// a dot product; out = (Re, Im), all-reduced over the ranks.  vec = local shard of a vector of the ACTIVE sector.
+int cdmft_b200_imp_kinetic(int64_t nloc, const void *vec, double out[2]) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("imp_kinetic: Hsector NOT set");
+  if (nloc != local_n()) return fail("imp_kinetic: nloc mismatch");
+  if (!c.kin_built) {
+    auto imp_only = [&](const std::vector<Term> &all) {
+      std::vector<Term> t;
+      for (const Term &x : all)
+        if (x.a < c.nimp && x.b < c.nimp) t.push_back(x);
+      return t;
+    };
+    const std::vector<double> e0(c.ns, 0.0);
+    int rc = build_spin_op(c.kin_up, c.up.npart, imp_only(c.terms_up), e0, 0.0, c.tables);
+    if (rc == 0) rc = build_spin_op(c.kin_dw, c.dw.npart, imp_only(c.terms_dw), e0, 0.0, c.tables);
+    if (rc) { free_spin_op(c.kin_up); free_spin_op(c.kin_dw); return rc; }
+    c.kin_built = true;
+  }
+  CB_CHECK(ensure_stage(std::max<int64_t>(nloc, 1)));
+  const double2 *dv = (const double2 *)vec;
+  if (nloc > 0 && !is_device_ptr(vec)) {
+    CB_CUDA(cudaMemcpyAsync(c.stage_v, vec, (size_t)nloc * 16, cudaMemcpyHostToDevice, c.stream));
+    dv = c.stage_v;
+  }
+  std::swap(c.up, c.kin_up);
+  std::swap(c.dw, c.kin_dw);
+  const bool jh = c.jhflag;
+  c.jhflag = false;
+  c.kin_only = true;
+  int rc = hxv_device(dv, c.stage_hv);
+  c.kin_only = false;
+  c.jhflag = jh;
+  std::swap(c.up, c.kin_up);
+  std::swap(c.dw, c.kin_dw);
+  CB_CHECK(rc);
+  std::complex<double> z;
+  CB_CHECK(dot(nloc, dv, (const double2 *)c.stage_hv, &z));
+  out[0] = z.real();
+  out[1] = z.imag();
+  return 0;
+}
+
 int cdmft_b200_add_to_lanczos_gf_full(const double vnorm2[2], double ei, double egs, int32_t finite_t, double beta, int32_t nlanc,
                                       const double *alanc, const double *blanc, int32_t isign, double zeta, int32_t lmats,
                                       const double *wm, double *gmats, int32_t lreal, const double *wr, double eps, double *greal,

@@ -891,6 +891,7 @@ int cdmft_b200_delete_hv_sector(void) {
     cudaStreamSynchronize(c.stream);
   }
   lz_free_slots();  // Krylov vectors kept by the ground-state driver
+  if (c.kin_built) { free_spin_op(c.kin_up); free_spin_op(c.kin_dw); c.kin_built = false; }
   free_spin_op(c.up);
   free_spin_op(c.dw);
   for (auto &r : c.rk) { dev_free(r.vt); dev_free(r.hvt); dev_free(r.sendbuf); dev_free(r.recvbuf); }

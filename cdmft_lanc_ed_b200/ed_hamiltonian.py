@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
     "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
     "cdmft_b200_colblk_host", "cdmft_b200_add_to_lanczos_gf_full", "cdmft_b200_build_hmat", "cdmft_b200_scatter_vector",
-    "cdmft_b200_gather_vector",
+    "cdmft_b200_gather_vector", "cdmft_b200_imp_kinetic",
 ]
 
 
@@ -550,6 +550,60 @@ def observables_from_weights(W: np.ndarray, nlat: int, norb: int, peso: float = 
         same_orb = np.eye(norb, dtype=bool)[None, None, :, :] & ~np.eye(nlat, dtype=bool)[:, :, None, None]
         out[name] = np.asfortranarray(np.where(same_orb, 0.0, full))
     out["dens"] = out["dens_up"] + out["dens_dw"]
+    return out
+
+
+def imp_kinetic(vec) -> complex:
+    """<vec| K |vec>, K = impurity block of the hopping part of H (both spins); vec lives in the active sector."""
+    n = int(vec.shape[0]) if hasattr(vec, "shape") else len(vec)
+    out = (C.c_double * 2)()
+    _chk(load_library().cdmft_b200_imp_kinetic(C.c_int64(n), _ptr(vec), out))
+    return complex(out[0], out[1])
+
+
+def local_energy_from_weights(W: np.ndarray, model, peso: float = 1.0) -> dict:
+    """The occupation-dependent pieces of lanc_local_energy (ED_OBSERVABLES.f90:246-460) from the impurity-configuration
+    weights W[mu, md], as contractions (N[config, a] = occupation table, a = imp_state_index - 1):
+    Eknot_diag = sum_a impHloc(a,a) n_a, Epot = U n_up n_dw + Ust(...) + (Ust-Jh)(...), Dust, Dund, Ehartree (hfmode;
+    the reference's constant term is 0.25*uloc(is) with the IMPURITY index, ED_OBSERVABLES.f90:392 -- kept)."""
+    nlat, norb, nspin = model.nlat, model.norb, model.nspin
+    nimp = nlat * norb
+    cfg = np.arange(1 << nimp)
+    N = ((cfg[:, None] >> np.arange(nimp)[None, :]) & 1).astype(float)
+    W = peso * np.asarray(W, dtype=float)
+    Wu, Wd = W.sum(axis=1), W.sum(axis=0)
+    nu, nd = N.T @ Wu, N.T @ Wd                       # <n_a,up>, <n_a,dw>
+    UD = N.T @ W @ N                                  # <n_a,up n_b,dw>
+    UU, DD = (N.T * Wu) @ N, (N.T * Wd) @ N           # <n_a,s n_b,s>
+    tot = W.sum()
+    hu = np.array([model.imphloc[a // norb, a // norb, 0, 0, a % norb, a % norb].real for a in range(nimp)])
+    hd = np.array([model.imphloc[a // norb, a // norb, nspin - 1, nspin - 1, a % norb, a % norb].real for a in range(nimp)])
+    u = np.asarray(model.uloc, dtype=float)
+    out = dict(Eknot_diag=float(hu @ nu + hd @ nd), Epot=0.0, Ehartree=0.0, Dust=0.0, Dund=0.0)
+    for il in range(nlat):
+        for io in range(norb):
+            a = io + il * norb
+            out["Epot"] += u[io] * UD[a, a]
+            if model.hfmode:
+                out["Ehartree"] += -0.5 * u[io] * (nu[a] + nd[a]) + 0.25 * (u[a] if a < 5 else 0.0) * tot
+            for jo in range(io + 1, norb):
+                b = jo + il * norb
+                dust = UD[a, b] + UD[b, a]
+                dund = UU[a, b] + DD[a, b]
+                out["Dust"] += dust
+                out["Dund"] += dund
+                out["Epot"] += model.ust * dust + (model.ust - model.jh) * dund
+                if model.hfmode:
+                    nn = nu[a] + nd[a] + nu[b] + nd[b]
+                    out["Ehartree"] += -0.5 * (2 * model.ust - model.jh) * nn + 0.25 * (2 * model.ust - model.jh) * tot
+    return out
+
+
+def lanc_local_energy(vec, model, peso: float = 1.0) -> dict:
+    """lanc_local_energy for one eigenstate of the active sector: {Eknot, Epot (before '+ Ehartree'), Ehartree, Dust, Dund}.
+    O(Dim) work on the device (weight table + one restricted H x v), formulas on the host."""
+    out = local_energy_from_weights(imp_weights(vec, model.nlat * model.norb), model, peso)
+    out["Eknot"] = out.pop("Eknot_diag") + peso * imp_kinetic(vec).real
     return out
 
 

@@ -21,7 +21,7 @@ MODULE ED_HAMILTONIAN_B200
   public :: b200_HxV
   public :: b200_lanc_eigh, b200_lanc_tridiag
   public :: b200_scatter_vector, b200_gather_vector
-  public :: b200_imp_weights
+  public :: b200_imp_weights, b200_imp_kinetic
 
   type, bind(C) :: cdmft_b200_model
      integer(c_int32_t) :: nlat, norb, nspin, nbath
@@ -135,6 +135,13 @@ MODULE ED_HAMILTONIAN_B200
        integer(c_int32_t), value :: nranks
        integer(c_int) :: rc
      end function c_ipc_import
+     function c_imp_kinetic(nloc, vec, ek) bind(C, name="cdmft_b200_imp_kinetic") result(rc)
+       import :: c_int, c_int64_t, c_double, c_double_complex
+       integer(c_int64_t), value :: nloc
+       complex(c_double_complex) :: vec(*)
+       real(c_double) :: ek(2)
+       integer(c_int) :: rc
+     end function c_imp_kinetic
      function c_imp_weights(nloc, vec, w) bind(C, name="cdmft_b200_imp_weights") result(rc)
        import :: c_int, c_int64_t, c_double, c_double_complex
        integer(c_int64_t), value :: nloc
@@ -314,5 +321,14 @@ contains
     real(8), dimension(0:,0:) :: W   ! (0:2**Nimp-1, 0:2**Nimp-1) = (mu, md)
     call check(c_imp_weights(int(size(vec), c_int64_t), vec, W), "lanc_observables")
   end subroutine b200_imp_weights
+
+  !> the hopping part of ed_Eknot in lanc_local_energy (ED_OBSERVABLES.f90:305-345): <vec| K |vec>, K = impurity block of
+  !> the off-diagonal impHloc of both spins; every other piece of that routine is a sum over the table of b200_imp_weights
+  function b200_imp_kinetic(vec) result(ek)
+    complex(8), dimension(:) :: vec
+    real(8) :: ek, tmp(2)
+    call check(c_imp_kinetic(int(size(vec), c_int64_t), vec, tmp), "lanc_local_energy")
+    ek = tmp(1)
+  end function b200_imp_kinetic
 
 END MODULE ED_HAMILTONIAN_B200

@@ -213,6 +213,14 @@ int cdmft_b200_gather_vector(const void *vloc, void *vfull, int32_t root);
  * sharded vectors the tables are all-reduced so every rank receives the full one.  Nimp <= 8. */
 int cdmft_b200_imp_weights(int64_t nloc, const void *vec, double *w);
 
+/* ---- local energy (ED_OBSERVABLES.f90:246-460, lanc_local_energy) --------------------------------------- */
+/* Every piece of the reference's master loop (:290-424) is a weighted sum over the impurity-configuration table of
+ * cdmft_b200_imp_weights (Epot, Ehartree, Dust, Dund and the diagonal part of Eknot) except the hopping part of Eknot,
+ * sum_i impHloc(is,js) sg1 sg2 vec(i) conjg(vec(j)) over |j> = c^+_is c_js |i> (:305-345) = <vec| K |vec> with K the
+ * impurity block of the off-diagonal one-body matrix of both spins.  out = (Re, Im) of that expectation value,
+ * all-reduced over the ranks; vec = local shard (host or device) of a vector of the ACTIVE sector. */
+int cdmft_b200_imp_kinetic(int64_t nloc, const void *vec, double out[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1231,6 +1231,99 @@ int32_t edo_lanc_observables(int32_t ns, int32_t nlat, int32_t norb, int32_t ise
   return 0;
 }
 
+/* ---- lanc_local_energy: energy pieces of one eigenstate (ED_OBSERVABLES.f90:246-460, master loop :290-424) ----
+ * out[0] ed_Eknot   = sum_i gs_weight * impHloc(ilat,ilat) n  +  sum_i impHloc(is,js) sg1 sg2 vec(i) conjg(vec(j)) peso
+ *                     over the impurity hops |j> = c^+_is c_js |i> of both spins (the complex sum lands in a real(8): real part)
+ * out[1] ed_Epot    = Uloc n_up n_dw + Ust (n_up,i n_dw,j + n_up,j n_dw,i) + (Ust-Jh)(n_up,i n_up,j + n_dw,i n_dw,j)   [before "+ Ehartree"]
+ * out[2] ed_Ehartree  (hfmode only) -- including the reference's constant term 0.25d0*uloc(is), indexed by the impurity
+ *                     position `is` instead of the orbital (:392): faithful, uloc has 5 entries (index beyond 5 -> 0 here)
+ * out[3] ed_Dust, out[4] ed_Dund.   All ACCUMULATED (+=).  vec = full sector vector. */
+int32_t edo_lanc_local_energy(const edo_ctx *c, int32_t isector, const edo_c64 *vec, double peso, double *out) {
+  const int ns = c->ns, Nlat = c->m.nlat, Norb = c->m.norb, Nspin = c->m.nspin;
+  int32_t nup_s, ndw_s;
+  edo_get_nup_ndw(ns, isector, &nup_s, &ndw_s);
+  int64_t dimup, dimdw;
+  const int64_t dim = edo_get_dim(ns, isector, &dimup, &dimdw);
+  int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimup), *mapd = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimdw);
+  if (!mapu || !mapd) { free(mapu); free(mapd); FAIL("edo_lanc_local_energy: out of memory"); }
+  edo_build_sector_map(ns, nup_s, mapu);
+  edo_build_sector_map(ns, ndw_s, mapd);
+  const double Ust = c->m.ust, Jh = c->m.jh;
+  double eknot = 0, epot = 0, ehart = 0, dust = 0, dund = 0;
+  for (int64_t i = 0; i < dim; i++) {
+    const int64_t iup = i % dimup, idw = i / dimup;
+    const int32_t mup = mapu[iup], mdw = mapd[idw];
+    const double gs_weight = peso * (creal(vec[i]) * creal(vec[i]) + cimag(vec[i]) * cimag(vec[i]));
+#define NUP(is) ((double)((mup >> ((is) - 1)) & 1))
+#define NDW(is) ((double)((mdw >> ((is) - 1)) & 1))
+    for (int ilat = 1; ilat <= Nlat; ilat++)
+      for (int iorb = 1; iorb <= Norb; iorb++) {
+        const int is = edo_imp_state_index(c, ilat, iorb);
+        eknot += creal(imphloc_at(c, ilat, ilat, 1, 1, iorb, iorb)) * NUP(is) * gs_weight;
+        eknot += creal(imphloc_at(c, ilat, ilat, Nspin, Nspin, iorb, iorb)) * NDW(is) * gs_weight;
+      }
+    for (int ilat = 1; ilat <= Nlat; ilat++)
+      for (int jlat = 1; jlat <= Nlat; jlat++)
+        for (int iorb = 1; iorb <= Norb; iorb++)
+          for (int jorb = 1; jorb <= Norb; jorb++) {
+            const int is = edo_imp_state_index(c, ilat, iorb), js = edo_imp_state_index(c, jlat, jorb);
+            int32_t k1, k2;
+            double sg1, sg2;
+            edo_c64 h = imphloc_at(c, ilat, jlat, 1, 1, iorb, jorb);
+            if (h != 0 && NUP(js) == 1 && NUP(is) == 0) {
+              edo_c(js, mup, &k1, &sg1);
+              edo_cdg(is, k1, &k2, &sg2);
+              const int64_t j = (edo_binary_search(mapu, (int32_t)dimup, k2) - 1) + idw * dimup;
+              eknot += creal(h * sg1 * sg2 * vec[i] * conj(vec[j]) * peso);
+            }
+            h = imphloc_at(c, ilat, jlat, Nspin, Nspin, iorb, jorb);
+            if (h != 0 && NDW(js) == 1 && NDW(is) == 0) {
+              edo_c(js, mdw, &k1, &sg1);
+              edo_cdg(is, k1, &k2, &sg2);
+              const int64_t j = iup + (int64_t)(edo_binary_search(mapd, (int32_t)dimdw, k2) - 1) * dimup;
+              eknot += creal(h * sg1 * sg2 * vec[i] * conj(vec[j]) * peso);
+            }
+          }
+    for (int ilat = 1; ilat <= Nlat; ilat++)
+      for (int iorb = 1; iorb <= Norb; iorb++) {
+        const int is = edo_imp_state_index(c, ilat, iorb);
+        epot += c->m.uloc[iorb - 1] * NUP(is) * NDW(is) * gs_weight;
+      }
+    if (Norb > 1)
+      for (int ilat = 1; ilat <= Nlat; ilat++)
+        for (int iorb = 1; iorb <= Norb; iorb++)
+          for (int jorb = iorb + 1; jorb <= Norb; jorb++) {
+            const int is = edo_imp_state_index(c, ilat, iorb), js = edo_imp_state_index(c, ilat, jorb);
+            epot += Ust * (NUP(is) * NDW(js) + NUP(js) * NDW(is)) * gs_weight;
+            dust += (NUP(is) * NDW(js) + NUP(js) * NDW(is)) * gs_weight;
+            epot += (Ust - Jh) * (NUP(is) * NUP(js) + NDW(is) * NDW(js)) * gs_weight;
+            dund += (NUP(is) * NUP(js) + NDW(is) * NDW(js)) * gs_weight;
+          }
+    if (c->m.hfmode) {
+      for (int ilat = 1; ilat <= Nlat; ilat++)
+        for (int iorb = 1; iorb <= Norb; iorb++) {
+          const int is = edo_imp_state_index(c, ilat, iorb);
+          const double uis = is <= 5 ? c->m.uloc[is - 1] : 0.0; /* the reference indexes uloc with `is` here (:392) */
+          ehart += -0.5 * c->m.uloc[iorb - 1] * (NUP(is) + NDW(is)) * gs_weight + 0.25 * uis * gs_weight;
+        }
+      if (Norb > 1)
+        for (int ilat = 1; ilat <= Nlat; ilat++)
+          for (int iorb = 1; iorb <= Norb; iorb++)
+            for (int jorb = iorb + 1; jorb <= Norb; jorb++) {
+              const int is = edo_imp_state_index(c, ilat, iorb), js = edo_imp_state_index(c, ilat, jorb);
+              const double nn = NUP(is) + NDW(is) + NUP(js) + NDW(js);
+              ehart += -0.5 * Ust * nn * gs_weight + 0.25 * Ust * gs_weight;
+              ehart += -0.5 * (Ust - Jh) * nn * gs_weight + 0.25 * (Ust - Jh) * gs_weight;
+            }
+    }
+#undef NUP
+#undef NDW
+  }
+  free(mapu); free(mapd);
+  out[0] += eknot; out[1] += epot; out[2] += ehart; out[3] += dust; out[4] += dund;
+  return 0;
+}
+
 int32_t edo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -154,6 +154,9 @@ int32_t edo_tridiag_eigh(int32_t n, double *d, double *e /* e[1..n-1] used, e[0]
 int32_t edo_lanc_observables(int32_t ns, int32_t nlat, int32_t norb, int32_t isector, const edo_c64 *vec, double peso,
                              double *dens_up, double *dens_dw, double *docc, double *magz, double *s2tot, double *sz2,
                              double *n2);
+/* lanc_local_energy (ED_OBSERVABLES.f90:246-460): out[5] += {Eknot, Epot (before + Ehartree), Ehartree, Dust, Dund} of one
+ * eigenstate `vec` (full sector vector) with weight peso; see ed_oracle.c for the term-by-term restatement. */
+int32_t edo_lanc_local_energy(const edo_ctx *c, int32_t isector, const edo_c64 *vec, double peso, double *out);
 int32_t edo_apply_op(int32_t ns, int32_t isector, int32_t iop, int32_t ispin, int32_t nops,
                      const int32_t *pos, const edo_c64 *coef, const edo_c64 *state, edo_c64 *out,
                      int32_t *jsector_out);

@@ -261,6 +261,13 @@ class Oracle:
         _chk(self.L.edo_hxv_rows_counter(self.h, C.c_int64(rows.size), _p(rows), C.c_uint64(seed), C.c_double(scale), _p(out)))
         return out
 
+    def lanc_local_energy(self, isector, vec, peso=1.0):
+        """{Eknot, Epot, Ehartree, Dust, Dund} of one eigenstate (ED_OBSERVABLES.f90:246-460); Epot before '+ Ehartree'."""
+        vec = np.ascontiguousarray(vec, dtype=np.complex128)
+        out = np.zeros(5)
+        _chk(self.L.edo_lanc_local_energy(self.h, C.c_int32(isector), _p(vec), C.c_double(peso), _p(out)))
+        return dict(zip(("Eknot", "Epot", "Ehartree", "Dust", "Dund"), out.tolist()))
+
     def get_csr(self, which):
         nnz = self.L.edo_get_csr(self.h, C.c_int32(which), None, None, None)
         if nnz < 0:

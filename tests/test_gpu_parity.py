@@ -537,6 +537,38 @@ def test_local_observables_vs_oracle(ed, oracle_lib):
         ed.delete_Hv_sector()
 
 
+def test_local_energy_vs_oracle(oracle_lib):
+    """lanc_local_energy (ED_OBSERVABLES.f90:246-460): <E0> through one product with the impurity-hopping operator, the
+    occupation-dependent pieces from the weight table; one rank and simulated ranks, SPARSE and DIRECT."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    cases = [(models.hm2x2(1), (4, 4)), (models.bhz2(1, kanamori=True), (4, 3)), (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 4)),
+             (models.random_model(1, 3, 1, seed=14, hfmode=False), (2, 3)), (models.hm2x2(2), (6, 5))]
+    for P in (1, 3):
+        if P == 1:
+            E.ed_init(0)
+        else:
+            E.ed_init_sim(P, 0)
+        try:
+            for mdl, (nup, ndw) in cases:
+                E.ed_set_model(mdl)
+                isec = models.get_sector(mdl.ns, nup, ndw)
+                orc = oracle_lib.Oracle(mdl)
+                for sparse in (True, False):
+                    n = E.build_Hv_sector(isec, sparse)
+                    vec = _rand_vec(n, seed=41)
+                    got = E.lanc_local_energy(vec, mdl, 0.6)
+                    hv = E.hxv(vec)  # the active operator is untouched by the restricted product
+                    ref = orc.lanc_local_energy(isec, vec, 0.6)
+                    for k in ("Eknot", "Epot", "Ehartree", "Dust", "Dund"):
+                        assert abs(got[k] - ref[k]) <= 1e-11 * max(1.0, abs(ref[k])), (mdl.name, P, sparse, k, got[k], ref[k])
+                    orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+                    assert _relerr(hv, orc.hxv(vec)) < RTOL
+                    orc.delete_hv_sector()
+                    E.delete_Hv_sector()
+        finally:
+            E.ed_finalize()
+
+
 @pytest.mark.parametrize("P", [3, 8])
 def test_local_observables_on_sharded_layout(oracle_lib, P):
     from cdmft_lanc_ed_b200 import ed_hamiltonian as E

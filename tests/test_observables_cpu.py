@@ -63,3 +63,25 @@ def test_add_to_lanczos_gf_all_branches_host_logic(oracle_lib):
     E.add_to_lanczos_gf_normal(0.5, -1.0, a, b, 1, 1.0, wm, g1)
     E.add_to_lanczos_gf_normal_full(0.5, -1.0, -1.0, 0, 0.0, a, b, 1, 1.0, wm, g2, np.zeros(0), 0.0, np.zeros(0, dtype=np.complex128))
     assert np.array_equal(g1, g2)
+
+
+def test_local_energy_host_formulas_against_oracle(oracle_lib):
+    """The occupation-dependent pieces of lanc_local_energy as contractions of the impurity-configuration weights
+    (host logic of the product; the weight table is built with numpy here) against the oracle's state loop."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    from cdmft_lanc_ed_b200 import models
+    for mdl, (nup, ndw) in [(models.hm2x2(1), (4, 3)), (models.bhz2(1, kanamori=True), (4, 4)),
+                            (models.random_model(1, 3, 1, seed=14, hfmode=False), (2, 3)), (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 3))]:
+        ns, nimp = mdl.ns, mdl.nlat * mdl.norb
+        isec = models.get_sector(ns, nup, ndw)
+        mu_of = oracle_lib.sector_map(ns, nup) & ((1 << nimp) - 1)
+        md_of = oracle_lib.sector_map(ns, ndw) & ((1 << nimp) - 1)
+        rng = np.random.default_rng(5)
+        vec = rng.normal(size=mu_of.size * md_of.size) + 1j * rng.normal(size=mu_of.size * md_of.size)
+        vec /= np.linalg.norm(vec)
+        W = np.zeros((1 << nimp, 1 << nimp))
+        np.add.at(W, (np.tile(mu_of, md_of.size), np.repeat(md_of, mu_of.size)), np.abs(vec) ** 2)
+        got = E.local_energy_from_weights(W, mdl, 0.3)
+        ref = oracle_lib.Oracle(mdl).lanc_local_energy(isec, vec, 0.3)
+        for k in ("Epot", "Ehartree", "Dust", "Dund"):
+            assert abs(got[k] - ref[k]) < 1e-12 * max(1.0, abs(ref[k])), (mdl.name, k)

@@ -195,3 +195,62 @@ def test_observables_oracle_against_jordan_wigner_operators(oracle_lib):
                         szi, szj = (num[p] - num[ns + p]) / 2.0, (num[q] - num[ns + q]) / 2.0
                         assert abs(ref["sz2"][il, jl, io, jo] - ev(szi @ szj)) < 1e-12
             assert abs(ref["s2tot"][il] - ev(sz_site @ sz_site)) < 1e-12
+
+
+def test_local_energy_oracle_against_jordan_wigner_operators(oracle_lib):
+    """Pins the oracle's lanc_local_energy restatement (ED_OBSERVABLES.f90:246-460): <E0> = <sum impHloc c^+ c> over the
+    impurity block of both spins, the interaction pieces and the Hartree terms from dense Jordan-Wigner operators on the
+    embedded sector vector (complex hoppings, Nspin=2, Norb=2 with Ust/Jh, hfmode on and off)."""
+    from oracle import jw_ed as jw
+    for mdl, (nup, ndw) in [(models.random_model(2, 1, 1, seed=2), (2, 1)), (models.random_model(2, 1, 1, nspin=2, seed=3), (2, 2)),
+                            (models.random_model(1, 2, 1, seed=9, kanamori=True), (2, 2)),
+                            (models.random_model(1, 2, 1, seed=4, hfmode=False), (1, 2))]:
+        ns, nlat, norb, nimp = mdl.ns, mdl.nlat, mdl.norb, mdl.nlat * mdl.norb
+        isec = models.get_sector(ns, nup, ndw)
+        idx = jw.sector_indices(ns, nup, ndw)
+        rng = np.random.default_rng(23)
+        vec = rng.normal(size=len(idx)) + 1j * rng.normal(size=len(idx))
+        vec /= np.linalg.norm(vec)
+        full = np.zeros(1 << (2 * ns), dtype=np.complex128)
+        full[idx] = vec
+        c = jw._ops(2 * ns)
+        cd = [op.T.conj() for op in c]
+        num = [cd[p] @ c[p] for p in range(2 * ns)]
+        ev = lambda A: np.vdot(full, A @ full).real
+        peso = 0.7
+        ref = oracle_lib.Oracle(mdl).lanc_local_energy(isec, vec, peso)
+        # <E0>: the impurity block of the one-body matrices of both spins (diagonal included)
+        K = 0
+        for s, off in ((0, 0), (mdl.nspin - 1, ns)):
+            h = jw.one_body_matrix(mdl, s)
+            for a in range(nimp):
+                for b in range(nimp):
+                    if a == b:
+                        K = K + mdl.imphloc[a // norb, a // norb, s, s, a % norb, a % norb] * num[off + a]
+                    elif h[a, b] != 0:
+                        K = K + h[a, b] * cd[off + a] @ c[off + b]
+        assert abs(ref["Eknot"] - peso * ev(K)) < 1e-12
+        u, ust, jh = mdl.uloc, mdl.ust, mdl.jh
+        V, dust, dund, eh = 0, 0, 0, 0
+        for il in range(nlat):
+            for io in range(norb):
+                p = io + il * norb
+                V = V + u[io] * num[p] @ num[ns + p]
+                if mdl.hfmode:
+                    eh = eh - 0.5 * u[io] * (num[p] + num[ns + p]) + 0.25 * (u[p] if p < 5 else 0.0) * np.eye(1 << (2 * ns))
+                for jo in range(io + 1, norb):
+                    q = jo + il * norb
+                    a_ = num[p] @ num[ns + q] + num[q] @ num[ns + p]
+                    b_ = num[p] @ num[q] + num[ns + p] @ num[ns + q]
+                    V = V + ust * a_ + (ust - jh) * b_
+                    dust, dund = dust + a_, dund + b_
+                    if mdl.hfmode:
+                        nn = num[p] + num[ns + p] + num[q] + num[ns + q]
+                        eh = eh - 0.5 * (2 * ust - jh) * nn + 0.25 * (2 * ust - jh) * np.eye(1 << (2 * ns))
+        assert abs(ref["Epot"] - peso * ev(V)) < 1e-12
+        if norb > 1:
+            assert abs(ref["Dust"] - peso * ev(dust)) < 1e-12 and abs(ref["Dund"] - peso * ev(dund)) < 1e-12
+        if mdl.hfmode:
+            assert abs(ref["Ehartree"] - peso * ev(eh)) < 1e-12
+        else:
+            assert ref["Ehartree"] == 0.0
