@@ -44,7 +44,7 @@ def _clock_sampler_start(path):
          "clocks_event_reasons.sw_power_cap")
     try:
         f = open(path, "w")
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                              stdout=f, stderr=subprocess.DEVNULL)
         return p, f
     except Exception:

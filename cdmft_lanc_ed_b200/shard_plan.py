@@ -61,3 +61,60 @@ def unpack_from_transpose(blocks: list[np.ndarray], nrow: int, ncol: int, P: int
         qc, co = split_of(ncol, P, r)
         B[:, co:co + qc] = blocks[r].reshape(qrow, qc)
     return B.ravel()
+
+
+# --------------------------------------------------------------------------------------------------
+# Way back of the copy-engine exchange (csrc/hxv.cu: hxv_sharded_ce, k_xpose_multi, k_unpack_multi): the Hdw pass runs
+# in `nch` chunks of the sender's up-rows; every (sender, chunk) block is packed transposed [iup_chunk + idw * q_chunk]
+# and lands in the owner's receive window at q_dw(owner) * (up_off(sender) + chunk_off).  The same formulas, in numpy.
+# --------------------------------------------------------------------------------------------------
+def xchg_chunks(dimup_rows: int, dimdw: int, P: int, option: int = 0) -> int:
+    """Chunk count every rank computes (it enters the window layout): about 96 MB per DMA copy, between 2 and 6."""
+    if option > 0:
+        return option
+    block_bytes = (dimdw // P + 1) * (dimup_rows // P + 1) * 16
+    return max(2, min(6, -(-block_bytes // (96 << 20))))
+
+
+def back_pack(hvt_local: np.ndarray, DU: int, dimdw: int, P: int, rank: int, nch_opt: int):
+    """hvt_local: my (Hdw vt) block, layout [idw + iup_local * dimdw] (dimdw x qup).  Returns {(dest, chunk): (window
+    offset in elements, packed block)} for every destination != rank, plus the own block's contribution as a dense
+    (qup, q_dw(rank)) array [iup_local, idw_local]."""
+    qup, uoff = split_of(DU, P, rank)
+    H = hvt_local.reshape(qup, dimdw)  # H[iup_local, idw]
+    nch = max(1, min(nch_opt, qup))
+    out = {}
+    for p in range(P):
+        qd, doff = split_of(dimdw, P, p)
+        if p == rank:
+            continue
+        for ch in range(nch):
+            cq, coff = split_of(qup, nch, ch)
+            if cq == 0 or qd == 0:
+                continue
+            blk = H[coff:coff + cq, doff:doff + qd].T  # [idw_p, iup_chunk] -> flatten: iup_chunk fastest
+            out[(p, ch)] = (qd * (uoff + coff), np.ascontiguousarray(blk).ravel())
+    qd, doff = split_of(dimdw, P, rank)
+    own = H[:, doff:doff + qd]
+    return out, own
+
+
+def back_unpack(window: np.ndarray, hv_local: np.ndarray, DU: int, dimdw: int, P: int, rank: int, nch_opt: int):
+    """k_unpack_multi: hv(i, r) += window element of the sender that owns up-row i (all rows outside my own range)."""
+    qdw, _ = split_of(dimdw, P, rank)
+    HV = hv_local.reshape(qdw, DU)  # HV[r, i]
+    for i in range(DU):
+        p = next(s for s in range(P) if split_of(DU, P, s)[1] <= i < split_of(DU, P, s)[1] + split_of(DU, P, s)[0])
+        if p == rank:
+            continue
+        uq, uoff = split_of(DU, P, p)
+        nch = max(1, min(nch_opt, uq))
+        q, rem = divmod(uq, nch)
+        il = i - uoff
+        if il < rem * (q + 1):
+            ch = il // (q + 1); coff = ch * (q + 1); cq = q + 1
+        else:
+            ch = rem + (il - rem * (q + 1)) // max(q, 1); coff = ch * q + rem; cq = q
+        for r in range(qdw):
+            HV[r, i] += window[qdw * (uoff + coff) + (il - coff) + r * cq]
+    return HV.ravel()

@@ -143,3 +143,66 @@ def test_paired_row_view_of_real_vectors_gloo(world, nrow, ncol):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
+
+
+def _back_worker(rank, world, port, DU, dimdw, nch, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        # the full (Hdw vt) result as a matrix F[iup, idw]; every rank owns the rows of its up-range
+        F = rng.normal(size=(DU, dimdw)) + 1j * rng.normal(size=(DU, dimdw))
+        qup, uoff = sp.split_of(DU, world, rank)
+        qdw, doff = sp.split_of(dimdw, world, rank)
+        hvt_local = np.ascontiguousarray(F[uoff:uoff + qup, :]).ravel()  # [idw + iup_local*dimdw]
+        blocks, own = sp.back_pack(hvt_local, DU, dimdw, world, rank, nch)
+        # my receive window: q_dw(me) * DU elements; peers write their (sender, chunk) blocks at the layout offsets
+        window = np.zeros(qdw * DU, dtype=np.complex128)
+        reqs, bufs = [], {}
+        for p in range(world):
+            if p == rank:
+                continue
+            mine = [(ch, off, b) for (dst, ch), (off, b) in sorted(blocks.items()) if dst == p]
+            uq, _ = sp.split_of(DU, world, p)
+            nchp = max(1, min(nch, uq))
+            for ch in range(nchp):  # what p sends me, chunk by chunk: sizes follow from the plan alone
+                cq, coff = sp.split_of(uq, nchp, ch)
+                if cq == 0 or qdw == 0:
+                    continue
+                t = torch.empty(2 * cq * qdw, dtype=torch.float64)
+                bufs[(p, ch)] = (qdw * (sp.split_of(DU, world, p)[1] + coff), t)
+                reqs.append(dist.irecv(t, p, tag=ch))
+            for ch, off, b in mine:
+                reqs.append(dist.isend(torch.from_numpy(b.view(np.float64).copy()), p, tag=ch))
+        for r_ in reqs:
+            r_.wait()
+        for (p, ch), (off, t) in bufs.items():
+            blk = t.numpy().view(np.complex128)
+            window[off:off + blk.size] = blk
+        hv = np.zeros(qdw * DU, dtype=np.complex128)  # hv(i, r) = [i + r*DU]
+        HV = hv.reshape(qdw, DU)
+        HV[:, uoff:uoff + qup] += own.T  # the own block is added in place by k_xpose_multi
+        hv = sp.back_unpack(window, HV.ravel(), DU, dimdw, world, rank, nch)
+        expect = np.ascontiguousarray(F[:, doff:doff + qdw].T).ravel()  # my columns of the transposed-back result
+        q.put((rank, bool(np.allclose(hv, expect, rtol=0, atol=0))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,DU,dimdw,nch", [(2, 9, 7, 4), (2, 12, 12, 3), (3, 10, 8, 2), (2, 5, 6, 8)])
+def test_copy_engine_exchange_window_layout_gloo(world, DU, dimdw, nch):
+    """The receive-window layout of the copy-engine exchange's way back (sender blocks cut into chunks of the sender's
+    up-rows, csrc/hxv.cu) with the formulas of k_xpose_multi / k_unpack_multi restated in shard_plan.py: the blocks
+    travel over gloo between real processes and the unpacked sum equals the transposed-back matrix, including ragged
+    splits and more chunks than rows."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world * 10 + DU % 7 + nch
+    procs = [ctx.Process(target=_back_worker, args=(r, world, port, DU, dimdw, nch, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
