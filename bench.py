@@ -390,6 +390,14 @@ def run_ours(args):
         gs["hxv_calls"] = "iterations + those recomputed for the eigenvector (0 when every Krylov vector fits in HBM)"
         fx = gs_lanczos(sec, 0, 0.0, fixed=100)
         gs["fixed_100_iterations"] = {"seconds": fx["seconds"], "iterations": fx["iterations"], "e0": fx["e0"]}
+        fx_path = os.path.join(ROOT, "tests", "golden", "k3_gs_oracle.json")  # the CPU oracle's run of the same ground-state problem
+        ofx = _load_json(fx_path) if args.workload == "K3" and args.lanc_tol == 1e-12 else None
+        if ofx:
+            gs["e0_oracle"] = ofx["e0"]
+            gs["abs_e0_minus_oracle"] = abs(gs["e0"] - ofx["e0"])
+            gs["iterations_oracle"] = ofx["iterations"]
+            gs["oracle_seconds"] = ofx["oracle_seconds"]
+            gs["oracle_note"] = f"sp_lanc_eigh restatement on {ofx['oracle_cores']} host cores (tests/golden/make_k3_gs.py; committed fixture, not run here)"
         if not args.no_e2e and world == 1:  # host start vector -> lanczos_gs -> host eigenvector
             hv0 = torch.zeros(nloc, dtype=torch.complex128, pin_memory=True)
             t0 = time.perf_counter()

@@ -111,6 +111,35 @@ def test_fullsize_K3_against_oracle(ed, oracle_lib):
     assert abs(np.vdot(hv, hv).real - np.vdot(ref, ref).real) < 1e-12 * np.vdot(ref, ref).real
 
 
+def test_fullsize_K3_ground_state_against_oracle_fixture(ed):
+    """Ground-state Lanczos of the full K3 sector against the committed run of the CPU oracle
+    (tests/golden/k3_gs_oracle.json, generator tests/golden/make_k3_gs.py): E0 to 1e-10 relative, the same number of
+    iterations, the leading alpha / beta to 1e-10 -- the device run keeps REAL vectors, the oracle complex ones."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "k3_gs_oracle.json")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    fx = json.load(open(path))
+    mdl = models.hm2x2(3)
+    isec = models.get_sector(16, 8, 8)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(isec, True)
+    assert n == fx["dim"]
+    vec = torch.zeros(n, dtype=torch.complex128, device="cuda")
+    e0, nit, al, bl = ed.sp_lanc_eigh(vec, 512, fx["threshold"], fx["ncheck"])
+    torch.cuda.synchronize()
+    ed.delete_Hv_sector()
+    assert abs(e0 - fx["e0"]) <= RTOL * abs(fx["e0"])
+    assert nit == fx["iterations"]
+    k = 20
+    oa, ob = np.array(fx["alanc"][:k]), np.array(fx["blanc"][:k])
+    assert np.abs(al[:k] - oa).max() <= RTOL * np.abs(oa).max()
+    assert np.abs(bl[:k] - ob).max() <= RTOL * np.abs(ob).max()
+    assert abs(float(torch.linalg.vector_norm(vec)) - 1.0) < 1e-12
+    assert abs(float(vec.abs().max()) - fx["vec_abs_max"]) < 1e-8
+
+
 def test_fullsize_K4_against_oracle(ed, oracle_lib):
     """One full K4 (complex BHZ hoppings) H x v against the CPU oracle, SPARSE and DIRECT."""
     import os
