@@ -230,18 +230,18 @@ contains
     integer(c_int64_t) :: nloc
 #ifdef _MPI
     character(kind=c_char) :: mine(128)
-    character(kind=c_char), allocatable :: all(:)
+    character(kind=c_char), allocatable :: allh(:)
     integer :: ierr
 #endif
     call push_model()      ! the reference re-reads the bath on every direct H*v (:59-69); once per sector here
     call check(c_build(int(isector, c_int32_t), merge(1_c_int32_t, 0_c_int32_t, ed_sparse_H), nloc), "build_Hv_sector")
 #ifdef _MPI
     if (MpiStatus .and. MpiSize > 1) then   ! CUDA-IPC windows for the copy-engine exchange (collective)
-       allocate(all(128*MpiSize))
+       allocate(allh(128*MpiSize))
        call check(c_ipc_export(mine), "ipc_export")
-       call MPI_Allgather(mine, 128, MPI_CHARACTER, all, 128, MPI_CHARACTER, MpiComm_Global, ierr)
-       call check(c_ipc_import(all, int(MpiSize, c_int32_t)), "ipc_import")
-       deallocate(all)
+       call MPI_Allgather(mine, 128, MPI_CHARACTER, allh, 128, MPI_CHARACTER, MpiComm_Global, ierr)
+       call check(c_ipc_import(allh, int(MpiSize, c_int32_t)), "ipc_import")
+       deallocate(allh)
     end if
 #endif
     if (present(Hmat)) call check(c_build_hmat(Hmat), "build_Hv_sector(Hmat)")

@@ -68,6 +68,25 @@ inline int64_t build_Hv_sector(int isector, bool ed_sparse_H = true) {
   spHtimesV_p() = b200_HxV;
   return nloc;
 }
+// build_Hv_sector(isector, Hmat): the reference's optional dense matrix (ED_HAMILTONIAN.f90:123-127, caller ED_DIAG.f90:199),
+// column-major [Dim, Dim]
+inline int64_t build_Hv_sector(int isector, std::vector<cplx> &Hmat, bool ed_sparse_H = true) {
+  const int64_t nloc = build_Hv_sector(isector, ed_sparse_H);
+  int64_t du = 0, dd = 0, dim = 0;
+  check(cdmft_b200_get_sector_dims(isector, &du, &dd, &dim), "build_Hv_sector(Hmat)");
+  Hmat.assign((size_t)dim * (size_t)dim, cplx(0.0, 0.0));
+  check(cdmft_b200_build_hmat(Hmat.data()), "build_Hv_sector(Hmat)");
+  return nloc;
+}
+// scatter_vector_MPI / gather_vector_MPI (ED_SETUP.f90:575-668), root = master
+inline void scatter_vector_MPI(const cplx *v, cplx *vloc) { check(cdmft_b200_scatter_vector(v, vloc, 0), "scatter_vector_MPI"); }
+inline void gather_vector_MPI(const cplx *vloc, cplx *v) { check(cdmft_b200_gather_vector(vloc, v, 0), "gather_vector_MPI"); }
+// hopping part of ed_Eknot in lanc_local_energy (ED_OBSERVABLES.f90:305-345)
+inline double imp_kinetic(const std::vector<cplx> &vec) {
+  double out[2] = {0, 0};
+  check(cdmft_b200_imp_kinetic((int64_t)vec.size(), vec.data(), out), "lanc_local_energy");
+  return out[0];
+}
 inline void delete_Hv_sector() {
   check(cdmft_b200_delete_hv_sector(), "delete_Hv_sector");
   spHtimesV_p() = nullptr;

@@ -36,11 +36,32 @@ int main() {
     double e0 = 0;
     int nit = sp_lanc_eigh(e0, gs, 512, 1e-14);
     delete_Hv_sector();
+    // the LAPACK branch of ED_DIAG.f90:199: build_Hv_sector(isector, Hmat) on a small sector; <E0> hopping part
+    const int ismall = get_Sector(2, 3);
+    std::vector<cplx> Hmat;
+    const int64_t ns_ = build_Hv_sector(ismall, Hmat);
+    std::vector<cplx> w(ns_), hw(ns_), sw(ns_), gw(ns_);
+    for (int64_t i = 0; i < ns_; i++) w[i] = cplx(std::cos(0.23 * (i + 1)), std::sin(0.31 * (i + 1)));
+    spHtimesV_p()((int)ns_, w.data(), hw.data());
+    double hdiff = 0, htrace = 0;
+    for (int64_t i = 0; i < ns_; i++) {
+      cplx acc(0, 0);
+      for (int64_t j = 0; j < ns_; j++) acc += Hmat[i + j * ns_] * w[j];
+      hdiff = std::fmax(hdiff, std::abs(acc - hw[i]));
+      htrace += Hmat[i + i * ns_].real();
+    }
+    const double ekin = imp_kinetic(w);
+    scatter_vector_MPI(w.data(), sw.data());
+    gather_vector_MPI(sw.data(), gw.data());
+    bool moved = true;
+    for (int64_t i = 0; i < ns_; i++) moved = moved && gw[i] == w[i];
+    delete_Hv_sector();
     bool threw = false;
     try { b200_HxV((int)n, v.data(), hv.data()); } catch (const std::runtime_error &) { threw = true; }
     ed_finalize();
-    std::printf("{\"n\": %lld, \"e0\": %.15e, \"niter\": %d, \"threw_after_delete\": %s, \"hv\": [", (long long)n, e0, nit,
-                threw ? "true" : "false");
+    std::printf("{\"n\": %lld, \"e0\": %.15e, \"niter\": %d, \"threw_after_delete\": %s, \"hmat_n\": %lld, \"hmat_maxdiff\": %.3e, "
+                "\"hmat_trace\": %.15e, \"imp_kinetic\": %.15e, \"scatter_gather_ok\": %s, \"hv\": [",
+                (long long)n, e0, nit, threw ? "true" : "false", (long long)ns_, hdiff, htrace, ekin, moved ? "true" : "false");
     for (int i = 0; i < 8; i++) std::printf("%s[%.17e, %.17e]", i ? ", " : "", hv[i * 601].real(), hv[i * 601].imag());
     std::printf("], \"alanc\": [");
     for (int i = 0; i < 10; i++) std::printf("%s%.17e", i ? ", " : "", a[i]);

@@ -45,3 +45,15 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_lib):
     e0 = orc.lanc_eigh(512, 1e-14)[0]
     assert abs(r["e0"] - e0) < 1e-10 * abs(e0)
     assert r["threw_after_delete"] and r["n"] == 4900
+    # build_Hv_sector(isector, Hmat), imp_kinetic, scatter / gather through the C++ mirror
+    orc.delete_hv_sector()
+    ismall = models.get_sector(8, 2, 3)
+    H = orc.dense_hmat(ismall)
+    assert r["hmat_n"] == H.shape[0] and r["hmat_maxdiff"] < 1e-12 and r["scatter_gather_ok"]
+    assert abs(r["hmat_trace"] - np.trace(H).real) < 1e-10 * max(1.0, abs(np.trace(H).real))
+    j = np.arange(1, H.shape[0] + 1)
+    w = np.cos(0.23 * j) + 1j * np.sin(0.31 * j)
+    en = orc.lanc_local_energy(ismall, w, 1.0)
+    diag_part = sum(mdl.imphloc[a, a, 0, 0, 0, 0].real for a in range(4))  # impHloc has no diagonal in this model
+    assert diag_part == 0.0
+    assert abs(r["imp_kinetic"] - en["Eknot"]) < 1e-10 * max(1.0, abs(en["Eknot"]))
