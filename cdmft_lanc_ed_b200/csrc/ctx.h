@@ -255,6 +255,9 @@ void free_spin_op(SpinOp &op);
 int cached_map_op(int npart, const SpinOp **out);  // lanczos.cu
 void free_map_ops();
 void lz_free_slots();  // lanczos.cu
+int allgather_full(const double2 *v, const double2 **out);  // hxv.cu
+// <v| sum_t h_t c^+_a c_b |v> for hop lists of the two spins, through the regular H x v path with the matrix-free kernels (lanczos.cu)
+int expect_terms(const std::vector<Term> &tu, const std::vector<Term> &td, const double2 *dv_local, double out[2]);
 int scatter_gather_dims(void *vfull, void *vloc, int root, bool scatter, int64_t dimup, int64_t dimdw);  // hxv.cu
 int hxv_device(const double2 *v, double2 *hv);  // local shard(s) on device, stream-ordered
 int build_rowtile(SpinOp &op, int ns, const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col,

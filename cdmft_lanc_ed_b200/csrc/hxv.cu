@@ -544,6 +544,26 @@ __global__ void __launch_bounds__(256) k_nonlocal(int64_t nloc, const double2 *_
 }
 
 static int hxv_local_terms(const double2 *v, double2 *hv, bool pairs);
+// allgather_vector_MPI (ED_SETUP.f90:672-708): every active rank sends its shard to every active rank; *out = the full
+// sector vector on this rank (c.vfull, allocated on first use).  One process (single rank, simulated ranks): v itself.
+int allgather_full(const double2 *v, const double2 **out) {
+  Ctx &c = ctx();
+  *out = v;
+  if (!(c.spmd && c.p_eff > 1) || c.rk.empty()) return 0;
+  if (!c.vfull) CB_CHECK(dev_alloc(&c.vfull, c.dim));
+  std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
+  for (int p = 0; p < c.p_eff; p++) {
+    Split pd = split_of(c.dimdw, c.p_eff, p);
+    cs[p] = c.rk[0].nloc; os[p] = 0;
+    cr[p] = pd.q * c.dimup; orr[p] = pd.off * c.dimup;
+  }
+  prof_begin(3);
+  CB_CHECK(nccl_all_to_all(v, c.vfull, cs.data(), os.data(), cr.data(), orr.data()));
+  prof_end();
+  *out = c.vfull;
+  return 0;
+}
+
 int hxv_device(const double2 *v, double2 *hv) {
   Ctx &c = ctx();
   CB_CHECK(hxv_local_terms(v, hv, false));
@@ -554,19 +574,8 @@ int hxv_device(const double2 *v, double2 *hv) {
   a.lbits = c.ns / 2; a.nlat = c.m.nlat; a.norb = c.m.norb; a.jx = c.m.jx; a.jp = c.m.jp; a.dimup = c.dimup;
   const double2 *vfull = v;
   if (c.spmd && c.p_eff > 1) {
-    // allgather_vector_MPI (ED_SETUP.f90:672-708): every rank sends its shard to every rank
     if (c.rk.empty()) return 0;
-    if (!c.vfull) CB_CHECK(dev_alloc(&c.vfull, c.dim));
-    std::vector<int64_t> cs(c.nranks, 0), os(c.nranks, 0), cr(c.nranks, 0), orr(c.nranks, 0);
-    for (int p = 0; p < c.p_eff; p++) {
-      Split pd = split_of(c.dimdw, c.p_eff, p);
-      cs[p] = c.rk[0].nloc; os[p] = 0;
-      cr[p] = pd.q * c.dimup; orr[p] = pd.off * c.dimup;
-    }
-    prof_begin(3);
-    CB_CHECK(nccl_all_to_all(v, c.vfull, cs.data(), os.data(), cr.data(), orr.data()));
-    prof_end();
-    vfull = c.vfull;
+    CB_CHECK(allgather_full(v, &vfull));
   }
   int64_t off = 0;
   for (auto &r : c.rk) {

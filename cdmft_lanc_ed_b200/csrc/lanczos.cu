@@ -842,6 +842,42 @@ int cdmft_b200_apply_op(int32_t isector, int32_t iop, int32_t ispin, int32_t nop
   return rc;
 }
 
+}  // extern "C"
+namespace cb {
+int expect_terms(const std::vector<Term> &tu, const std::vector<Term> &td, const double2 *dv, double out[2]) {
+  Ctx &c = ctx();
+  const int64_t nloc = local_n();
+  CB_CHECK(ensure_stage(std::max<int64_t>(nloc, 1)));
+  SpinOp ku, kd;
+  const std::vector<double> e0(c.ns, 0.0);
+  int rc = build_spin_op(ku, c.up.npart, tu, e0, 0.0, false);
+  if (rc == 0) rc = build_spin_op(kd, c.dw.npart, td, e0, 0.0, false);
+  if (rc == 0) {
+    std::swap(c.up, ku);
+    std::swap(c.dw, kd);
+    const bool jh = c.jhflag, tb = c.tables;
+    c.jhflag = false;
+    c.tables = false;  // one-term operators: the matrix-free kernels, nothing to build
+    c.kin_only = true;
+    rc = hxv_device(dv, c.stage_hv);
+    c.kin_only = false;
+    c.tables = tb;
+    c.jhflag = jh;
+    std::swap(c.up, ku);
+    std::swap(c.dw, kd);
+  }
+  free_spin_op(ku);
+  free_spin_op(kd);
+  CB_CHECK(rc);
+  std::complex<double> z;
+  CB_CHECK(dot(nloc, dv, (const double2 *)c.stage_hv, &z));
+  out[0] = z.real();
+  out[1] = z.imag();
+  return 0;
+}
+}  // namespace cb
+extern "C" {
+
 // <vec| K |vec> for K = the impurity block of the hopping part of H (off-diagonal impHloc, both spins): the only piece of
 // lanc_local_energy (ED_OBSERVABLES.f90:246-460) that is not a function of the impurity occupations -- the reference
 // accumulates impHloc(is,js) sg1 sg2 vec(i) conjg(vec(j)) over the hops |j> = c^+_is c_js |i> (:305-345).  One product

@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_lanczos_tridiag", "cdmft_b200_lanczos_gs", "cdmft_b200_apply_op",
     "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
     "cdmft_b200_colblk_host", "cdmft_b200_add_to_lanczos_gf_full", "cdmft_b200_build_hmat", "cdmft_b200_scatter_vector",
-    "cdmft_b200_gather_vector", "cdmft_b200_imp_kinetic",
+    "cdmft_b200_gather_vector", "cdmft_b200_imp_kinetic", "cdmft_b200_density_matrices",
 ]
 
 
@@ -605,6 +605,17 @@ def lanc_local_energy(vec, model, peso: float = 1.0) -> dict:
     out = local_energy_from_weights(imp_weights(vec, model.nlat * model.norb), model, peso)
     out["Eknot"] = out.pop("Eknot_diag") + peso * imp_kinetic(vec).real
     return out
+
+
+def density_matrix_impurity(vec, nlat: int, norb: int, nspin: int, peso: float = 1.0):
+    """density_matrix_impurity for one eigenstate of the active sector: (cluster_density_matrix [4^Nimp, 4^Nimp],
+    single_particle_density_matrix [Nlat,Nlat,Nspin,Nspin,Norb,Norb]), Fortran-ordered complex128."""
+    n = int(vec.shape[0]) if hasattr(vec, "shape") else len(vec)
+    ni = 1 << (2 * nlat * norb)
+    cdm = np.zeros((ni, ni), dtype=np.complex128, order="F")
+    sp = np.zeros((nlat, nlat, nspin, nspin, norb, norb), dtype=np.complex128, order="F")
+    _chk(load_library().cdmft_b200_density_matrices(C.c_int64(n), _ptr(vec), C.c_double(peso), _ptr(cdm), _ptr(sp)))
+    return cdm, sp
 
 
 def lanc_observables(vec, nlat: int, norb: int, peso: float = 1.0) -> dict:

@@ -21,7 +21,7 @@ MODULE ED_HAMILTONIAN_B200
   public :: b200_HxV
   public :: b200_lanc_eigh, b200_lanc_tridiag
   public :: b200_scatter_vector, b200_gather_vector
-  public :: b200_imp_weights, b200_imp_kinetic
+  public :: b200_imp_weights, b200_imp_kinetic, b200_density_matrices
 
   type, bind(C) :: cdmft_b200_model
      integer(c_int32_t) :: nlat, norb, nspin, nbath
@@ -142,6 +142,13 @@ MODULE ED_HAMILTONIAN_B200
        real(c_double) :: ek(2)
        integer(c_int) :: rc
      end function c_imp_kinetic
+     function c_density_matrices(nloc, vec, peso, cdm, spdm) bind(C, name="cdmft_b200_density_matrices") result(rc)
+       import :: c_int, c_int64_t, c_double, c_double_complex
+       integer(c_int64_t), value :: nloc
+       complex(c_double_complex) :: vec(*), cdm(*), spdm(*)
+       real(c_double), value :: peso
+       integer(c_int) :: rc
+     end function c_density_matrices
      function c_imp_weights(nloc, vec, w) bind(C, name="cdmft_b200_imp_weights") result(rc)
        import :: c_int, c_int64_t, c_double, c_double_complex
        integer(c_int64_t), value :: nloc
@@ -330,5 +337,15 @@ contains
     call check(c_imp_kinetic(int(size(vec), c_int64_t), vec, tmp), "lanc_local_energy")
     ek = tmp(1)
   end function b200_imp_kinetic
+
+  !> the two accumulations of density_matrix_impurity (ED_OBSERVABLES.f90:465-686) for ONE eigenvector of the active
+  !> sector: cluster_density_matrix and single_particle_density_matrix are the module arrays of ED_OBSERVABLES, += peso * ...
+  subroutine b200_density_matrices(vec, peso, cluster_dm, sp_dm)
+    complex(8), dimension(:)           :: vec
+    real(8)                            :: peso
+    complex(8), dimension(:,:)         :: cluster_dm
+    complex(8), dimension(:,:,:,:,:,:) :: sp_dm
+    call check(c_density_matrices(int(size(vec), c_int64_t), vec, peso, cluster_dm, sp_dm), "density_matrix_impurity")
+  end subroutine b200_density_matrices
 
 END MODULE ED_HAMILTONIAN_B200

@@ -221,6 +221,17 @@ int cdmft_b200_imp_weights(int64_t nloc, const void *vec, double *w);
  * all-reduced over the ranks; vec = local shard (host or device) of a vector of the ACTIVE sector. */
 int cdmft_b200_imp_kinetic(int64_t nloc, const void *vec, double out[2]);
 
+/* ---- density matrices of the impurity (ED_OBSERVABLES.f90:465-686, density_matrix_impurity) ------------------ */
+/* For one eigenvector `vec` (local shard, host or device) of the ACTIVE sector with weight peso, ACCUMULATED (+=) like the
+ * reference's sum over state_list; either output may be NULL:
+ *   cdm  complex [4^Nimp, 4^Nimp] column-major: rho_IMP = Tr_BATH |vec><vec|, row / column label IimpUp + 2^Nimp*IimpDw
+ *        (0-based; the reference's io - 1).  Computed as Gram matrices of the amplitude blocks that share a bath
+ *        configuration (k_cluster_gram); needs the whole vector on every process (all-gathered in SPMD mode).
+ *   spdm complex [Nlat,Nlat,Nspin,Nspin,Norb,Norb] column-major: <C^+_a C_b>; diagonal from the weight table of
+ *        cdmft_b200_imp_weights, off-diagonal one matrix-free product per pair and spin block through the regular H x v path.
+ * Host arrays.  Nimp <= 6. */
+int cdmft_b200_density_matrices(int64_t nloc, const void *vec, double peso, double *cdm, double *spdm);
+
 #ifdef __cplusplus
 }
 #endif

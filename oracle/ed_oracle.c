@@ -1324,6 +1324,90 @@ int32_t edo_lanc_local_energy(const edo_ctx *c, int32_t isector, const edo_c64 *
   return 0;
 }
 
+/* ---- density_matrix_impurity (ED_OBSERVABLES.f90:465-686) for one eigenstate ------------------------------------
+ * cdm  [4^Nimp, 4^Nimp] column-major, io = IimpUp + 2^Nimp*IimpDw (0-based here):   rho_IMP = Tr_BATH |vec><vec|,
+ *      accumulated exactly as the reference does (:513-575): for every (IimpUp,JimpUp) the bath states shared by both
+ *      (sp_return_intersection on the itrace map), the same for dw, then the sum over (IbathUp,IbathDw) of
+ *      vec(i) conjg(vec(j)) peso with i, j found by binary_search on Iimp + 2^Nimp*Ibath;
+ * spdm [Nlat,Nlat,Nspin,Nspin,Norb,Norb] column-major: <C^+_a C_b> (:600-676): diagonal peso*n*|vec|^2, off-diagonal
+ *      peso*sgn1*vec(i)*sgn2*conjg(vec(j)) over the impurity hops |j> = c^+_is c_js |i> of spin ispin.
+ * Both ACCUMULATED (+=); vec = full sector vector. */
+int32_t edo_density_matrix_impurity(const edo_ctx *c, int32_t isector, const edo_c64 *vec, double peso, edo_c64 *cdm, edo_c64 *spdm) {
+  const int ns = c->ns, nimp = c->nimp, Nlat = c->m.nlat, Norb = c->m.norb, Nspin = c->m.nspin;
+  const int64_t NI = (int64_t)1 << nimp;
+  int32_t nup_s, ndw_s;
+  edo_get_nup_ndw(ns, isector, &nup_s, &ndw_s);
+  int64_t dimup, dimdw;
+  const int64_t dim = edo_get_dim(ns, isector, &dimup, &dimdw);
+  int32_t *mapu = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimup), *mapd = (int32_t *)malloc(sizeof(int32_t) * (size_t)dimdw);
+  edo_build_sector_map(ns, nup_s, mapu);
+  edo_build_sector_map(ns, ndw_s, mapd);
+  /* build_sector(isector, HI, itrace=.true.): the sparse maps of both spins */
+  int64_t *rpu = (int64_t *)malloc((NI + 1) * sizeof(int64_t)), *rpd = (int64_t *)malloc((NI + 1) * sizeof(int64_t));
+  int32_t *bu = (int32_t *)malloc(dimup * sizeof(int32_t)), *iu = (int32_t *)malloc(dimup * sizeof(int32_t));
+  int32_t *bd = (int32_t *)malloc(dimdw * sizeof(int32_t)), *id = (int32_t *)malloc(dimdw * sizeof(int32_t));
+  edo_build_sparse_map(c, nup_s, rpu, bu, iu);
+  edo_build_sparse_map(c, ndw_s, rpd, bd, id);
+  int32_t *BATHup = (int32_t *)malloc((dimup + 1) * sizeof(int32_t)), *BATHdw = (int32_t *)malloc((dimdw + 1) * sizeof(int32_t));
+  if (cdm)
+    for (int64_t IimpUp = 0; IimpUp < NI; IimpUp++)
+      for (int64_t JimpUp = 0; JimpUp < NI; JimpUp++) {
+        const int32_t lenUp = edo_sparse_map_intersection(rpu, bu, (int32_t)IimpUp, (int32_t)JimpUp, BATHup);
+        if (lenUp == 0) continue;
+        for (int64_t IimpDw = 0; IimpDw < NI; IimpDw++)
+          for (int64_t JimpDw = 0; JimpDw < NI; JimpDw++) {
+            const int32_t lenDw = edo_sparse_map_intersection(rpd, bd, (int32_t)IimpDw, (int32_t)JimpDw, BATHdw);
+            if (lenDw == 0) continue;
+            const int64_t io = IimpUp + NI * IimpDw, jo = JimpUp + NI * JimpDw;
+            for (int32_t bUP = 0; bUP < lenUp; bUP++)
+              for (int32_t bDW = 0; bDW < lenDw; bDW++) {
+                const int64_t IbathUp = BATHup[bUP], IbathDw = BATHdw[bDW];
+                const int64_t iUP = edo_binary_search(mapu, (int32_t)dimup, (int32_t)(IimpUp + NI * IbathUp));
+                const int64_t iDW = edo_binary_search(mapd, (int32_t)dimdw, (int32_t)(IimpDw + NI * IbathDw));
+                const int64_t jUP = edo_binary_search(mapu, (int32_t)dimup, (int32_t)(JimpUp + NI * IbathUp));
+                const int64_t jDW = edo_binary_search(mapd, (int32_t)dimdw, (int32_t)(JimpDw + NI * IbathDw));
+                const int64_t i = iUP + (iDW - 1) * dimup, j = jUP + (jDW - 1) * dimup; /* 1-based */
+                cdm[io + jo * NI * NI] += vec[i - 1] * conj(vec[j - 1]) * peso;
+              }
+          }
+      }
+  if (spdm) {
+#define SPIX(il, jl, is_, js_, io_, jo_) ((il) + Nlat * ((jl) + Nlat * ((is_) + Nspin * ((js_) + Nspin * ((io_) + Norb * (jo_))))))
+    for (int64_t i = 0; i < dim; i++) {
+      const int64_t iup = i % dimup, idw = i / dimup;
+      const int32_t m[2] = {mapu[iup], mapd[idw]};
+      const double w = creal(vec[i]) * creal(vec[i]) + cimag(vec[i]) * cimag(vec[i]);
+      for (int ilat = 1; ilat <= Nlat; ilat++)
+        for (int ispin = 1; ispin <= Nspin; ispin++)
+          for (int iorb = 1; iorb <= Norb; iorb++) {
+            const int is = edo_imp_state_index(c, ilat, iorb);
+            spdm[SPIX(ilat - 1, ilat - 1, ispin - 1, ispin - 1, iorb - 1, iorb - 1)] += peso * (double)((m[ispin - 1] >> (is - 1)) & 1) * w;
+          }
+      for (int ispin = 1; ispin <= Nspin; ispin++)
+        for (int ilat = 1; ilat <= Nlat; ilat++)
+          for (int jlat = 1; jlat <= Nlat; jlat++)
+            for (int iorb = 1; iorb <= Norb; iorb++)
+              for (int jorb = 1; jorb <= Norb; jorb++) {
+                const int is = edo_imp_state_index(c, ilat, iorb), js = edo_imp_state_index(c, jlat, jorb);
+                const int32_t st = m[ispin - 1];
+                if (((st >> (js - 1)) & 1) == 1 && ((st >> (is - 1)) & 1) == 0) {
+                  int32_t r, k;
+                  double sgn1, sgn2;
+                  edo_c(js, st, &r, &sgn1);
+                  edo_cdg(is, r, &k, &sgn2);
+                  int64_t j;
+                  if (ispin == 1) j = (edo_binary_search(mapu, (int32_t)dimup, k) - 1) + idw * dimup;
+                  else j = iup + (int64_t)(edo_binary_search(mapd, (int32_t)dimdw, k) - 1) * dimup;
+                  spdm[SPIX(ilat - 1, jlat - 1, ispin - 1, ispin - 1, iorb - 1, jorb - 1)] += peso * sgn1 * vec[i] * sgn2 * conj(vec[j]);
+                }
+              }
+    }
+#undef SPIX
+  }
+  free(mapu); free(mapd); free(rpu); free(rpd); free(bu); free(iu); free(bd); free(id); free(BATHup); free(BATHdw);
+  return 0;
+}
+
 int32_t edo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -157,6 +157,9 @@ int32_t edo_lanc_observables(int32_t ns, int32_t nlat, int32_t norb, int32_t ise
 /* lanc_local_energy (ED_OBSERVABLES.f90:246-460): out[5] += {Eknot, Epot (before + Ehartree), Ehartree, Dust, Dund} of one
  * eigenstate `vec` (full sector vector) with weight peso; see ed_oracle.c for the term-by-term restatement. */
 int32_t edo_lanc_local_energy(const edo_ctx *c, int32_t isector, const edo_c64 *vec, double peso, double *out);
+/* density_matrix_impurity (ED_OBSERVABLES.f90:465-686): cdm [4^Nimp,4^Nimp] += Tr_BATH |vec><vec| peso (io = IimpUp + 2^Nimp IimpDw),
+ * spdm [Nlat,Nlat,Nspin,Nspin,Norb,Norb] += <C^+_a C_b> peso; either may be NULL. */
+int32_t edo_density_matrix_impurity(const edo_ctx *c, int32_t isector, const edo_c64 *vec, double peso, edo_c64 *cdm, edo_c64 *spdm);
 int32_t edo_apply_op(int32_t ns, int32_t isector, int32_t iop, int32_t ispin, int32_t nops,
                      const int32_t *pos, const edo_c64 *coef, const edo_c64 *state, edo_c64 *out,
                      int32_t *jsector_out);

@@ -268,6 +268,17 @@ class Oracle:
         _chk(self.L.edo_lanc_local_energy(self.h, C.c_int32(isector), _p(vec), C.c_double(peso), _p(out)))
         return dict(zip(("Eknot", "Epot", "Ehartree", "Dust", "Dund"), out.tolist()))
 
+    def density_matrix_impurity(self, isector, vec, peso=1.0):
+        """(cluster_density_matrix [4^Nimp,4^Nimp], single_particle_density_matrix [Nlat,Nlat,Nspin,Nspin,Norb,Norb]) of one
+        eigenstate, Fortran-ordered (ED_OBSERVABLES.f90:465-686)."""
+        m = self.model
+        ni = 1 << (2 * m.nlat * m.norb)
+        vec = np.ascontiguousarray(vec, dtype=np.complex128)
+        cdm = np.zeros((ni, ni), dtype=np.complex128, order="F")
+        sp = np.zeros((m.nlat, m.nlat, m.nspin, m.nspin, m.norb, m.norb), dtype=np.complex128, order="F")
+        _chk(self.L.edo_density_matrix_impurity(self.h, C.c_int32(isector), _p(vec), C.c_double(peso), _p(cdm), _p(sp)))
+        return cdm, sp
+
     def get_csr(self, which):
         nnz = self.L.edo_get_csr(self.h, C.c_int32(which), None, None, None)
         if nnz < 0:

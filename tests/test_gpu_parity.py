@@ -565,6 +565,36 @@ def test_gf_matrix_batched_channels_vs_oracle(ed, oracle_lib):
     assert np.all(Gr[np.arange(nimp), np.arange(nimp)].imag <= 1e-12)
 
 
+def test_density_matrices_vs_oracle(oracle_lib):
+    """density_matrix_impurity (ED_OBSERVABLES.f90:465-686): the cluster density matrix (Gram matrices of the amplitude
+    blocks sharing a bath configuration) and <C^+_a C_b> against the oracle's restatement of the reference loops; one rank
+    and simulated ranks, Nspin = 1 and 2, Norb = 2 (Nimp = 2..4, 16..256-dimensional impurity space)."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    cases = [(models.hm2x2(1), (4, 4)), (models.hm2x2(1), (5, 2)), (models.bhz2(1, kanamori=True), (4, 3)),
+             (models.random_model(2, 1, 2, nspin=2, seed=12), (3, 4)), (models.random_model(1, 2, 2, seed=14), (2, 3))]
+    for P in (1, 3):
+        if P == 1:
+            E.ed_init(0)
+        else:
+            E.ed_init_sim(P, 0)
+        try:
+            for mdl, (nup, ndw) in cases:
+                E.ed_set_model(mdl)
+                isec = models.get_sector(mdl.ns, nup, ndw)
+                n = E.build_Hv_sector(isec, True)
+                vec = _rand_vec(n, seed=51)
+                cdm, sp = E.density_matrix_impurity(vec, mdl.nlat, mdl.norb, mdl.nspin, 0.9)
+                cdm2, sp2 = E.density_matrix_impurity(vec, mdl.nlat, mdl.norb, mdl.nspin, 0.9)
+                assert np.array_equal(cdm, cdm2) and np.array_equal(sp, sp2)  # deterministic
+                E.delete_Hv_sector()
+                ocdm, osp = oracle_lib.Oracle(mdl).density_matrix_impurity(isec, vec, 0.9)
+                assert np.abs(cdm - ocdm).max() < 1e-13, (mdl.name, P)
+                assert np.abs(sp - osp).max() < 1e-12, (mdl.name, P)
+                assert abs(np.trace(cdm).real - 0.9) < 1e-12
+        finally:
+            E.ed_finalize()
+
+
 def test_local_energy_vs_oracle(oracle_lib):
     """lanc_local_energy (ED_OBSERVABLES.f90:246-460): <E0> through one product with the impurity-hopping operator, the
     occupation-dependent pieces from the weight table; one rank and simulated ranks, SPARSE and DIRECT."""

@@ -254,3 +254,45 @@ def test_local_energy_oracle_against_jordan_wigner_operators(oracle_lib):
             assert abs(ref["Ehartree"] - peso * ev(eh)) < 1e-12
         else:
             assert ref["Ehartree"] == 0.0
+
+
+def test_density_matrices_oracle_against_jordan_wigner(oracle_lib):
+    """Pins the oracle's density_matrix_impurity restatement (ED_OBSERVABLES.f90:465-686): the cluster density matrix is the
+    partial trace over the bath of |vec><vec| in the reference's labelling io = IimpUp + 2^Nimp IimpDw (einsum on the
+    full-Fock vector reshaped to [bath_dw, imp_dw, bath_up, imp_up]); the single-particle one is <c^+_a c_b> from dense
+    Jordan-Wigner operators."""
+    from oracle import jw_ed as jw
+    for mdl, (nup, ndw) in [(models.random_model(2, 1, 1, seed=2), (2, 1)), (models.random_model(2, 1, 1, nspin=2, seed=3), (2, 2)),
+                            (models.random_model(1, 2, 1, seed=9, kanamori=True), (1, 3))]:
+        ns, nlat, norb, nimp = mdl.ns, mdl.nlat, mdl.norb, mdl.nlat * mdl.norb
+        nb = ns - nimp
+        isec = models.get_sector(ns, nup, ndw)
+        idx = jw.sector_indices(ns, nup, ndw)
+        rng = np.random.default_rng(31)
+        vec = rng.normal(size=len(idx)) + 1j * rng.normal(size=len(idx))
+        vec /= np.linalg.norm(vec)
+        full = np.zeros(1 << (2 * ns), dtype=np.complex128)
+        full[idx] = vec
+        peso = 0.8
+        cdm, sp = oracle_lib.Oracle(mdl).density_matrix_impurity(isec, vec, peso)
+        # Fock index = mup + (mdw << Ns), m = imp + (bath << Nimp): C-order reshape [bath_dw, imp_dw, bath_up, imp_up]
+        T = full.reshape(1 << nb, 1 << nimp, 1 << nb, 1 << nimp)
+        rho = peso * np.einsum("pdqu,pDqU->udUD", T, T.conj())  # [Iup, Idw, Jup, Jdw]
+        ni = 1 << nimp
+        R = np.zeros((ni * ni, ni * ni), dtype=np.complex128)
+        for Iu in range(ni):
+            for Id in range(ni):
+                for Ju in range(ni):
+                    for Jd in range(ni):
+                        R[Iu + ni * Id, Ju + ni * Jd] = rho[Iu, Id, Ju, Jd]
+        assert np.abs(cdm - R).max() < 1e-13
+        assert abs(np.trace(cdm).real - peso) < 1e-12 and np.abs(cdm - cdm.conj().T).max() < 1e-13
+        c = jw._ops(2 * ns)
+        for s, off in ((0, 0), (mdl.nspin - 1, ns)):
+            for a in range(nimp):
+                for b in range(nimp):
+                    ev = peso * np.vdot(full, c[off + a].T.conj() @ (c[off + b] @ full))
+                    got = sp[a // norb, b // norb, s, s, a % norb, b % norb]
+                    if mdl.nspin == 1 and off == ns:
+                        continue  # Nspin = 1: the reference fills the spin-up block only
+                    assert abs(got - ev) < 1e-12, (a, b, s)
