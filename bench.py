@@ -398,6 +398,16 @@ def run_ours(args):
             gs["iterations_oracle"] = ofx["iterations"]
             gs["oracle_seconds"] = ofx["oracle_seconds"]
             gs["oracle_note"] = f"sp_lanc_eigh restatement on {ofx['oracle_cores']} host cores (tests/golden/make_k3_gs.py; committed fixture, not run here)"
+        if world == 1:  # the reference's default LANC_METHOD (sp_eigh, ED_DIAG.f90:150-170): device-resident thick-restart Lanczos
+            try:
+                t0 = time.perf_counter()
+                we, _, inf = E.sp_eigh_device(2, nblock=20, nitermax=512, tol=args.lanc_tol,
+                                              basis=torch.zeros((2, nloc), dtype=torch.complex128, device="cuda"))
+                gs["sp_eigh_device"] = {"seconds": time.perf_counter() - t0, "neigen": 2, "nblock": 20, "tol": args.lanc_tol,
+                                        "eig_values": [float(x) for x in we], "nconv": inf["nconv"], "hxv_calls": inf["nmatvec"],
+                                        "note": "cdmft_b200_eigh: Krylov basis, full reorthogonalisation and restarts on the device"}
+            except Exception as ex:  # a sub-record must not take the headline down
+                gs["sp_eigh_device"] = {"error": str(ex)[:200]}
         if not args.no_e2e and world == 1:  # host start vector -> lanczos_gs -> host eigenvector
             hv0 = torch.zeros(nloc, dtype=torch.complex128, pin_memory=True)
             t0 = time.perf_counter()

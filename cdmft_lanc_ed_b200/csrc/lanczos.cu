@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "trlan.h"
 
 namespace cb {
 
@@ -652,6 +653,213 @@ static int gs_run(LanczosRun<T> &L, T *gs, int32_t nitermax, double threshold, i
   return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// cdmft_b200_eigh: device backend of the thick-restart Lanczos of trlan.h (sp_eigh, ED_DIAG.f90:150-170).
+// The Krylov basis (ncv + 1 vectors) and the work vector live in the slot pool of the ground-state driver; one
+// step = H x v + one classical Gram-Schmidt pass against the whole basis (k_multi_dot reads w once per 8 basis
+// vectors, k_multi_axpy likewise; coefficients stay on the device between the two) + the norm; one read-back
+// (coefficients + norm) per step.  Restarts rotate the basis in place (k_rotate: every thread owns one vector
+// element of all basis vectors).  Fixed grids and reduction trees -> bitwise reproducible.
+// ------------------------------------------------------------------------------------
+constexpr int kMdVecs = 8;  // basis vectors per launch of the multi-dot / multi-axpy kernels
+template <typename T>
+struct MdArgs {
+  const T *v[kMdVecs];
+  int nv;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_multi_dot(int64_t n, MdArgs<T> a, const T *__restrict__ w, double2 *__restrict__ partial) {
+  double re[kMdVecs], im[kMdVecs];
+#pragma unroll
+  for (int k = 0; k < kMdVecs; k++) re[k] = im[k] = 0.0;
+  GRID_STRIDE(i, n) {
+    const T x = w[i];
+#pragma unroll
+    for (int k = 0; k < kMdVecs; k++)
+      if (k < a.nv) dot_acc(re[k], im[k], a.v[k][i], x);
+  }
+#pragma unroll
+  for (int k = 0; k < kMdVecs; k++) {
+    block_sum2(re[k], im[k]);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * kMdVecs + k] = make_double2(re[k], im[k]);
+    __syncthreads();  // block_sum2's shared scratch is reused by the next vector
+  }
+}
+// out[g] = sum over the blocks of partial[(group(g) * nblocks + b) * kMdVecs + g % kMdVecs]; one CTA per basis vector
+__global__ void __launch_bounds__(256) k_multi_reduce(int nblocks, const double2 *__restrict__ partial, double *__restrict__ out) {
+  const int g = blockIdx.x, grp = g / kMdVecs, k = g % kMdVecs;
+  double re = 0, im = 0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const double2 p = partial[((size_t)grp * nblocks + b) * kMdVecs + k];
+    re += p.x;
+    im += p.y;
+  }
+  block_sum2(re, im);
+  if (threadIdx.x == 0) { out[2 * g] = re; out[2 * g + 1] = im; }
+}
+__device__ __forceinline__ double2 sub_cmul(double2 w, double hre, double him, double2 v) {  // w - h * v
+  return make_double2(w.x - (hre * v.x - him * v.y), w.y - (hre * v.y + him * v.x));
+}
+__device__ __forceinline__ double sub_cmul(double w, double hre, double, double v) { return w - hre * v; }
+// w -= sum_k h[k] v_k, coefficients (re, im) read from device memory
+template <typename T>
+__global__ void __launch_bounds__(256) k_multi_axpy(int64_t n, MdArgs<T> a, const double *__restrict__ h, T *__restrict__ w) {
+  double hre[kMdVecs], him[kMdVecs];
+#pragma unroll
+  for (int k = 0; k < kMdVecs; k++) {
+    hre[k] = k < a.nv ? h[2 * k] : 0.0;
+    him[k] = k < a.nv ? h[2 * k + 1] : 0.0;
+  }
+  GRID_STRIDE(i, n) {
+    T x = w[i];
+#pragma unroll
+    for (int k = 0; k < kMdVecs; k++)
+      if (k < a.nv) x = sub_cmul(x, hre[k], him[k], a.v[k][i]);
+    w[i] = x;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_to(int64_t n, T *__restrict__ out, const T *__restrict__ in, double s) {
+  GRID_STRIDE(i, n) out[i] = scaled(in[i], s);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_rand_fill(int64_t n, int64_t goff, uint64_t seed, T *__restrict__ w) {
+  GRID_STRIDE(i, n) set_real(w[i], trl_rand(seed, (uint64_t)(goff + i)));
+}
+template <typename T>
+struct RotArgs {
+  T *v[kTrlMaxNcv];
+};
+__device__ __forceinline__ void zero_of(double2 &x) { x = make_double2(0.0, 0.0); }
+__device__ __forceinline__ void zero_of(double &x) { x = 0.0; }
+// V[0..k) = V[0..m) Y in place: a thread reads its element of all m vectors before it writes any
+template <typename T>
+__global__ void __launch_bounds__(128) k_rotate(int64_t n, RotArgs<T> a, int m, int k, const double *__restrict__ Y) {
+  extern __shared__ double sY[];
+  for (int i = threadIdx.x; i < m * k; i += blockDim.x) sY[i] = Y[i];
+  __syncthreads();
+  GRID_STRIDE(i, n) {
+    T x[kTrlMaxNcv];
+    for (int r = 0; r < m; r++) x[r] = a.v[r][i];
+    for (int c = 0; c < k; c++) {
+      T acc;
+      zero_of(acc);
+      const double *y = sY + (size_t)c * m;
+      for (int r = 0; r < m; r++) acc = axpy1(acc, y[r], x[r]);
+      a.v[c][i] = acc;
+    }
+  }
+}
+
+template <typename T>
+struct TrlDevBackend {
+  typedef std::complex<double> cplx;
+  int64_t n = 0, goff = 0;
+  std::vector<T *> V;          // ncv + 1 basis vectors (slots of the pool)
+  T *w = nullptr;              // work vector
+  double2 *partial = nullptr;  // [ngroups * kRedBlocks * kMdVecs]
+  double *coef = nullptr;      // device: (re, im) per basis vector, then |w|^2 at 2 * (kTrlMaxNcv + 1)
+  double *ydev = nullptr;      // device copy of the rotation matrix
+  std::vector<double> host;
+
+  int rand_w(uint64_t seed) {
+    Ctx &c = ctx();
+    if (n > 0) { k_rand_fill<T><<<vec_grid(n), 256, 0, c.stream>>>(n, goff, seed, w); c.launches++; }
+    return 0;
+  }
+  int orth_w(int nv, cplx *h, double *nrm2) {
+    Ctx &c = ctx();
+    const unsigned grid = std::min<unsigned>(vec_grid(n), kRedBlocks);
+    const int ngrp = (nv + kMdVecs - 1) / kMdVecs;
+    prof_begin(4);
+    if (nv > 0) {
+      for (int g = 0; g < ngrp; g++) {
+        MdArgs<T> a{};
+        a.nv = std::min(kMdVecs, nv - g * kMdVecs);
+        for (int k = 0; k < a.nv; k++) a.v[k] = V[g * kMdVecs + k];
+        if (n > 0) { k_multi_dot<T><<<grid, 256, 0, c.stream>>>(n, a, w, partial + (size_t)g * grid * kMdVecs); c.launches++; }
+      }
+      if (n > 0) { k_multi_reduce<<<nv, 256, 0, c.stream>>>((int)grid, partial, coef); c.launches++; }
+      else CB_CUDA(cudaMemsetAsync(coef, 0, (size_t)2 * nv * sizeof(double), c.stream));
+      CB_CHECK(nccl_allreduce_sum(coef, 2 * nv));
+      for (int g = 0; g < ngrp; g++) {
+        MdArgs<T> a{};
+        a.nv = std::min(kMdVecs, nv - g * kMdVecs);
+        for (int k = 0; k < a.nv; k++) a.v[k] = V[g * kMdVecs + k];
+        if (n > 0) { k_multi_axpy<T><<<vec_grid(n), 256, 0, c.stream>>>(n, a, coef + 2 * g * kMdVecs, w); c.launches++; }
+      }
+    }
+    double *nrm = coef + 2 * (kTrlMaxNcv + 1);
+    CB_CHECK(zero_partials());
+    if (n > 0) { k_dot<T><<<grid, 256, 0, c.stream>>>(n, w, w, (double2 *)c.red); c.launches++; }
+    CB_CHECK(finish_reduce_dev(nrm));
+    prof_end();
+    host.resize(2 * (kTrlMaxNcv + 2));
+    CB_CUDA(cudaMemcpyAsync(host.data(), coef, host.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CB_CUDA(cudaStreamSynchronize(c.stream));
+    CB_CUDA(cudaGetLastError());
+    for (int k = 0; k < nv; k++) h[k] = cplx(host[2 * k], host[2 * k + 1]);
+    *nrm2 = host[2 * (kTrlMaxNcv + 1)];
+    return 0;
+  }
+  int store_w(int j, double scale) {
+    Ctx &c = ctx();
+    if (n > 0) { k_scale_to<T><<<vec_grid(n), 256, 0, c.stream>>>(n, V[j], w, scale); c.launches++; }
+    return 0;
+  }
+  int matvec(int j) { return hxv_t(V[j], w); }
+  int rotate(int m, int k, const double *Y) {
+    Ctx &c = ctx();
+    CB_CUDA(cudaMemcpyAsync(ydev, Y, (size_t)m * k * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    RotArgs<T> a{};
+    for (int r = 0; r < m; r++) a.v[r] = V[r];
+    if (n > 0) {
+      prof_begin(4);
+      const int64_t nb = (n + 127) / 128;
+      const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)c.sm_count * 8));
+      k_rotate<T><<<grid, 128, (size_t)m * k * sizeof(double), c.stream>>>(n, a, m, k, ydev);
+      c.launches++;
+      prof_end();
+    }
+    CB_CUDA(cudaStreamSynchronize(c.stream));  // Y is a host temporary of the caller
+    return 0;
+  }
+  int move(int dst, int src) {
+    Ctx &c = ctx();
+    if (n > 0) CB_CUDA(cudaMemcpyAsync(V[dst], V[src], (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+    return 0;
+  }
+};
+
+template <typename T>
+static int eigh_run(int64_t nloc, int nev, int ncv, int maxrestart, double tol, std::vector<double> &theta, TrlStats &st,
+                    std::vector<T *> *ritz) {
+  Ctx &c = ctx();
+  TrlDevBackend<T> be;
+  be.n = nloc;
+  be.goff = (c.spmd && !c.rk.empty()) ? c.rk[0].dw.off * c.dimup : 0;
+  const size_t vbytes = (size_t)std::max<int64_t>(nloc, 1) * sizeof(T);
+  be.V.resize(ncv + 1);
+  for (int j = 0; j <= ncv; j++) { void *p = nullptr; CB_CHECK(lz_slot(j, vbytes, &p)); be.V[j] = (T *)p; }
+  { void *p = nullptr; CB_CHECK(lz_slot(ncv + 1, vbytes, &p)); be.w = (T *)p; }
+  const int ngrp = (ncv + 1 + kMdVecs - 1) / kMdVecs;
+  double *scratch = nullptr;
+  const int64_t npart = (int64_t)ngrp * kRedBlocks * kMdVecs * 2, ncoef = 2 * (kTrlMaxNcv + 2), ny = (int64_t)kTrlMaxNcv * kTrlMaxNcv;
+  CB_CHECK(dev_alloc(&scratch, npart + ncoef + ny));
+  be.partial = (double2 *)scratch;
+  be.coef = scratch + npart;
+  be.ydev = be.coef + ncoef;
+  cudaError_t e = cudaMemsetAsync(be.coef, 0, (size_t)ncoef * sizeof(double), c.stream);
+  int rc = e == cudaSuccess ? trl_solve(be, nev, ncv, maxrestart, tol, theta, st) : fail("eigh: cudaMemsetAsync failed");
+  cudaStreamSynchronize(c.stream);
+  cudaFree(scratch);
+  if (rc == -1) return fail("eigh: the start vector has zero norm");
+  if (rc == -2) return fail("eigh: no direction left orthogonal to the Krylov basis (ncv too close to Dim)");
+  CB_CHECK(rc);
+  ritz->assign(be.V.begin(), be.V.begin() + nev);
+  return 0;
+}
+
 // Fock map + Lin tables of one particle number, without hop terms (apply_op, scatter/gather helpers)
 int cached_map_op(int npart, const SpinOp **out) {
   Ctx &c = ctx();
@@ -750,6 +958,89 @@ int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double thr
   }
   if (!dev && nloc > 0) CB_CUDA(cudaMemcpyAsync(vect, gs, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
   CB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// sp_eigh(MatVec, eig_values, eig_basis, Nblock, Nitermax, tol) -- the reference's default LANC_METHOD (ED_DIAG.f90:94-97,
+// 150-170; SciFortran wraps (P)ARPACK, which = 'SA'): the neigen lowest eigenpairs of the active sector by a device-resident
+// thick-restart Lanczos (trlan.h).  Collective in SPMD mode (every dot product is all-reduced, the start vector is a
+// function of the global index): the P-ARPACK call of the reference, without a single vector crossing PCIe.
+int cdmft_b200_eigh(int64_t nloc, int32_t neigen, int32_t nblock, int32_t nitermax, double tol, double *eig_values,
+                    void *eig_basis, int32_t *nconv, int32_t *nmatvec) {
+  CB_REQUIRE_INIT();
+  Ctx &c = ctx();
+  if (!c.hstatus) return fail("eigh: Hsector NOT set");
+  if (nloc != local_n()) return fail("eigh: nloc mismatch");
+  if (neigen < 1) return fail("eigh: Neigen must be positive");
+  if ((int64_t)neigen + 1 >= c.dim)
+    return fail("eigh: Neigen = %d needs a sector of more than %d states (the reference diagonalises such sectors densely, ED_DIAG.f90:104-106)",
+                neigen, neigen + 1);
+  // ncv: ARPACK wants nev < ncv <= n; here additionally ncv + 1 orthonormal vectors must exist and the rotation kernel
+  // holds at most kTrlMaxNcv of them
+  int ncv = nblock > 0 ? nblock : std::max(2 * neigen, 20);
+  ncv = (int)std::min<int64_t>(std::min<int64_t>(ncv, kTrlMaxNcv), c.dim - 1);
+  if (ncv <= neigen) ncv = neigen + 1;
+  if (ncv > kTrlMaxNcv) return fail("eigh: Neigen = %d exceeds the %d basis vectors of the restart kernel", neigen, kTrlMaxNcv - 1);
+  if (nitermax < 0) nitermax = 0;
+  const bool real = real_mode_possible();  // the start vector is real: real H, no Jx/Jp -> real Krylov vectors
+  const size_t vbytes = (size_t)std::max<int64_t>(nloc, 1) * (real ? sizeof(double) : sizeof(double2));
+  int have = 0;
+  CB_CHECK(lz_slot_budget(vbytes, ncv + 2, &have));
+  if (have < ncv + 2) {
+    if (have < neigen + 3) return fail("eigh: HBM holds only %d vectors of this sector, Neigen = %d needs %d", have, neigen, neigen + 3);
+    ncv = have - 2;
+  }
+  std::vector<double> theta;
+  TrlStats st;
+  std::vector<double *> rz_r;
+  std::vector<double2 *> rz_c;
+  if (real) CB_CHECK(eigh_run<double>(nloc, neigen, ncv, nitermax, tol, theta, st, &rz_r));
+  else CB_CHECK(eigh_run<double2>(nloc, neigen, ncv, nitermax, tol, theta, st, &rz_c));
+  for (int i = 0; i < neigen; i++) eig_values[i] = theta[i];
+  if (nconv) *nconv = st.nconv;
+  if (nmatvec) *nmatvec = st.nmatvec;
+  if (eig_basis && nloc > 0) {
+    const bool dev = is_device_ptr(eig_basis);
+    if (real && !dev) CB_CHECK(ensure_kv(nloc, 1));
+    for (int i = 0; i < neigen; i++) {
+      double2 *dst = (double2 *)eig_basis + (size_t)i * nloc;
+      if (real) {
+        double2 *z = dev ? dst : c.kv[0];
+        k_r2c<<<vec_grid(nloc), 256, 0, c.stream>>>(nloc, rz_r[i], z);
+        c.launches++;
+        if (!dev) CB_CUDA(cudaMemcpyAsync(dst, z, (size_t)nloc * 16, cudaMemcpyDeviceToHost, c.stream));
+      } else {
+        CB_CUDA(cudaMemcpyAsync(dst, rz_c[i], (size_t)nloc * 16, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+      }
+    }
+  }
+  CB_CUDA(cudaStreamSynchronize(c.stream));
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Host-only test hook (no CUDA call, like cdmft_b200_schedule_host): the restart logic of cdmft_b200_eigh (trl_solve)
+// on host vectors around the CALLER's mat-vec -- the CPU tests drive it with the oracle's H x v.  Not a product path.
+int cdmft_b200_eigh_logic_host(int64_t n, void (*matvec)(int64_t, const double *, double *, void *), void *user, int32_t neigen,
+                               int32_t nblock, int32_t nitermax, double tol, double *eig_values, double *eig_basis,
+                               int32_t *nconv, int32_t *nmatvec) {
+  if (!matvec || n < 3 || neigen < 1 || (int64_t)neigen + 1 >= n) return fail("eigh_logic_host: bad arguments");
+  int ncv = nblock > 0 ? nblock : std::max(2 * neigen, 20);
+  ncv = (int)std::min<int64_t>(std::min<int64_t>(ncv, kTrlMaxNcv), n - 1);
+  if (ncv <= neigen) ncv = neigen + 1;
+  if (ncv > kTrlMaxNcv) return fail("eigh_logic_host: Neigen too large");
+  TrlHostBackend be;
+  be.init(n, ncv + 1, matvec, user);
+  std::vector<double> theta;
+  TrlStats st;
+  const int rc = trl_solve(be, neigen, ncv, std::max(nitermax, 0), tol, theta, st);
+  if (rc) return fail("eigh_logic_host: thick-restart Lanczos failed (%d)", rc);
+  for (int i = 0; i < neigen; i++) {
+    eig_values[i] = theta[i];
+    if (eig_basis) std::copy((const double *)be.V[i].data(), (const double *)be.V[i].data() + 2 * n, eig_basis + (size_t)2 * n * i);
+  }
+  if (nconv) *nconv = st.nconv;
+  if (nmatvec) *nmatvec = st.nmatvec;
   return 0;
 }
 

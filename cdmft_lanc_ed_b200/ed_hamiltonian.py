@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "cdmft_b200_add_to_lanczos_gf", "cdmft_b200_schedule_host", "cdmft_b200_imp_weights",
     "cdmft_b200_colblk_host", "cdmft_b200_add_to_lanczos_gf_full", "cdmft_b200_build_hmat", "cdmft_b200_scatter_vector",
     "cdmft_b200_gather_vector", "cdmft_b200_imp_kinetic", "cdmft_b200_density_matrices",
+    "cdmft_b200_eigh", "cdmft_b200_eigh_logic_host",
 ]
 
 
@@ -439,6 +440,48 @@ def sp_eigh(neigen: int, nblock: int | None = None, nitermax: int = 512, tol: fl
                  tol=0.0 if tol < 1e-15 else tol, v0=v0)
     order = np.argsort(w)
     return w[order], z[:, order]
+
+
+def sp_eigh_device(neigen: int, nblock: int | None = None, nitermax: int = 512, tol: float = 1e-18, basis=None):
+    """The same call -- `sp_eigh(MpiComm, spHtimesV_p, eig_values, eig_basis, Nblock, Nitermax, tol)`, ED_DIAG.f90:150-170 --
+    without ARPACK on the host: `cdmft_b200_eigh`, a device-resident thick-restart Lanczos (csrc/trlan.h).  Works on one
+    rank, on simulated ranks and collectively in SPMD mode (the P-ARPACK branch).  `basis`: optional CUDA tensor
+    [neigen, nloc] complex128 that receives the eigenvectors (row i = eig_basis(:, i)); otherwise a numpy array
+    [nloc, neigen] is returned.  Returns (eig_values, eig_basis, info) with info = dict(nconv, nmatvec)."""
+    if spHtimesV_p is None:
+        raise EdB200Error("sp_eigh: Hsector NOT set (call build_Hv_sector)")
+    n = _sector["nloc"]
+    # Nblock = min(dim, lanc_ncv_factor*max(Neigen, lanc_nstates_sector) + lanc_ncv_add), defaults 10, 2, 0 (ED_INPUT_VARS.f90:171-175)
+    ncv = nblock if nblock else 10 * max(neigen, 2)
+    w = np.zeros(neigen)
+    out = basis if basis is not None else np.zeros((neigen, max(n, 1)), dtype=np.complex128)
+    nconv, nmv = C.c_int32(), C.c_int32()
+    _chk(load_library().cdmft_b200_eigh(C.c_int64(n), C.c_int32(neigen), C.c_int32(ncv), C.c_int32(nitermax), C.c_double(tol),
+                                        _ptr(w), _ptr(out), C.byref(nconv), C.byref(nmv)))
+    info = dict(nconv=nconv.value, nmatvec=nmv.value)
+    if basis is not None:
+        return w, basis, info
+    return w, np.ascontiguousarray(out[:, :n].T), info
+
+
+_MATVEC_FN = C.CFUNCTYPE(None, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+
+def eigh_logic_host(matvec, n: int, neigen: int, nblock: int | None = None, nitermax: int = 512, tol: float = 1e-18):
+    """CPU test hook: the restart logic of `cdmft_b200_eigh` on host vectors around `matvec` (complex128[n] -> complex128[n],
+    e.g. the oracle's H x v).  Needs no GPU and computes no Hamiltonian itself.  Returns (eig_values, eig_basis [n, neigen], info)."""
+    def cb(nn, pv, phv, _user):
+        v = np.ctypeslib.as_array(pv, shape=(2 * nn,)).view(np.complex128)
+        hv = np.ctypeslib.as_array(phv, shape=(2 * nn,)).view(np.complex128)
+        hv[:] = matvec(v.copy())
+    fn = _MATVEC_FN(cb)
+    w = np.zeros(neigen)
+    z = np.zeros((neigen, n), dtype=np.complex128)
+    nconv, nmv = C.c_int32(), C.c_int32()
+    ncv = nblock if nblock else 10 * max(neigen, 2)
+    _chk(load_library().cdmft_b200_eigh_logic_host(C.c_int64(n), fn, None, C.c_int32(neigen), C.c_int32(ncv), C.c_int32(nitermax),
+                                                   C.c_double(tol), _ptr(w), _ptr(z), C.byref(nconv), C.byref(nmv)))
+    return w, np.ascontiguousarray(z.T), dict(nconv=nconv.value, nmatvec=nmv.value)
 
 
 def apply_op(isector: int, iop: int, ispin: int, pos, coef, state: np.ndarray):

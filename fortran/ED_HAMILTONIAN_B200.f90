@@ -19,7 +19,7 @@ MODULE ED_HAMILTONIAN_B200
   public :: b200_init, b200_finalize
   public :: build_Hv_sector, delete_Hv_sector, vecDim_Hv_sector
   public :: b200_HxV
-  public :: b200_lanc_eigh, b200_lanc_tridiag
+  public :: b200_lanc_eigh, b200_lanc_tridiag, b200_sp_eigh
   public :: b200_scatter_vector, b200_gather_vector
   public :: b200_imp_weights, b200_imp_kinetic, b200_density_matrices
 
@@ -96,6 +96,17 @@ MODULE ED_HAMILTONIAN_B200
        type(c_ptr), value :: alanc, blanc
        integer(c_int) :: rc
      end function c_lanc_gs
+     function c_eigh(nloc, neigen, nblock, nitermax, tol, eig_values, eig_basis, nconv, nmatvec) &
+          bind(C, name="cdmft_b200_eigh") result(rc)
+       import :: c_int, c_int32_t, c_int64_t, c_double, c_double_complex
+       integer(c_int64_t), value :: nloc
+       integer(c_int32_t), value :: neigen, nblock, nitermax
+       real(c_double), value :: tol
+       real(c_double) :: eig_values(*)
+       complex(c_double_complex) :: eig_basis(*)
+       integer(c_int32_t) :: nconv, nmatvec
+       integer(c_int) :: rc
+     end function c_eigh
      function c_lanc_tridiag(nloc, v0, nitermax, threshold, alanc, blanc, ndone) &
           bind(C, name="cdmft_b200_lanczos_tridiag") result(rc)
        import :: c_int, c_int32_t, c_int64_t, c_double, c_double_complex
@@ -304,6 +315,22 @@ contains
     call check(c_lanc_gs(int(size(vect), c_int64_t), vect, int(Nitermax, c_int32_t), thr, int(nck, c_int32_t), &
          egs, niter, c_null_ptr, c_null_ptr), "sp_lanc_eigh")
   end subroutine b200_lanc_eigh
+
+  !> replaces `call sp_eigh([MpiComm,]spHtimesV_p,eig_values,eig_basis,Nblock,Nitermax,tol=lanc_tolerance)` at
+  !> ED_DIAG.f90:152-169 (the default LANC_METHOD, (P)ARPACK): device-resident thick-restart Lanczos, collective over the
+  !> ranks; the Krylov basis never leaves the GPUs.  eig_basis(vecDim,Neigen) as the reference allocates it.
+  subroutine b200_sp_eigh(eig_values, eig_basis, Nblock, Nitermax, tol)
+    real(8), dimension(:)      :: eig_values
+    complex(8), dimension(:,:) :: eig_basis
+    integer                    :: Nblock, Nitermax
+    real(8), optional          :: tol
+    integer(c_int32_t)         :: nconv, nmatvec
+    real(8) :: tl
+    tl = 0d0 ; if (present(tol)) tl = tol
+    if (size(eig_basis, 2) /= size(eig_values)) stop "b200_sp_eigh: eig_basis(:,Neigen) does not match eig_values(Neigen)"
+    call check(c_eigh(int(size(eig_basis, 1), c_int64_t), int(size(eig_values), c_int32_t), int(Nblock, c_int32_t), &
+         int(Nitermax, c_int32_t), tl, eig_values, eig_basis, nconv, nmatvec), "sp_eigh")
+  end subroutine b200_sp_eigh
 
   !> replaces `call sp_lanc_tridiag(MpiComm,spHtimesV_p,vvloc,alfa_,beta_)` at ED_GF_NORMAL.f90:215
   subroutine b200_lanc_tridiag(vin, alanc, blanc, threshold)

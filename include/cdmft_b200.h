@@ -166,6 +166,27 @@ int cdmft_b200_lanczos_tridiag(int64_t nloc, const void *v0, int32_t nitermax, d
 int cdmft_b200_lanczos_gs(int64_t nloc, void *vect, int32_t nitermax, double threshold,
                           int32_t ncheck, double *egs, int32_t *niter, double *alanc, double *blanc);
 
+/* sp_eigh(MatVec, eig_values, eig_basis, Nblock, Nitermax, tol) -- the reference's DEFAULT LANC_METHOD
+ * (ED_DIAG.f90:94-97,150-170; SciFortran wraps (P)ARPACK in reverse communication, which = 'SA', nev = Neigen,
+ * ncv = Nblock, mxiter = Nitermax): the neigen lowest eigenpairs of the ACTIVE sector by a device-resident
+ * thick-restart Lanczos with full reorthogonalisation (the same Krylov subspaces as ARPACK's implicit restart for a
+ * Hermitian operator; csrc/trlan.h).  Collective in SPMD mode (the P-ARPACK branch, ED_DIAG.f90:153-158): every
+ * rank passes its shard sizes, dot products are all-reduced, the pseudo-random start vector is a function of the
+ * global index, so the result does not depend on the number of ranks beyond rounding.
+ *   eig_values[neigen] ascending (host); eig_basis complex(8)[nloc, neigen] column-major (host or device; may be
+ *   NULL); nblock <= 0 -> max(2 neigen, 20); nblock is capped at 64, at Dim - 1 and at what HBM holds.
+ *   tol: a pair is converged when its Ritz bound <= max(tol, eps) * max(eps^(2/3), |theta|) (ARPACK's test; the
+ *   reference's default 1e-18 acts as machine precision).  *nconv = converged pairs (< neigen: Nitermax restarts were
+ *   not enough -- ARPACK's info = 1 -- the current Ritz pairs are returned); *nmatvec = H x v products used. */
+int cdmft_b200_eigh(int64_t nloc, int32_t neigen, int32_t nblock, int32_t nitermax, double tol, double *eig_values,
+                    void *eig_basis, int32_t *nconv, int32_t *nmatvec);
+/* Host-only TEST HOOK (no CUDA call, like cdmft_b200_schedule_host): the restart logic of cdmft_b200_eigh run on host
+ * vectors around the CALLER's mat-vec (complex(8)[n] -> complex(8)[n]); the CPU tests drive it with the oracle's
+ * H x v.  It is not a product path and computes no Hamiltonian itself. */
+int cdmft_b200_eigh_logic_host(int64_t n, void (*matvec)(int64_t n, const double *v, double *hv, void *user), void *user,
+                               int32_t neigen, int32_t nblock, int32_t nitermax, double tol, double *eig_values,
+                               double *eig_basis, int32_t *nconv, int32_t *nmatvec);
+
 /* ---- Green's function helpers (ED_GF_NORMAL.f90) --------------------------------------- */
 /* out = sum_k coef[k] * op(pos[k]) |state>  with op = c^+ (iop=+1) or c (iop=-1) acting on spin
  * ispin (1 = up, 2 = dw) of a vector living in sector `isector`; the result lives in

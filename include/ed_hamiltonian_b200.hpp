@@ -5,6 +5,7 @@
 //   build_Hv_sector / delete_Hv_sector / vecDim_Hv_sector     ED_HAMILTONIAN.f90:39-221
 //   spHtimesV_p (procedure pointer, cc_sparse_HxV)            ED_VARS_GLOBAL.f90:72-78,146
 //   sp_lanc_eigh / sp_lanc_tridiag call sites                 ED_DIAG.f90:176-184, ED_GF_NORMAL.f90:215
+//   sp_eigh (default LANC_METHOD, (P)ARPACK)                  ED_DIAG.f90:150-170
 #pragma once
 #include <complex>
 #include <cstdint>
@@ -103,6 +104,17 @@ inline int sp_lanc_eigh(double &egs, std::vector<cplx> &vect, int Nitermax, doub
   check(cdmft_b200_lanczos_gs((int64_t)vect.size(), vect.data(), Nitermax, threshold, ncheck, &egs, &niter, nullptr, nullptr),
         "sp_lanc_eigh");
   return niter;
+}
+// sp_eigh(spHtimesV_p, eig_values, eig_basis, Nblock, Nitermax, tol) -- the default LANC_METHOD (ED_DIAG.f90:150-170):
+// eig_values.size() = Neigen on entry; eig_basis receives [vecDim, Neigen] column-major.  Device-resident thick-restart
+// Lanczos (cdmft_b200_eigh); returns the number of converged pairs (ARPACK's nconv).
+inline int sp_eigh(std::vector<double> &eig_values, std::vector<cplx> &eig_basis, int64_t vecDim, int Nblock, int Nitermax,
+                   double tol = 1e-18) {
+  int32_t nconv = 0, nmv = 0;
+  eig_basis.assign((size_t)vecDim * eig_values.size(), cplx(0.0, 0.0));
+  check(cdmft_b200_eigh(vecDim, (int32_t)eig_values.size(), Nblock, Nitermax, tol, eig_values.data(), eig_basis.data(), &nconv, &nmv),
+        "sp_eigh");
+  return nconv;
 }
 // sp_lanc_tridiag(spHtimesV_p, vin, alanc, blanc)
 inline int sp_lanc_tridiag(const std::vector<cplx> &vin, std::vector<double> &alanc, std::vector<double> &blanc,

@@ -35,6 +35,18 @@ int main() {
     std::vector<cplx> gs(n, cplx(0, 0));
     double e0 = 0;
     int nit = sp_lanc_eigh(e0, gs, 512, 1e-14);
+    // the default LANC_METHOD of ED_DIAG.f90:150-170: sp_eigh with Neigen = 2, Nblock = 20
+    std::vector<double> evals(2, 0.0);
+    std::vector<cplx> ebasis;
+    const int nconv = sp_eigh(evals, ebasis, n, 20, 512, 1e-13);
+    double eres = 0;
+    for (int k = 0; k < 2; k++) {
+      spHtimesV_p()((int)n, ebasis.data() + (size_t)k * n, hv.data());
+      double r2 = 0;
+      for (int64_t i = 0; i < n; i++) r2 += std::norm(hv[i] - evals[k] * ebasis[(size_t)k * n + i]);
+      eres = std::fmax(eres, std::sqrt(r2));
+    }
+    spHtimesV_p()((int)n, v.data(), hv.data());
     delete_Hv_sector();
     // the LAPACK branch of ED_DIAG.f90:199: build_Hv_sector(isector, Hmat) on a small sector; <E0> hopping part
     const int ismall = get_Sector(2, 3);
@@ -59,7 +71,8 @@ int main() {
     bool threw = false;
     try { b200_HxV((int)n, v.data(), hv.data()); } catch (const std::runtime_error &) { threw = true; }
     ed_finalize();
-    std::printf("{\"n\": %lld, \"e0\": %.15e, \"niter\": %d, \"threw_after_delete\": %s, \"hmat_n\": %lld, \"hmat_maxdiff\": %.3e, "
+    std::printf("{\"sp_eigh\": [%.15e, %.15e], \"sp_eigh_nconv\": %d, \"sp_eigh_residual\": %.3e, ", evals[0], evals[1], nconv, eres);
+    std::printf("\"n\": %lld, \"e0\": %.15e, \"niter\": %d, \"threw_after_delete\": %s, \"hmat_n\": %lld, \"hmat_maxdiff\": %.3e, "
                 "\"hmat_trace\": %.15e, \"imp_kinetic\": %.15e, \"scatter_gather_ok\": %s, \"hv\": [",
                 (long long)n, e0, nit, threw ? "true" : "false", (long long)ns_, hdiff, htrace, ekin, moved ? "true" : "false");
     for (int i = 0; i < 8; i++) std::printf("%s[%.17e, %.17e]", i ? ", " : "", hv[i * 601].real(), hv[i * 601].imag());

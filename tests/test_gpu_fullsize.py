@@ -140,6 +140,31 @@ def test_fullsize_K3_ground_state_against_oracle_fixture(ed):
     assert abs(float(vec.abs().max()) - fx["vec_abs_max"]) < 1e-8
 
 
+def test_fullsize_K3_sp_eigh_device_against_oracle_fixture(ed):
+    """The reference's default LANC_METHOD at full size: cdmft_b200_eigh (device-resident thick-restart Lanczos, two
+    eigenpairs, Nblock = 20) on the K3 sector; E0 against the committed ground-state run of the CPU oracle, residuals of
+    both pairs through the H x v path that is itself checked against the oracle at this size."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "k3_gs_oracle.json")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    fx = json.load(open(path))
+    ed.ed_set_model(models.hm2x2(3))
+    n = ed.build_Hv_sector(models.get_sector(16, 8, 8), True)
+    basis = torch.zeros((2, n), dtype=torch.complex128, device="cuda")
+    w, _, info = ed.sp_eigh_device(2, nblock=20, nitermax=512, tol=1e-12, basis=basis)
+    torch.cuda.synchronize()
+    assert info["nconv"] == 2, info
+    assert abs(w[0] - fx["e0"]) <= RTOL * abs(fx["e0"]) and w[1] > w[0]
+    for k in range(2):
+        hv = _hxv(ed, n, basis[k])
+        assert float(torch.linalg.vector_norm(hv - w[k] * basis[k])) < 1e-8
+        assert abs(float(torch.linalg.vector_norm(basis[k])) - 1.0) < 1e-12
+    assert abs(complex(torch.vdot(basis[0], basis[1]))) < 1e-10
+    ed.delete_Hv_sector()
+
+
 def test_fullsize_K4_against_oracle(ed, oracle_lib):
     """One full K4 (complex BHZ hoppings) H x v against the CPU oracle, SPARSE and DIRECT."""
     import os

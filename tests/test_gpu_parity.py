@@ -664,6 +664,96 @@ def test_sp_eigh_arpack_with_device_matvec(ed, oracle_lib):
         ed.delete_Hv_sector()
 
 
+def _check_eigpairs(hxv, w, z, ref, neigen):
+    assert np.abs(w - ref[:neigen]).max() < RTOL * max(1.0, np.abs(ref[:neigen]).max())
+    for k in range(neigen):
+        zk = np.ascontiguousarray(z[:, k])
+        assert np.linalg.norm(hxv(zk) - w[k] * zk) < 1e-8
+    assert np.abs(z.conj().T @ z - np.eye(neigen)).max() < 1e-10
+
+
+def test_sp_eigh_device_resident(ed, oracle_lib):
+    """cdmft_b200_eigh: the same call as above with the Krylov basis, the reorthogonalisation and the restarts on the
+    device (thick-restart Lanczos, csrc/trlan.h) -- real model (real Krylov vectors), complex model, Kanamori model
+    (Jx/Jp term, complex vectors), DIRECT mode; several eigenpairs against the dense spectrum of the oracle's Hmat;
+    eigenvectors into a CUDA tensor as well."""
+    import torch
+    cases = [(models.hm2x2(1), (4, 4), 3, None, True), (models.bhz2(1), (3, 3), 4, None, True),
+             (models.bhz2(1, kanamori=True), (3, 3), 2, 12, True), (models.hm2x2(2), (6, 6), 2, 16, False),
+             (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 4), 1, 2, True)]
+    for mdl, (nup, ndw), neigen, nblock, sparse in cases:
+        orc = oracle_lib.Oracle(mdl)
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        ed.ed_set_model(mdl)
+        n = ed.build_Hv_sector(isec, sparse)
+        if n <= 5000:
+            ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
+            # one Krylov sequence resolves one vector per degenerate level (ARPACK likewise): stop the request below a multiplet
+            while neigen > 1 and abs(ref[neigen] - ref[neigen - 1]) < 1e-8:
+                neigen -= 1
+        w, z, info = ed.sp_eigh_device(neigen, nblock=nblock, tol=1e-13)
+        assert z.shape == (n, neigen) and info["nconv"] == neigen and info["nmatvec"] > 0, info
+        if n <= 5000:
+            _check_eigpairs(ed.hxv, w, z, ref, neigen)
+        else:  # Ns = 12 (Dim 853 776): the oracle's ground-state Lanczos for E0, the oracle's mat-vec for the residuals
+            orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+            e0 = orc.lanc_eigh(threshold=1e-14)[0]
+            assert abs(w[0] - e0) < RTOL * abs(e0) and np.all(np.diff(w) > 0)
+            for k in range(neigen):
+                zk = np.ascontiguousarray(z[:, k])
+                assert np.linalg.norm(orc.hxv(zk) - w[k] * zk) < 1e-8
+            orc.delete_hv_sector()
+        basis = torch.zeros((neigen, n), dtype=torch.complex128, device="cuda")
+        w2, _, _ = ed.sp_eigh_device(neigen, nblock=nblock, tol=1e-13, basis=basis)
+        assert np.array_equal(w, w2)  # fixed reduction trees: bitwise the same run
+        assert np.array_equal(basis.cpu().numpy().T, z)
+        ed.delete_Hv_sector()
+
+
+@pytest.mark.parametrize("P", [2, 3, 5])
+def test_sp_eigh_device_resident_sharded(oracle_lib, P):
+    """The P-ARPACK branch (ED_DIAG.f90:153-158): the same driver on the Ndw-sharded layout (simulated ranks: the
+    transposing code path, paired-row real vectors); the start vector depends on the global index only, so the
+    eigenvalues must agree with the one-rank run to rounding."""
+    from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+    res = {}
+    for mode in ("single", "sim"):
+        E.ed_init(0) if mode == "single" else E.ed_init_sim(P)
+        try:
+            for mdl, (nup, ndw), neigen in [(models.hm2x2(1), (4, 4), 2), (models.bhz2(1), (3, 4), 3)]:
+                E.ed_set_model(mdl)
+                isec = models.get_sector(mdl.ns, nup, ndw)
+                n = E.build_Hv_sector(isec, True)
+                w, z, info = E.sp_eigh_device(neigen, nblock=14, tol=1e-13)
+                assert info["nconv"] == neigen
+                ref = np.linalg.eigvalsh(oracle_lib.Oracle(mdl).dense_hmat(isec))
+                _check_eigpairs(E.hxv, w, z, ref, neigen)
+                res[(mode, mdl.name)] = w
+                E.delete_Hv_sector()
+        finally:
+            E.ed_finalize()
+    for (mode, name), w in res.items():
+        if mode == "sim":
+            assert np.abs(w - res[("single", name)]).max() < 1e-11
+
+
+def test_sp_eigh_device_rejects_bad_requests(ed):
+    mdl = models.hm2x2(1)
+    ed.ed_set_model(mdl)
+    with pytest.raises(ed.EdB200Error):
+        ed.sp_eigh_device(1)  # no active sector
+    isec = models.get_sector(mdl.ns, 1, 1)  # Dim = 64
+    n = ed.build_Hv_sector(isec, True)
+    with pytest.raises(ed.EdB200Error):
+        ed.sp_eigh_device(63)  # the reference diagonalises such requests densely (ED_DIAG.f90:104-106)
+    w, z, info = ed.sp_eigh_device(2, nblock=100, tol=1e-13)  # Nblock is capped at Dim - 1 = 63 (< 64, the kernel limit)
+    assert info["nconv"] == 2
+    for k in range(2):
+        zk = np.ascontiguousarray(z[:, k])
+        assert np.linalg.norm(ed.hxv(zk) - w[k] * zk) < 1e-9
+    ed.delete_Hv_sector()
+
+
 def test_dense_hmat_and_vector_moves(ed, oracle_lib):
     """build_Hv_sector(isector, Hmat) (dense assembly, ED_HAMILTONIAN_SPARSE_HxV.f90:112-148) against the oracle's
     dense matrix, in both modes; scatter_vector_MPI / gather_vector_MPI with one rank are copies."""

@@ -30,3 +30,75 @@ def test_sp_eigh_wrapper_with_oracle_matvec(case):
 def test_sp_eigh_rejects_full_spectrum_requests():
     with pytest.raises(E.EdB200Error):
         E.sp_eigh(5, matvec=lambda x: x, n=5)
+
+
+# ---- restart logic of the DEVICE-RESIDENT sp_eigh (cdmft_b200_eigh, csrc/trlan.h) through its host test hook ----------
+def _check_pairs(hxv, w, z, ref, neigen, tol_e=1e-10):
+    assert np.abs(w - ref[:neigen]).max() < tol_e * max(1.0, np.abs(ref[:neigen]).max())
+    for k in range(neigen):
+        assert np.linalg.norm(hxv(z[:, k]) - w[k] * z[:, k]) < 1e-8
+    assert np.abs(z.conj().T @ z - np.eye(neigen)).max() < 1e-10
+
+
+@pytest.mark.parametrize("case", [("hm2x2(1)", (4, 4), 1, None), ("hm2x2(1)", (4, 4), 3, 12), ("bhz2(1)", (3, 3), 4, None),
+                                  ("random_model(2, 2, 1, seed=8)", (3, 4), 2, 3), ("bhz2(1, kanamori=True)", (3, 3), 3, 20)])
+def test_thick_restart_logic_with_oracle_matvec(case):
+    """nev lowest eigenpairs of real, complex and Kanamori sectors vs a dense diagonalisation of the oracle's Hmat;
+    default Nblock (the reference's 10*max(Neigen,2)), a small one (many restarts) and the minimum nev + 1."""
+    mdl = eval("models." + case[0])
+    (nup, ndw), neigen, nblock = case[1], case[2], case[3]
+    isec = models.get_sector(mdl.ns, nup, ndw)
+    orc = edo.Oracle(mdl)
+    ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
+    orc.build_hv_sector(isec, edo.SPARSE_SERIAL)
+    # pairs inside a degenerate multiplet cannot be told apart by one Krylov sequence (ARPACK neither): only ask for
+    # as many pairs as are separated from the next level
+    while neigen > 1 and abs(ref[neigen] - ref[neigen - 1]) < 1e-8:
+        neigen -= 1
+    w, z, info = E.eigh_logic_host(orc.hxv, orc.dim, neigen, nblock=nblock, nitermax=2000, tol=1e-12)
+    assert info["nconv"] == neigen, info
+    mult = [np.sum(np.abs(ref - e) < 1e-8) for e in ref[:neigen]]
+    if max(mult) == 1:
+        _check_pairs(orc.hxv, w, z, ref, neigen)
+    else:  # a degenerate level below the cut: every returned value must be an eigenvalue, every vector an eigenvector
+        for k in range(neigen):
+            assert np.abs(ref - w[k]).min() < 1e-9
+            assert np.linalg.norm(orc.hxv(z[:, k]) - w[k] * z[:, k]) < 1e-8
+    orc.delete_hv_sector()
+
+
+def test_thick_restart_default_tolerance_terminates():
+    """The reference passes lanc_tolerance = 1e-18 (ED_INPUT_VARS.f90:178): it must act as machine precision, not run forever."""
+    mdl = models.hm2x2(1)
+    isec = models.get_sector(mdl.ns, 4, 4)
+    orc = edo.Oracle(mdl)
+    ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
+    orc.build_hv_sector(isec, edo.SPARSE_SERIAL)
+    w, z, info = E.eigh_logic_host(orc.hxv, orc.dim, 2, nitermax=512, tol=1e-18)
+    assert info["nconv"] == 2 and info["nmatvec"] < 2000, info
+    _check_pairs(orc.hxv, w, z, ref, 2, tol_e=1e-12)
+    orc.delete_hv_sector()
+
+
+def test_thick_restart_invariant_subspace_and_restart_cap():
+    """A diagonal operator with 5 distinct levels: the Krylov space closes after 5 steps (beta = 0) and the driver must go
+    on with fresh orthogonal directions; then Nitermax = 0 on a generic operator: one sweep, nconv < neigen, no failure."""
+    n = 200
+    d = np.repeat(np.array([-2.0, -1.0, 0.5, 1.0, 3.0]), n // 5)
+    w, z, info = E.eigh_logic_host(lambda v: d * v, n, 3, nblock=12, nitermax=50, tol=1e-12)
+    assert np.allclose(w, [-2.0, -2.0, -2.0], atol=1e-10) or np.allclose(w, [-2.0, -1.0, 0.5], atol=1e-10) or \
+        all(np.abs(d - x).min() < 1e-10 for x in w), w
+    for k in range(3):
+        assert np.linalg.norm(d * z[:, k] - w[k] * z[:, k]) < 1e-8
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(300, 300)) + 1j * rng.normal(size=(300, 300))
+    a = a + a.conj().T
+    w, z, info = E.eigh_logic_host(lambda v: a @ v, 300, 2, nblock=6, nitermax=0, tol=1e-12)
+    assert info["nconv"] < 2 and info["nmatvec"] == 6
+    w, z, info = E.eigh_logic_host(lambda v: a @ v, 300, 2, nblock=24, nitermax=500, tol=1e-12)
+    _check_pairs(lambda v: a @ v, w, z, np.linalg.eigvalsh(a), 2)
+
+
+def test_thick_restart_rejects_tiny_spaces():
+    with pytest.raises(E.EdB200Error):
+        E.eigh_logic_host(lambda v: v, 3, 2)

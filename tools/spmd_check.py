@@ -53,7 +53,8 @@ def main():
                 orc.build_hv_sector(isec, edo.SPARSE_MPI if sparse else edo.DIRECT_MPI, world)
                 ref = dict(hv=orc.hxv(v), tri=orc.lanc_tridiag(v, 30), trir=orc.lanc_tridiag(vreal, 30),
                            cop=edo.apply_op(ns, isec, +1, 1, [1], [1.0 + 0.0j], v),
-                           copd=edo.apply_op(ns, isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], v), p_eff=orc.active_ranks())
+                           copd=edo.apply_op(ns, isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], v), p_eff=orc.active_ranks(),
+                           eig=np.linalg.eigvalsh(orc.dense_hmat(isec)) if sparse and 8 <= dim <= 5000 else None)
                 orc.delete_hv_sector()
             for mode in SEL:
                 use_ipc, chunks = MODES[mode]
@@ -75,6 +76,23 @@ def main():
                 # real start vector: real Krylov vectors on the sharded layout (paired-row view) when H is real
                 vr = np.ascontiguousarray(vreal[off:off + nloc])
                 ndr, ar, br = E.sp_lanc_tridiag(vr, 30)
+                # sp_eigh, P-ARPACK branch (ED_DIAG.f90:153-158): the device-resident thick-restart Lanczos is collective;
+                # two lowest pairs against the dense spectrum, residuals through the sharded mat-vec (first back-end only)
+                eig_ok, eig_err = True, 0.0
+                if mode == SEL[0] and sparse and 8 <= dim <= 5000:
+                    w, z, info = E.sp_eigh_device(2, nblock=12, tol=1e-13)
+                    res2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+                    for k in range(2):
+                        zk = np.ascontiguousarray(z[:, k]) if nloc else np.zeros(0, dtype=np.complex128)
+                        hz = np.empty_like(zk)
+                        E.spHtimesV_p(nloc, zk, hz)
+                        res2[k] = float(np.linalg.norm(hz - w[k] * zk) ** 2)
+                    dist.all_reduce(res2)
+                    if rank == 0:
+                        dref = ref["eig"]
+                        eig_err = float(np.abs(w - dref[:2]).max()) if abs(dref[2] - dref[1]) > 1e-8 and abs(dref[1] - dref[0]) > 1e-8 \
+                            else float(min(np.abs(dref - w[0]).min(), 1.0))
+                        eig_ok = info["nconv"] == 2 and eig_err < 1e-10 * max(1.0, float(np.abs(dref[:2]).max())) and float(res2.max()) < 1e-16
                 # c^+_{1,up} on the sharded vector (start vector of a GF channel, ED_GF_NORMAL.f90:180-194): shard-local
                 jsec, cv = E.apply_op(isec, +1, 1, [1], [1.0 + 0.0j], vloc)
                 cparts = [None] * world
@@ -110,10 +128,10 @@ def main():
                     ojd, ocd = ref["copd"]
                     gotd = np.concatenate([p for p in dparts if p is not None and p.size] or [np.zeros(0, dtype=np.complex128)])
                     okc = okc and (ojd == jsecd) and (ojd == 0 or (gotd.size == ocd.size and np.abs(gotd - ocd).max() < 1e-14))
-                    good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == ref["p_eff"] and nd == ond and ndr == ondr and okc
+                    good = err < 1e-10 and erra < 1e-9 and errr < 1e-9 and p_eff == ref["p_eff"] and nd == ond and ndr == ondr and okc and eig_ok
                     ok &= bool(good)
                     print(f"{mdl.name} sector({nup},{ndw}) sparse={sparse} P={world} p_eff={p_eff} dim={dim} backend={mode} "
-                          f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} alpha_realstart_relerr={errr:.2e} apply_op={'ok' if okc else 'BAD'} {'OK' if good else 'FAIL'}", flush=True)
+                          f"hxv_relerr={err:.2e} alpha_relerr={erra:.2e} alpha_realstart_relerr={errr:.2e} apply_op={'ok' if okc else 'BAD'} sp_eigh={'ok' if eig_ok else 'BAD'}({eig_err:.1e}) {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     E.ed_finalize()
