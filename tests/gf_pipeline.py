@@ -97,3 +97,70 @@ def gimp_element(backend, mdl, ia, ib, wm, ed=None, edo=None, gs=None):
     _channel(be, isec, e0, vec, -1, [ia, ib], [1.0, -1.0j], -1.0j, -1, wm, g, getdim)
     # non-diagonal trick, ED_GF_NORMAL.f90:91-103 (chan4 = 1)
     return 0.5 * (g - (1 - 1j) * diag(ia) - (1 - 1j) * diag(ib))
+
+
+# ---- the reference's own non-interacting Green's function (ED_BATH_FUNCTIONS.f90) ---------------------------------------
+def _lso(m6):
+    """nnn2lso_reshape (ED_AUX_FUNX.f90): [Nlat,Nlat,Nspin,Nspin,Norb,Norb] -> [Nlso,Nlso] with the index
+    iorb + (ilat-1)*Norb + (ispin-1)*Norb*Nlat of index_stride_lso (ED_AUX_FUNX.f90:81-87)."""
+    L, _, S, _, O, _ = m6.shape
+    n = L * S * O
+    out = np.zeros((n, n), dtype=np.complex128)
+    for il in range(L):
+        for jl in range(L):
+            for isp in range(S):
+                for jsp in range(S):
+                    for io in range(O):
+                        for jo in range(O):
+                            out[io + il * O + isp * O * L, jo + jl * O + jsp * O * L] = m6[il, jl, isp, jsp, io, jo]
+    return out
+
+
+def g0and_bath(mdl, x):
+    """g0and_bath(x) of the reference, restated from ED_BATH_FUNCTIONS.f90:39-155:
+        Delta(x) = sum_ib diag(v_ib) (x 1 - Hbath_ib)^-1 diag(v_ib)            delta_bath_array   :69-99
+        G0^-1(x) = (x + xmu) 1 - impHloc - Delta(x)                             invg0_bath_array   :140-155
+        G0(x)    = inv(G0^-1(x))                                                 g0and_bath         :102-121
+    in the lso basis.  Returns [Nlso, Nlso, len(x)]."""
+    hloc = _lso(mdl.imphloc)
+    n = hloc.shape[0]
+    out = np.zeros((n, n, len(x)), dtype=np.complex128)
+    for i, z in enumerate(x):
+        delta = np.zeros((n, n), dtype=np.complex128)
+        for ib in range(mdl.nbath):
+            vk = np.diag(mdl.vbath[:, ib]).astype(np.complex128)
+            delta += vk @ np.linalg.inv(z * np.eye(n) - _lso(mdl.hbath[..., ib])) @ vk
+        out[:, :, i] = np.linalg.inv((z + mdl.xmu) * np.eye(n) - hloc - delta)
+    return out
+
+
+def noninteracting_half_filled(mdl, grid=None):
+    """U = 0 copy of a model with xmu chosen so that the ground state is the non-degenerate Slater determinant of the
+    sector (Ns/2, Ns/2): exactly Ns/2 single-particle levels of [[impHloc - xmu, V], [V, Hbath]] below zero.  Returns
+    (model, gap) or (None, 0) when no xmu of the grid does it.  Nspin = 1."""
+    import copy
+    assert mdl.nspin == 1
+    n = mdl.nimp
+    ns = mdl.ns
+    best, best_gap = None, 0.0
+    for xmu in (np.linspace(-3.0, 3.0, 241) if grid is None else grid):
+        h1 = np.zeros((ns, ns), dtype=np.complex128)
+        h1[:n, :n] = _lso(mdl.imphloc) - xmu * np.eye(n)
+        for ib in range(mdl.nbath):
+            sl = slice(n * (ib + 1), n * (ib + 2))  # getBathStride: Nimp + imp index + (ibath-1)*Nimp, ED_SETUP.f90:367-375
+            h1[sl, sl] = _lso(mdl.hbath[..., ib])
+            h1[:n, sl] = np.diag(mdl.vbath[:, ib])
+            h1[sl, :n] = np.diag(mdl.vbath[:, ib])
+        e = np.linalg.eigvalsh(h1)
+        if np.sum(e < 0) == ns // 2:
+            gap = min(-e[ns // 2 - 1], e[ns // 2])
+            if gap > best_gap:
+                best, best_gap = xmu, gap
+    if best is None:
+        return None, 0.0
+    m = copy.deepcopy(mdl)
+    m.uloc = np.zeros(5)
+    m.ust = m.jh = m.jx = m.jp = 0.0
+    m.xmu = float(best)
+    m.name = mdl.name + "_U0"
+    return m, best_gap

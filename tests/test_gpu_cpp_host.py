@@ -45,13 +45,13 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_lib):
     e0 = orc.lanc_eigh(512, 1e-14)[0]
     assert abs(r["e0"] - e0) < 1e-10 * abs(e0)
     assert r["threw_after_delete"] and r["n"] == 4900
+    # build_Hv_sector(isector, Hmat), imp_kinetic, scatter / gather through the C++ mirror
+    orc.delete_hv_sector()
     # sp_eigh (default LANC_METHOD) through the C++ mirror: two lowest pairs against the dense spectrum
     dref = np.linalg.eigvalsh(orc.dense_hmat(isec))
     assert r["sp_eigh_nconv"] == 2 and r["sp_eigh_residual"] < 1e-8
     assert abs(r["sp_eigh"][0] - dref[0]) < 1e-10 * abs(dref[0])
     assert np.abs(dref - r["sp_eigh"][1]).min() < 1e-10 * abs(dref[0]) and r["sp_eigh"][1] > r["sp_eigh"][0] - 1e-9
-    # build_Hv_sector(isector, Hmat), imp_kinetic, scatter / gather through the C++ mirror
-    orc.delete_hv_sector()
     ismall = models.get_sector(8, 2, 3)
     H = orc.dense_hmat(ismall)
     assert r["hmat_n"] == H.shape[0] and r["hmat_maxdiff"] < 1e-12 and r["scatter_gather_ok"]

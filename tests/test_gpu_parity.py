@@ -279,6 +279,25 @@ def test_gimp_matsubara_vs_oracle(ed, oracle_lib):
     assert _relerr(g_prod, g_orc) < 1e-6
 
 
+@pytest.mark.parametrize("case", ["models.hm2x2(1)", "models.bhz2(1)", "models.random_model(2, 2, 1, seed=31)"])
+def test_u0_gimp_equals_the_references_g0and_bath(ed, case):
+    """The anchor that comes from the reference itself (tests/test_oracle_pin.py has the oracle's side): at U = 0 the
+    whole product pipeline on the device -- sector build, ground-state Lanczos, c / c^+ start vectors, tridiagonalisation,
+    pole sums -- must reproduce the reference's analytic g0and_bath (ED_BATH_FUNCTIONS.f90:102-155), diagonal and
+    off-diagonal elements.  No oracle involved."""
+    from tests.gf_pipeline import g0and_bath, gimp_element, noninteracting_half_filled
+    mdl, gap = noninteracting_half_filled(eval(case))
+    assert mdl is not None and gap > 1e-2
+    wm = np.pi / 40.0 * (2 * np.arange(1, 25) - 1)
+    g0 = g0and_bath(mdl, 1j * wm)
+    n = mdl.nimp
+    for ia, ib in [(1, 1), (n, n), (1, 2), (2, 1), (1, n)]:
+        g = gimp_element("product", mdl, ia, ib, wm, ed=ed)
+        # limited by the Lanczos ground-state vector (the stopping rule acts on the energy), as in test_gimp_matsubara_vs_oracle (b);
+        # a convention error would be O(1)
+        assert np.abs(g - g0[ia - 1, ib - 1]).max() < 1e-6 * max(1.0, np.abs(g0[ia - 1, ib - 1]).max()), (case, ia, ib)
+
+
 @pytest.mark.parametrize("opts", [
     dict(),                                                    # defaults: tile-resident row pass writes, column-resident pass accumulates
     dict(tma2d=0),                                             # tiles by per-column bulk copies instead of 2-D TMA tensor copies
@@ -680,7 +699,7 @@ def test_sp_eigh_device_resident(ed, oracle_lib):
     import torch
     cases = [(models.hm2x2(1), (4, 4), 3, None, True), (models.bhz2(1), (3, 3), 4, None, True),
              (models.bhz2(1, kanamori=True), (3, 3), 2, 12, True), (models.hm2x2(2), (6, 6), 2, 16, False),
-             (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 4), 1, 2, True)]
+             (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 4), 1, 3, True)]
     for mdl, (nup, ndw), neigen, nblock, sparse in cases:
         orc = oracle_lib.Oracle(mdl)
         isec = models.get_sector(mdl.ns, nup, ndw)

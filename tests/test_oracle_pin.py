@@ -296,3 +296,35 @@ def test_density_matrices_oracle_against_jordan_wigner(oracle_lib):
                     if mdl.nspin == 1 and off == ns:
                         continue  # Nspin = 1: the reference fills the spin-up block only
                     assert abs(got - ev) < 1e-12, (a, b, s)
+
+
+@pytest.mark.parametrize("case", ["models.hm2x2(1)", "models.bhz2(1)", "models.random_model(2, 2, 1, seed=31)",
+                                  "models.random_model(3, 1, 1, seed=32)", "models.hubbard_cluster(2, 1, 2)"])
+def test_u0_gimp_equals_the_references_g0and_bath(oracle_lib, case):
+    """An anchor that comes from the REFERENCE itself, not from this repository's reading of it: at U = 0 the impurity
+    Green's function of the ED pipeline (sector Hamiltonian -> ground-state Lanczos -> c / c^+ start vectors ->
+    tridiagonalisation -> pole sums, ED_GF_NORMAL.f90) must equal the reference's analytic non-interacting function
+    g0and_bath (ED_BATH_FUNCTIONS.f90:102-155: G0^-1 = (iw + xmu) - impHloc - sum_ib V (iw - Hbath_ib)^-1 V).  This pins
+    the bath-orbital layout (getBathStride), the hybridisation and replica-hopping conventions, the sign of xmu, the
+    fermionic signs of the hops and the whole Green's-function flow, diagonal and off-diagonal (4-channel) elements."""
+    from tests.gf_pipeline import g0and_bath, gimp_element, noninteracting_half_filled
+    mdl, gap = noninteracting_half_filled(eval(case))
+    assert mdl is not None and gap > 1e-2, "no half-filled non-degenerate ground state on the xmu grid"
+    wm = np.pi / 40.0 * (2 * np.arange(1, 25) - 1)
+    g0 = g0and_bath(mdl, 1j * wm)
+    o = _Oracle_gs(mdl, oracle_lib)
+    n = mdl.nimp
+    pairs = [(a, a) for a in range(1, n + 1)] + [(1, 2), (2, 1)] + ([(1, n), (n, 2)] if n > 2 else [])
+    for ia, ib in pairs:
+        g = gimp_element("oracle", mdl, ia, ib, wm, edo=oracle_lib, gs=o)
+        # limited by the Lanczos ground-state vector (gaps down to 0.14), not by conventions: a convention error is O(1)
+        assert np.abs(g - g0[ia - 1, ib - 1]).max() < 5e-8 * max(1.0, np.abs(g0[ia - 1, ib - 1]).max()), (case, ia, ib)
+
+
+def _Oracle_gs(mdl, edo):
+    """ground state of the sector (Ns/2, Ns/2) once, shared by all elements"""
+    o = edo.Oracle(mdl)
+    o.build_hv_sector(models.get_sector(mdl.ns, mdl.ns // 2, mdl.ns // 2), edo.SPARSE_SERIAL)
+    e0, vec, _, _, _ = o.lanc_eigh(512, 1e-14)  # (a threshold below what the recurrence resolves runs 512 steps and spoils the vector)
+    o.delete_hv_sector()
+    return e0, vec

@@ -53,9 +53,9 @@ def main():
                 orc.build_hv_sector(isec, edo.SPARSE_MPI if sparse else edo.DIRECT_MPI, world)
                 ref = dict(hv=orc.hxv(v), tri=orc.lanc_tridiag(v, 30), trir=orc.lanc_tridiag(vreal, 30),
                            cop=edo.apply_op(ns, isec, +1, 1, [1], [1.0 + 0.0j], v),
-                           copd=edo.apply_op(ns, isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], v), p_eff=orc.active_ranks(),
-                           eig=np.linalg.eigvalsh(orc.dense_hmat(isec)) if sparse and 8 <= dim <= 5000 else None)
+                           copd=edo.apply_op(ns, isec, -1, 2, [min(2, ns)], [0.5 - 0.25j], v), p_eff=orc.active_ranks())
                 orc.delete_hv_sector()
+                ref["eig"] = np.linalg.eigvalsh(orc.dense_hmat(isec)) if sparse and 8 <= dim <= 5000 else None
             for mode in SEL:
                 use_ipc, chunks = MODES[mode]
                 E.set_option("use_ipc", use_ipc)
