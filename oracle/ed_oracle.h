@@ -10,9 +10,11 @@
  * PARITY STATUS: "parity unpinned" by reference fixtures -- the reference ships
  * no tests, golden vectors or known-answer files for this path (SURVEY.md §4,
  * §8c) and cannot be compiled here (no Fortran compiler, no MPI, no SciFortran).
- * Substitute anchors (tests/test_oracle_*.py): an independent full-Fock
+ * Substitute anchors (tests/test_oracle_pin.py): an independent full-Fock
  * Jordan-Wigner ED (oracle/jw_ed.py), dense == sparse == direct == MPI(P),
- * U=0 vs the analytic non-interacting Green's function, scipy eigsh.
+ * scipy eigsh, and -- the one anchor taken from the reference itself -- the
+ * U=0 impurity Green's function of the whole pipeline against the reference's
+ * analytic g0and_bath (ED_BATH_FUNCTIONS.f90:102-155).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference root).  The Krylov routines restate SciFortran's SF_SP_LINALG
