@@ -1021,23 +1021,27 @@ int cdmft_b200_eigh(int64_t nloc, int32_t neigen, int32_t nblock, int32_t niterm
 
 // Host-only test hook (no CUDA call, like cdmft_b200_schedule_host): the restart logic of cdmft_b200_eigh (trl_solve)
 // on host vectors around the CALLER's mat-vec -- the CPU tests drive it with the oracle's H x v.  Not a product path.
-int cdmft_b200_eigh_logic_host(int64_t n, void (*matvec)(int64_t, const double *, double *, void *), void *user, int32_t neigen,
-                               int32_t nblock, int32_t nitermax, double tol, double *eig_values, double *eig_basis,
-                               int32_t *nconv, int32_t *nmatvec) {
-  if (!matvec || n < 3 || neigen < 1 || (int64_t)neigen + 1 >= n) return fail("eigh_logic_host: bad arguments");
+// Sharded runs (the gloo test): n = local length, goff = global index of the first local element, ntot = global length,
+// allreduce = in-place sum over the ranks (NULL with one rank) -- the same contract the device backend has with NCCL.
+int cdmft_b200_eigh_logic_host(int64_t n, int64_t goff, int64_t ntot, void (*matvec)(int64_t, const double *, double *, void *),
+                               void (*allreduce)(double *, int64_t, void *), void *user, int32_t neigen, int32_t nblock,
+                               int32_t nitermax, double tol, double *eig_values, double *eig_basis, int32_t *nconv,
+                               int32_t *nmatvec) {
+  if (!matvec || n < 0 || goff < 0 || ntot < 3 || n + goff > ntot || neigen < 1 || (int64_t)neigen + 1 >= ntot)
+    return fail("eigh_logic_host: bad arguments");
   int ncv = nblock > 0 ? nblock : std::max(2 * neigen, 20);
-  ncv = (int)std::min<int64_t>(std::min<int64_t>(ncv, kTrlMaxNcv), n - 1);
+  ncv = (int)std::min<int64_t>(std::min<int64_t>(ncv, kTrlMaxNcv), ntot - 1);
   if (ncv <= neigen) ncv = neigen + 1;
   if (ncv > kTrlMaxNcv) return fail("eigh_logic_host: Neigen too large");
   TrlHostBackend be;
-  be.init(n, ncv + 1, matvec, user);
+  be.init(n, goff, ncv + 1, matvec, allreduce, user);
   std::vector<double> theta;
   TrlStats st;
   const int rc = trl_solve(be, neigen, ncv, std::max(nitermax, 0), tol, theta, st);
   if (rc) return fail("eigh_logic_host: thick-restart Lanczos failed (%d)", rc);
   for (int i = 0; i < neigen; i++) {
     eig_values[i] = theta[i];
-    if (eig_basis) std::copy((const double *)be.V[i].data(), (const double *)be.V[i].data() + 2 * n, eig_basis + (size_t)2 * n * i);
+    if (eig_basis && n > 0) std::copy((const double *)be.V[i].data(), (const double *)be.V[i].data() + 2 * n, eig_basis + (size_t)2 * n * i);
   }
   if (nconv) *nconv = st.nconv;
   if (nmatvec) *nmatvec = st.nmatvec;

@@ -183,18 +183,20 @@ int trl_solve(Backend &be, int nev, int ncv, int maxrestart, double tol, std::ve
 struct TrlHostBackend {
   typedef std::complex<double> cplx;
   typedef void (*matvec_fn)(int64_t n, const double *v, double *hv, void *user);
-  int64_t n = 0;
+  typedef void (*allreduce_fn)(double *buf, int64_t count, void *user);  // in-place sum over the ranks (NULL: one rank)
+  int64_t n = 0, goff = 0;  // local length, global index of the first local element (sharded runs)
   matvec_fn mv = nullptr;
+  allreduce_fn red = nullptr;
   void *user = nullptr;
   std::vector<std::vector<cplx>> V;
   std::vector<cplx> w;
-  void init(int64_t n_, int nvec, matvec_fn f, void *u) {
-    n = n_; mv = f; user = u;
+  void init(int64_t n_, int64_t goff_, int nvec, matvec_fn f, allreduce_fn r, void *u) {
+    n = n_; goff = goff_; mv = f; red = r; user = u;
     V.assign(nvec, std::vector<cplx>((size_t)n_));
     w.assign((size_t)n_, cplx(0.0, 0.0));
   }
   int rand_w(uint64_t seed) {
-    for (int64_t i = 0; i < n; i++) w[i] = cplx(trl_rand(seed, (uint64_t)i), 0.0);
+    for (int64_t i = 0; i < n; i++) w[i] = cplx(trl_rand(seed, (uint64_t)(goff + i)), 0.0);
     return 0;
   }
   int orth_w(int nv, cplx *h, double *nrm2) {
@@ -203,10 +205,12 @@ struct TrlHostBackend {
       for (int64_t i = 0; i < n; i++) s += std::conj(V[k][i]) * w[i];
       h[k] = s;
     }
+    if (red && nv > 0) red((double *)h, 2 * (int64_t)nv, user);
     for (int k = 0; k < nv; k++)
       for (int64_t i = 0; i < n; i++) w[i] -= h[k] * V[k][i];
     double s = 0.0;
     for (int64_t i = 0; i < n; i++) s += std::norm(w[i]);
+    if (red) red(&s, 1, user);
     *nrm2 = s;
     return 0;
   }

@@ -465,23 +465,36 @@ def sp_eigh_device(neigen: int, nblock: int | None = None, nitermax: int = 512, 
 
 
 _MATVEC_FN = C.CFUNCTYPE(None, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+_ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int64, C.c_void_p)
 
 
-def eigh_logic_host(matvec, n: int, neigen: int, nblock: int | None = None, nitermax: int = 512, tol: float = 1e-18):
+def eigh_logic_host(matvec, n: int, neigen: int, nblock: int | None = None, nitermax: int = 512, tol: float = 1e-18,
+                    goff: int = 0, ntot: int | None = None, allreduce=None):
     """CPU test hook: the restart logic of `cdmft_b200_eigh` on host vectors around `matvec` (complex128[n] -> complex128[n],
-    e.g. the oracle's H x v).  Needs no GPU and computes no Hamiltonian itself.  Returns (eig_values, eig_basis [n, neigen], info)."""
+    e.g. the oracle's H x v).  Needs no GPU and computes no Hamiltonian itself.  Sharded runs: `n` local elements starting
+    at global index `goff` of `ntot`, `allreduce(array)` sums a float64 array in place over the ranks.
+    Returns (eig_values, eig_basis [n, neigen], info)."""
     def cb(nn, pv, phv, _user):
+        if nn == 0:
+            matvec(np.zeros(0, dtype=np.complex128))
+            return
         v = np.ctypeslib.as_array(pv, shape=(2 * nn,)).view(np.complex128)
         hv = np.ctypeslib.as_array(phv, shape=(2 * nn,)).view(np.complex128)
         hv[:] = matvec(v.copy())
+
+    def red(pbuf, count, _user):
+        buf = np.ctypeslib.as_array(pbuf, shape=(count,))
+        allreduce(buf)
     fn = _MATVEC_FN(cb)
+    rfn = _ALLREDUCE_FN(red) if allreduce is not None else C.cast(None, _ALLREDUCE_FN)
     w = np.zeros(neigen)
-    z = np.zeros((neigen, n), dtype=np.complex128)
+    z = np.zeros((neigen, max(n, 1)), dtype=np.complex128)
     nconv, nmv = C.c_int32(), C.c_int32()
     ncv = nblock if nblock else 10 * max(neigen, 2)
-    _chk(load_library().cdmft_b200_eigh_logic_host(C.c_int64(n), fn, None, C.c_int32(neigen), C.c_int32(ncv), C.c_int32(nitermax),
-                                                   C.c_double(tol), _ptr(w), _ptr(z), C.byref(nconv), C.byref(nmv)))
-    return w, np.ascontiguousarray(z.T), dict(nconv=nconv.value, nmatvec=nmv.value)
+    _chk(load_library().cdmft_b200_eigh_logic_host(C.c_int64(n), C.c_int64(goff), C.c_int64(n if ntot is None else ntot), fn, rfn, None,
+                                                   C.c_int32(neigen), C.c_int32(ncv), C.c_int32(nitermax), C.c_double(tol), _ptr(w),
+                                                   _ptr(z), C.byref(nconv), C.byref(nmv)))
+    return w, np.ascontiguousarray(z[:, :n].T), dict(nconv=nconv.value, nmatvec=nmv.value)
 
 
 def apply_op(isector: int, iop: int, ispin: int, pos, coef, state: np.ndarray):

@@ -182,10 +182,14 @@ int cdmft_b200_eigh(int64_t nloc, int32_t neigen, int32_t nblock, int32_t niterm
                     void *eig_basis, int32_t *nconv, int32_t *nmatvec);
 /* Host-only TEST HOOK (no CUDA call, like cdmft_b200_schedule_host): the restart logic of cdmft_b200_eigh run on host
  * vectors around the CALLER's mat-vec (complex(8)[n] -> complex(8)[n]); the CPU tests drive it with the oracle's
- * H x v.  It is not a product path and computes no Hamiltonian itself. */
-int cdmft_b200_eigh_logic_host(int64_t n, void (*matvec)(int64_t n, const double *v, double *hv, void *user), void *user,
-                               int32_t neigen, int32_t nblock, int32_t nitermax, double tol, double *eig_values,
-                               double *eig_basis, int32_t *nconv, int32_t *nmatvec);
+ * H x v.  It is not a product path and computes no Hamiltonian itself.  Sharded runs (the gloo test): n = local length,
+ * goff = global index of the first local element, ntot = global length, allreduce = in-place sum of `count` doubles over
+ * the ranks (NULL with one rank: goff = 0, ntot = n) -- the contract the device backend has with NCCL. */
+int cdmft_b200_eigh_logic_host(int64_t n, int64_t goff, int64_t ntot,
+                               void (*matvec)(int64_t n, const double *v, double *hv, void *user),
+                               void (*allreduce)(double *buf, int64_t count, void *user), void *user, int32_t neigen,
+                               int32_t nblock, int32_t nitermax, double tol, double *eig_values, double *eig_basis,
+                               int32_t *nconv, int32_t *nmatvec);
 
 /* ---- Green's function helpers (ED_GF_NORMAL.f90) --------------------------------------- */
 /* out = sum_k coef[k] * op(pos[k]) |state>  with op = c^+ (iop=+1) or c (iop=-1) acting on spin

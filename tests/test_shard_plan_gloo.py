@@ -206,3 +206,80 @@ def test_copy_engine_exchange_window_layout_gloo(world, DU, dimdw, nch):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+# ---- collective sp_eigh (P-ARPACK branch, ED_DIAG.f90:153-158): the contract cdmft_b200_eigh has with NCCL, on gloo --------
+def _eigh_worker(rank, world, port, case, nup, ndw, neigen, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cdmft_lanc_ed_b200 import ed_hamiltonian as E
+        from cdmft_lanc_ed_b200 import models
+        from oracle import edo
+        mdl = eval("models." + case)
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        orc = edo.Oracle(mdl)
+        orc.build_hv_sector(isec, edo.SPARSE_SERIAL)
+        dim = orc.dim
+        from math import comb
+        dimup, dimdw = comb(mdl.ns, nup), comb(mdl.ns, ndw)
+        nloc = sp.vecdim(dimup, dimdw, world, rank)  # this rank's Ndw shard (0 on ranks outside a shrunk communicator)
+        off = sum(sp.vecdim(dimup, dimdw, world, r) for r in range(rank))
+        sizes = [sp.vecdim(dimup, dimdw, world, r) for r in range(world)]
+
+        def matvec(vloc):  # collective: all-gather the shards, the oracle's H x v on the full vector, keep my rows
+            parts = [torch.zeros(2 * max(s, 1), dtype=torch.float64) for s in sizes]
+            mine = torch.zeros(2 * max(nloc, 1), dtype=torch.float64)
+            mine[: 2 * nloc] = torch.from_numpy(np.ascontiguousarray(vloc).view(np.float64).copy())
+            dist.all_gather(parts, mine) if len(set(t.numel() for t in parts)) == 1 else _all_gather_ragged(parts, mine, rank, world)
+            full = np.concatenate([p.numpy()[: 2 * s] for p, s in zip(parts, sizes)]).view(np.complex128)
+            return orc.hxv(np.ascontiguousarray(full))[off:off + nloc]
+
+        def allreduce(buf):
+            t = torch.from_numpy(buf)  # shares memory: the sum lands in the caller's buffer
+            dist.all_reduce(t)
+
+        w, z, info = E.eigh_logic_host(matvec, nloc, neigen, nblock=12, tol=1e-13, goff=off, ntot=dim, allreduce=allreduce)
+        # the one-process run of the same driver: same start vector (function of the global index), same control flow
+        w1, z1, info1 = E.eigh_logic_host(orc.hxv, dim, neigen, nblock=12, tol=1e-13)
+        ov = torch.zeros(2 * neigen, dtype=torch.float64)
+        for k in range(neigen):
+            d = np.vdot(z1[off:off + nloc, k], z[:, k]) if nloc else 0.0
+            ov[2 * k], ov[2 * k + 1] = float(np.real(d)), float(np.imag(d))
+        dist.all_reduce(ov)
+        overlap = [abs(complex(ov[2 * k], ov[2 * k + 1])) for k in range(neigen)]
+        q.put((rank, w, w1, info, info1, overlap, nloc))
+    finally:
+        dist.destroy_process_group()
+
+
+def _all_gather_ragged(parts, mine, rank, world):
+    for r in range(world):
+        if r == rank:
+            parts[r].copy_(mine)
+        dist.broadcast(parts[r], r)
+
+
+@pytest.mark.parametrize("world,case,nup,ndw,neigen", [(2, "hm2x2(1)", 4, 4, 2), (3, "bhz2(1)", 3, 4, 2), (4, "hm2x2(1)", 2, 1, 2), (4, "hm2x2(1)", 3, 8, 2),
+                                                       (2, "random_model(2, 2, 1, seed=15, kanamori=True)", 7, 1, 1)])
+def test_collective_sp_eigh_gloo(oracle_lib, world, case, nup, ndw, neigen):
+    """Every rank owns its Ndw shard of the Krylov basis, dot products are all-reduced, the start vector depends on the
+    global index only: eigenvalues, step counts and eigenvectors equal the one-process run (the property the SPMD GPU path
+    relies on; includes ragged shards, a shrunk communicator and DimDw < P)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + world * 10 + nup
+    procs = [ctx.Process(target=_eigh_worker, args=(r, world, port, case, nup, ndw, neigen, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, w, w1, info, info1, overlap, nloc in res:
+        assert info["nconv"] == neigen and info1["nconv"] == neigen
+        assert np.abs(w - w1).max() < 1e-11 * max(1.0, np.abs(w1).max()), (rank, w, w1)
+        assert abs(info["nmatvec"] - info1["nmatvec"]) <= 12  # rounding may move the last restart, nothing else
+        assert all(abs(o - 1.0) < 1e-7 for o in overlap), overlap
+    assert len({tuple(np.round(r[1], 12)) for r in res}) == 1  # every rank returns the same eigenvalues
