@@ -164,3 +164,31 @@ def noninteracting_half_filled(mdl, grid=None):
     m.xmu = float(best)
     m.name = mdl.name + "_U0"
     return m, best_gap
+
+
+def slater_reference(mdl):
+    """U = 0 ground state of `noninteracting_half_filled` models as a Slater determinant of the single-particle matrix the
+    reference's g0and_bath implies ([[impHloc - xmu, V], [V, Hbath]], checked against g0and_bath in the tests): returns
+    (E0, rho) with rho[a, b] = <c^+_a c_b> over the impurity orbitals of one spin, E0 = 2 * sum of the occupied levels."""
+    n, ns = mdl.nimp, mdl.ns
+    h1 = np.zeros((ns, ns), dtype=np.complex128)
+    h1[:n, :n] = _lso(mdl.imphloc) - mdl.xmu * np.eye(n)
+    for ib in range(mdl.nbath):
+        sl = slice(n * (ib + 1), n * (ib + 2))
+        h1[sl, sl] = _lso(mdl.hbath[..., ib])
+        h1[:n, sl] = np.diag(mdl.vbath[:, ib])
+        h1[sl, :n] = np.diag(mdl.vbath[:, ib])
+    e, psi = np.linalg.eigh(h1)
+    occ = psi[:, : ns // 2]
+    rho = occ[:n, :].conj() @ occ[:n, :].T  # sum_k conj(psi_k(a)) psi_k(b)
+    return 2.0 * float(e[: ns // 2].sum()), rho
+
+
+def slater_cluster_spectrum(rho):
+    """Spectrum of the impurity reduced density matrix of a Slater determinant with the same correlation matrix `rho` for
+    both spins (Peschel): all products of nu_i or 1 - nu_i over the eigenvalues nu of rho, spin up times spin down."""
+    nu = np.clip(np.linalg.eigvalsh(rho), 0.0, 1.0)
+    one = np.array([1.0])
+    for x in nu:
+        one = np.concatenate([one * x, one * (1.0 - x)])
+    return np.sort(np.outer(one, one).ravel())

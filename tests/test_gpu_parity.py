@@ -298,6 +298,35 @@ def test_u0_gimp_equals_the_references_g0and_bath(ed, case):
         assert np.abs(g - g0[ia - 1, ib - 1]).max() < 1e-6 * max(1.0, np.abs(g0[ia - 1, ib - 1]).max()), (case, ia, ib)
 
 
+@pytest.mark.parametrize("case", ["models.hm2x2(1)", "models.bhz2(1)"])
+def test_u0_observables_equal_the_slater_determinant(ed, case):
+    """Device side of tests/test_oracle_pin.py::test_u0_observables_equal_the_slater_determinant, no oracle involved: the
+    product's ground state at U = 0 must be the Slater determinant of the single-particle problem the reference's
+    g0and_bath fixes -- E0, <C^+_a C_b>, dens, docc, <E0> of lanc_local_energy, spectrum of the cluster density matrix."""
+    from tests.gf_pipeline import _lso, noninteracting_half_filled, slater_cluster_spectrum, slater_reference
+    mdl, gap = noninteracting_half_filled(eval(case))
+    assert mdl is not None and gap > 1e-2
+    e0_ref, rho = slater_reference(mdl)
+    ed.ed_set_model(mdl)
+    n = ed.build_Hv_sector(models.get_sector(mdl.ns, mdl.ns // 2, mdl.ns // 2), True)
+    vec = np.zeros(n, dtype=np.complex128)
+    e0, _, _, _ = ed.sp_lanc_eigh(vec, 512, 1e-14)
+    assert abs(e0 - e0_ref) < RTOL * max(1.0, abs(e0_ref))
+    cdm, sp = ed.density_matrix_impurity(vec, mdl.nlat, mdl.norb, mdl.nspin, 1.0)
+    nimp, norb = mdl.nimp, mdl.norb
+    tol = 1e-6  # the Lanczos stopping rule acts on the energy: the vector is converged to ~1e-7
+    for a in range(nimp):
+        for b in range(nimp):
+            assert abs(sp[a // norb, b // norb, 0, 0, a % norb, b % norb] - rho[a, b]) < tol, (a, b)
+    obs = ed.lanc_observables(vec, mdl.nlat, mdl.norb)
+    d = np.real(np.diag(rho)).reshape(mdl.nlat, mdl.norb)
+    assert np.abs(np.asarray(obs["dens"]) - 2 * d).max() < tol and np.abs(np.asarray(obs["docc"]) - d * d).max() < tol
+    assert np.abs(np.sort(np.linalg.eigvalsh(cdm)) - slater_cluster_spectrum(rho)).max() < tol
+    en = ed.lanc_local_energy(vec, mdl, 1.0)
+    assert abs(en["Eknot"] - 2.0 * np.real(np.sum(_lso(mdl.imphloc) * rho))) < tol and abs(en["Epot"]) < 1e-14
+    ed.delete_Hv_sector()
+
+
 @pytest.mark.parametrize("opts", [
     dict(),                                                    # defaults: tile-resident row pass writes, column-resident pass accumulates
     dict(tma2d=0),                                             # tiles by per-column bulk copies instead of 2-D TMA tensor copies

@@ -328,3 +328,34 @@ def _Oracle_gs(mdl, edo):
     e0, vec, _, _, _ = o.lanc_eigh(512, 1e-14)  # (a threshold below what the recurrence resolves runs 512 steps and spoils the vector)
     o.delete_hv_sector()
     return e0, vec
+
+
+@pytest.mark.parametrize("case", ["models.hm2x2(1)", "models.bhz2(1)", "models.random_model(3, 1, 1, seed=32)"])
+def test_u0_observables_equal_the_slater_determinant(oracle_lib, case):
+    """The N4 restatements (lanc_observables, lanc_local_energy, density_matrix_impurity) on the U = 0 ground state against
+    the Slater determinant of the single-particle problem that the reference's g0and_bath fixes: E0 = 2 sum of occupied
+    levels, <C^+_a C_b> = the correlation matrix, dens = 2 rho_aa, docc = rho_aa^2 (the spins factorise), the spectrum
+    of the cluster density matrix = Peschel's products of nu_i / (1 - nu_i), <E0> = 2 Re sum impHloc(a,b) rho(a,b)."""
+    from tests.gf_pipeline import noninteracting_half_filled, slater_cluster_spectrum, slater_reference
+    mdl, gap = noninteracting_half_filled(eval(case))
+    assert mdl is not None and gap > 1e-2
+    e0_ref, rho = slater_reference(mdl)
+    e0, vec = _Oracle_gs(mdl, oracle_lib)
+    isec = models.get_sector(mdl.ns, mdl.ns // 2, mdl.ns // 2)
+    # the Hamiltonian carries the Hartree-Fock constant of HFMODE only through U: none at U = 0
+    assert abs(e0 - e0_ref) < 1e-10 * max(1.0, abs(e0_ref))
+    cdm, sp = oracle_lib.Oracle(mdl).density_matrix_impurity(isec, vec, 1.0)
+    n, norb = mdl.nimp, mdl.norb
+    for a in range(n):
+        for b in range(n):
+            assert abs(sp[a // norb, b // norb, 0, 0, a % norb, b % norb] - rho[a, b]) < 2e-7, (a, b)
+    obs = oracle_lib.lanc_observables(mdl.ns, mdl.nlat, mdl.norb, isec, vec)
+    d = np.real(np.diag(rho)).reshape(mdl.nlat, mdl.norb)
+    assert np.abs(np.asarray(obs["dens"]).reshape(d.shape) - 2 * d).max() < 2e-7
+    assert np.abs(np.asarray(obs["docc"]).reshape(d.shape) - d * d).max() < 2e-7
+    assert np.abs(np.sort(np.linalg.eigvalsh(cdm)) - slater_cluster_spectrum(rho)).max() < 2e-7
+    # lanc_local_energy: <E0> = sum_ab impHloc(a,b) <c^+_a c_b> over both spins; no interaction energy at U = 0
+    from tests.gf_pipeline import _lso
+    en = oracle_lib.Oracle(mdl).lanc_local_energy(isec, vec, 1.0)
+    assert abs(en["Eknot"] - 2.0 * np.real(np.sum(_lso(mdl.imphloc) * rho))) < 2e-7
+    assert en["Epot"] == 0.0 and en["Ehartree"] == 0.0
