@@ -613,6 +613,36 @@ def test_gf_matrix_batched_channels_vs_oracle(ed, oracle_lib):
     assert np.all(Gr[np.arange(nimp), np.arange(nimp)].imag <= 1e-12)
 
 
+def test_gf_over_a_state_list_finite_temperature(ed, oracle_lib):
+    """The finite-temperature flow end to end on the device: `sp_eigh` (cdmft_b200_eigh) fills a state list -- several
+    eigenpairs of several sectors -- and build_gf_normal_states runs every channel of every state with its Boltzmann weight
+    (ED_GF_NORMAL.f90:38-106, :930-936), Matsubara and real axis.  Checked against the same orchestration served by the
+    oracle on the same states (tests/test_gf_normal_cpu.py pins that orchestration against the exact Lehmann sum)."""
+    from cdmft_lanc_ed_b200 import gf_normal
+    from tests.test_gf_normal_cpu import OracleBackend
+    mdl = models.hm2x2(1)
+    ed.ed_set_model(mdl)
+    states = []
+    for nup, ndw, neig in [(4, 4, 2), (4, 3, 1), (3, 4, 1)]:
+        isec = models.get_sector(mdl.ns, nup, ndw)
+        ed.build_Hv_sector(isec, True)
+        w, z, info = ed.sp_eigh_device(neig, tol=1e-13)
+        ed.delete_Hv_sector()
+        assert info["nconv"] == neig
+        states += [(isec, float(w[k]), np.ascontiguousarray(z[:, k])) for k in range(neig)]
+    beta = 4.0
+    wm = np.pi / beta * (2 * np.arange(1, 17) - 1)
+    wr = np.linspace(-3, 3, 9)
+    nimp = mdl.nlat * mdl.norb
+    G, Gr = gf_normal.build_gf_normal_states(nimp, states, wm, wr=wr, eps=0.05, finite_t=True, beta=beta)
+    assert gf_normal.build_gf_normal_states.last_sector_builds <= 2 * len(states)
+    Go, Gor = gf_normal.build_gf_normal_states(nimp, states, wm, wr=wr, eps=0.05, finite_t=True, beta=beta, backend=OracleBackend(mdl))
+    assert _relerr(G, Go) < RTOL and _relerr(Gr, Gor) < RTOL
+    # weights: the list minimum carries weight 1/zeta, the others exp(-beta dE)/zeta -> the spectral weight of G_aa sums to 1
+    zeta = gf_normal.zeta_function([e for _, e, _ in states], True, beta)
+    assert zeta > 1.0
+
+
 def test_density_matrices_vs_oracle(oracle_lib):
     """density_matrix_impurity (ED_OBSERVABLES.f90:465-686): the cluster density matrix (Gram matrices of the amplitude
     blocks sharing a bath configuration) and <C^+_a C_b> against the oracle's restatement of the reference loops; one rank
