@@ -125,3 +125,52 @@ def test_symmetric_two_channel_variant_and_real_axis():
     refr = _exact(mdl, None, beta, 0, zs=wr + 1j * eps)  # impGreal: the same poles and weights at w + i eps (:968-971)
     assert np.abs(G2r[0] - refr).max() < 1e-10 * np.abs(refr).max()
     assert n2 <= 2 * len(states)  # channels batched by target sector: at most two sector builds per state
+
+
+# ---- observables over a state list (cdmft_lanc_ed_b200/observables.py) against exact thermal averages -------------------
+class OracleObsBackend:
+    def __init__(self, mdl):
+        self.m = mdl
+        self.o = edo.Oracle(mdl)
+
+    def build(self, isector):
+        pass
+
+    def delete(self):
+        pass
+
+    def observables(self, isector, vec, peso):
+        return edo.lanc_observables(self.m.ns, self.m.nlat, self.m.norb, isector, vec, peso)
+
+    def local_energy(self, isector, vec, peso):
+        return self.o.lanc_local_energy(isector, vec, peso)
+
+    def density_matrices(self, isector, vec, peso):
+        return self.o.density_matrix_impurity(isector, vec, peso)
+
+
+@pytest.mark.parametrize("case", ["models.random_model(2, 1, 1, seed=24)", "models.random_model(1, 2, 1, seed=9, kanamori=True)"])
+def test_observables_over_the_state_list_against_thermal_averages(case):
+    """dens, docc, <C^+_a C_b> and the trace of the cluster density matrix summed over a complete state list with Boltzmann
+    weights = Tr(rho O) with rho = exp(-beta H)/Z from the dense Jordan-Wigner ED."""
+    from cdmft_lanc_ed_b200 import observables
+    mdl = eval(case)
+    beta = 1.3
+    states = _all_states(mdl)
+    res = observables.observables_states(mdl, states, finite_t=True, beta=beta, backend=OracleObsBackend(mdl))
+    H = jw_ed.full_hamiltonian(mdl)
+    w, U = np.linalg.eigh(H)
+    p = np.exp(-beta * (w - w[0]))
+    assert abs(res["zeta_function"] - p.sum()) < 1e-10 * p.sum()
+    rho = (U * (p / p.sum())) @ U.conj().T
+    c = jw_ed._ops(2 * mdl.ns)
+    ns, nimp, norb = mdl.ns, mdl.nimp, mdl.norb
+    for a in range(nimp):
+        nu, nd = c[a].T.conj() @ c[a], c[ns + a].T.conj() @ c[ns + a]
+        il, io = a // norb, a % norb
+        assert abs(res["dens"][il, io] - np.trace(rho @ (nu + nd)).real) < 1e-11
+        assert abs(res["docc"][il, io] - np.trace(rho @ nu @ nd).real) < 1e-11
+        for b in range(nimp):
+            ev = np.trace(rho @ c[a].T.conj() @ c[b])
+            assert abs(res["single_particle_density_matrix"][il, b // norb, 0, 0, io, b % norb] - ev) < 1e-11
+    assert abs(np.trace(res["cluster_density_matrix"]).real - 1.0) < 1e-11

@@ -641,6 +641,15 @@ def test_gf_over_a_state_list_finite_temperature(ed, oracle_lib):
     # weights: the list minimum carries weight 1/zeta, the others exp(-beta dE)/zeta -> the spectral weight of G_aa sums to 1
     zeta = gf_normal.zeta_function([e for _, e, _ in states], True, beta)
     assert zeta > 1.0
+    # the same state list through the observables loops (lanc_observables, lanc_local_energy, density_matrix_impurity)
+    from cdmft_lanc_ed_b200 import observables
+    from tests.test_gf_normal_cpu import OracleObsBackend
+    got = observables.observables_states(mdl, states, finite_t=True, beta=beta)
+    ref = observables.observables_states(mdl, states, finite_t=True, beta=beta, backend=OracleObsBackend(mdl))
+    assert abs(got["zeta_function"] - zeta) < 1e-14
+    for k in ("dens", "docc", "s2tot", "n2", "Eknot", "Epot", "Ehartree", "cluster_density_matrix", "single_particle_density_matrix"):
+        assert np.abs(np.asarray(got[k]) - np.asarray(ref[k])).max() < 1e-11 * max(1.0, np.abs(np.asarray(ref[k])).max()), k
+    assert abs(np.trace(got["cluster_density_matrix"]).real - 1.0) < 1e-11
 
 
 def test_density_matrices_vs_oracle(oracle_lib):
