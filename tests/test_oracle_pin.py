@@ -359,3 +359,30 @@ def test_u0_observables_equal_the_slater_determinant(oracle_lib, case):
     en = oracle_lib.Oracle(mdl).lanc_local_energy(isec, vec, 1.0)
     assert abs(en["Eknot"] - 2.0 * np.real(np.sum(_lso(mdl.imphloc) * rho))) < 2e-7
     assert en["Epot"] == 0.0 and en["Ehartree"] == 0.0
+
+
+def test_one_orbital_density_matrix_against_the_reference_drivers_benchmark(oracle_lib):
+    """The reference's only in-tree self-check (drivers/cdn_hm_2dsquare.f90:443-464, `one_orb_benchmark`, Eq. 4 of
+    Mod. Phys. Lett. B 27 (2013) 05): the reduced density matrix of ONE impurity orbital, obtained by tracing the cluster
+    density matrix over the other orbitals, has the diagonal (1 - n_up - n_dw + docc, n_up - docc, n_dw - docc, docc).
+    Ties the labelling of cluster_density_matrix (IimpUp + 2^Nimp IimpDw) to the observables of lanc_observables."""
+    for mdl, (nup, ndw) in [(models.hm2x2(1), (4, 3)), (models.random_model(2, 2, 1, nspin=2, seed=12), (3, 5)),
+                            (models.bhz2(1, kanamori=True), (4, 4))]:
+        ns, nimp, norb = mdl.ns, mdl.nimp, mdl.norb
+        isec = models.get_sector(ns, nup, ndw)
+        orc = oracle_lib.Oracle(mdl)
+        rng = np.random.default_rng(77)
+        dim = orc.get_dim(isec)[0]
+        vec = rng.normal(size=dim) + 1j * rng.normal(size=dim)
+        vec /= np.linalg.norm(vec)
+        cdm, _ = orc.density_matrix_impurity(isec, vec, 1.0)
+        obs = oracle_lib.lanc_observables(ns, mdl.nlat, norb, isec, vec)
+        p = np.real(np.diag(cdm))
+        ni = 1 << nimp
+        iu, idw = np.arange(ni * ni) % ni, np.arange(ni * ni) // ni
+        for a in range(nimp):
+            il, io = a // norb, a % norb
+            nu, nd, d = obs["dens_up"][il][io], obs["dens_dw"][il][io], obs["docc"][il][io]
+            bu, bd = (iu >> a) & 1, (idw >> a) & 1
+            one_orb = [p[(bu == x) & (bd == y)].sum() for (x, y) in ((0, 0), (1, 0), (0, 1), (1, 1))]
+            assert np.abs(np.array(one_orb) - np.array([1 - nu - nd + d, nu - d, nd - d, d])).max() < 1e-13, (mdl.name, a)
