@@ -298,6 +298,24 @@ def test_u0_gimp_equals_the_references_g0and_bath(ed, case):
         assert np.abs(g - g0[ia - 1, ib - 1]).max() < 1e-6 * max(1.0, np.abs(g0[ia - 1, ib - 1]).max()), (case, ia, ib)
 
 
+@pytest.mark.parametrize("u,t", [(2.0, 0.25), (4.0, 1.0)])
+def test_hubbard_dimer_closed_form(ed, u, t):
+    """Literature anchor, no oracle involved: the two-site Hubbard model (bath switched off) on the device -- dense Hmat of
+    build_Hv_sector(isector, Hmat) and the device-resident sp_eigh -- against E0 = U/2 - sqrt(U^2/4 + 4t^2) (singlet, sector
+    (1,1)); HFMODE adds -U/2 in that sector (sparse/H_local.f90:61-77)."""
+    from tests.gf_pipeline import hubbard_dimer
+    for hf in (False, True):
+        mdl = hubbard_dimer(u, t, hf)
+        ed.ed_set_model(mdl)
+        exact = u / 2 - np.sqrt(u * u / 4 + 4 * t * t) + (-u / 2 if hf else 0.0)
+        for sparse in (True, False):
+            ed.build_Hv_sector(models.get_sector(mdl.ns, 1, 1), sparse)
+            w = np.linalg.eigvalsh(ed.build_Hmat())
+            we, _, info = ed.sp_eigh_device(1, tol=1e-13)
+            ed.delete_Hv_sector()
+            assert abs(w[0] - exact) < 1e-12 and abs(we[0] - exact) < 1e-11 and info["nconv"] == 1, (u, t, hf, sparse)
+
+
 @pytest.mark.parametrize("case", ["models.hm2x2(1)", "models.bhz2(1)"])
 def test_u0_observables_equal_the_slater_determinant(ed, case):
     """Device side of tests/test_oracle_pin.py::test_u0_observables_equal_the_slater_determinant, no oracle involved: the

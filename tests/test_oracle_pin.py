@@ -386,3 +386,19 @@ def test_one_orbital_density_matrix_against_the_reference_drivers_benchmark(orac
             bu, bd = (iu >> a) & 1, (idw >> a) & 1
             one_orb = [p[(bu == x) & (bd == y)].sum() for (x, y) in ((0, 0), (1, 0), (0, 1), (1, 1))]
             assert np.abs(np.array(one_orb) - np.array([1 - nu - nd + d, nu - d, nd - d, d])).max() < 1e-13, (mdl.name, a)
+
+
+@pytest.mark.parametrize("u,t", [(2.0, 0.25), (4.0, 1.0), (0.5, 1.3)])
+def test_hubbard_dimer_closed_form(oracle_lib, u, t):
+    """A literature anchor that owes nothing to this repository: the two-site Hubbard model (bath switched off) has the
+    singlet ground-state energy U/2 - sqrt(U^2/4 + 4t^2) in the sector (1,1); with HFMODE the Hamiltonian carries
+    -U/2 (n_up + n_dw) + U/4 per site (sparse/H_local.f90:61-77), i.e. -U/2 in that sector.  The triplet sits at 0 (-U/2)."""
+    from tests.gf_pipeline import hubbard_dimer
+    for hf in (False, True):
+        mdl = hubbard_dimer(u, t, hf)
+        orc = oracle_lib.Oracle(mdl)
+        w = np.linalg.eigvalsh(orc.dense_hmat(models.get_sector(mdl.ns, 1, 1)))
+        shift = -u / 2 if hf else 0.0
+        assert abs(w[0] - (u / 2 - np.sqrt(u * u / 4 + 4 * t * t) + shift)) < 1e-12
+        wt = np.linalg.eigvalsh(orc.dense_hmat(models.get_sector(mdl.ns, 2, 0)))  # both electrons up: the triplet
+        assert abs(wt[0] - shift) < 1e-12
