@@ -40,7 +40,7 @@ def _check_pairs(hxv, w, z, ref, neigen, tol_e=1e-10):
     assert np.abs(z.conj().T @ z - np.eye(neigen)).max() < 1e-10
 
 
-@pytest.mark.parametrize("case", [("hm2x2(1)", (4, 4), 1, None), ("hm2x2(1)", (4, 4), 3, 12), ("bhz2(1)", (3, 3), 4, None),
+@pytest.mark.parametrize("case", [("hm2x2(1)", (4, 4), 1, None), ("hm2x2(1)", (3, 2), 3, 12), ("bhz2(1)", (3, 3), 4, None),
                                   ("random_model(2, 2, 1, seed=8)", (3, 4), 2, 3), ("bhz2(1, kanamori=True)", (3, 3), 3, 20)])
 def test_thick_restart_logic_with_oracle_matvec(case):
     """nev lowest eigenpairs of real, complex and Kanamori sectors vs a dense diagonalisation of the oracle's Hmat;
@@ -70,7 +70,7 @@ def test_thick_restart_logic_with_oracle_matvec(case):
 def test_thick_restart_default_tolerance_terminates():
     """The reference passes lanc_tolerance = 1e-18 (ED_INPUT_VARS.f90:178): it must act as machine precision, not run forever."""
     mdl = models.hm2x2(1)
-    isec = models.get_sector(mdl.ns, 4, 4)
+    isec = models.get_sector(mdl.ns, 3, 3)
     orc = edo.Oracle(mdl)
     ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
     orc.build_hv_sector(isec, edo.SPARSE_SERIAL)
