@@ -174,3 +174,65 @@ def test_observables_over_the_state_list_against_thermal_averages(case):
             ev = np.trace(rho @ c[a].T.conj() @ c[b])
             assert abs(res["single_particle_density_matrix"][il, b // norb, 0, 0, io, b % norb] - ev) < 1e-11
     assert abs(np.trace(res["cluster_density_matrix"]).real - 1.0) < 1e-11
+
+
+# ---- the diagonalisation step (cdmft_lanc_ed_b200/ed_diag.py): sector loop + state-list rules of ED_DIAG.f90 -------------
+class OracleDiagBackend:
+    def __init__(self, mdl):
+        self.m, self.o, self.isec = mdl, edo.Oracle(mdl), None
+
+    def build(self, isector):
+        self.o.build_hv_sector(isector, edo.SPARSE_SERIAL)
+        self.isec = isector
+        return self.o.dim
+
+    def delete(self):
+        self.o.delete_hv_sector()
+
+    def dense_hmat(self):
+        return edo.Oracle(self.m).dense_hmat(self.isec)
+
+    def sp_eigh(self, neigen, nblock, nitermax, tol):
+        w, z, _ = E.eigh_logic_host(self.o.hxv, self.o.dim, neigen, nblock=nblock, nitermax=nitermax, tol=tol)
+        return w, z
+
+    def sp_lanc_eigh(self, n, nitermax, tol):
+        e0, vec, _, _, _ = self.o.lanc_eigh(nitermax, max(tol, 1e-14))
+        return np.array([e0]), vec.reshape(-1, 1)
+
+
+def test_ed_diag_state_list_rules():
+    """ed_diag_c + ed_post_diag: T = 0 keeps exactly the (degenerate) ground states of the whole Fock space; at finite
+    temperature the list converges, through the reference's own adaptation of neigen_sector / lanc_nstates_total, to the
+    lowest states of the exact spectrum up to the Boltzmann cut-off.  Krylov branch (sp_eigh logic / sp_lanc_eigh with the
+    oracle's mat-vec) and LAPACK branch (dense Hmat) both exercised via lanc_dim_threshold."""
+    from cdmft_lanc_ed_b200 import ed_diag
+    mdl = models.random_model(3, 1, 1, seed=5)  # Ns = 6, sectors up to 400 states
+    exact = np.sort(np.concatenate([np.linalg.eigvalsh(edo.Oracle(mdl).dense_hmat(i)) for i in range(1, (mdl.ns + 1) ** 2 + 1)]))
+    be = OracleDiagBackend(mdl)
+    # T = 0, default method, Krylov solver for every sector above 30 states
+    p0 = ed_diag.DiagParams(finite_t=False, lanc_nstates_total=1, lanc_dim_threshold=30, lanc_tolerance=1e-13)
+    st = ed_diag.ed_diag(mdl.ns, p0, backend=be)
+    st, zeta, numgs = ed_diag.ed_post_diag(mdl.ns, st, p0)
+    ngs = int(np.sum(exact - exact[0] <= 1e-9))
+    assert len(st) == ngs == numgs and zeta == float(ngs)
+    assert all(abs(e - exact[0]) < 1e-9 for _, e, _ in st)
+    for isec, e, v in st:  # eigenpairs of their sectors
+        h = edo.Oracle(mdl).dense_hmat(isec)
+        assert np.linalg.norm(h @ v - e * v) < 1e-7
+    # T = 0 with the plain Lanczos method: same ground-state energy
+    pl = ed_diag.DiagParams(finite_t=False, lanc_method="lanczos", lanc_nstates_total=1, lanc_dim_threshold=30)
+    sl = ed_diag.ed_diag(mdl.ns, pl, backend=be)
+    assert abs(sl[0][1] - exact[0]) < 1e-9
+    # finite temperature: iterate diag / post_diag as the DMFT loop does; the list must settle on the exact low-energy spectrum
+    beta = 30.0  # cut-off 1e-4 -> levels within 0.307 of the ground state: 7 states; the list grows by lanc_nstates_step per call
+    pf = ed_diag.DiagParams(finite_t=True, beta=beta, lanc_nstates_sector=2, lanc_nstates_total=4, lanc_nstates_step=2,
+                            lanc_dim_threshold=30, lanc_tolerance=1e-13, cutoff=1e-4)
+    for _ in range(8):
+        st = ed_diag.ed_diag(mdl.ns, pf, backend=be)
+        st, zeta, numgs = ed_diag.ed_post_diag(mdl.ns, st, pf)
+    want = exact[np.exp(-beta * (exact - exact[0])) > pf.cutoff]
+    got = np.array([e for _, e, _ in st])
+    assert len(got) == len(want) and np.abs(got - want).max() < 1e-8, (got, want)
+    # the reference sums zeta_function BEFORE it trims the list (:355-366 vs :455-469): the trimmed states are still in it
+    assert 0.0 <= zeta - np.exp(-beta * (want - want[0])).sum() < 10 * pf.cutoff

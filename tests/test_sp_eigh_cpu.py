@@ -102,3 +102,26 @@ def test_thick_restart_invariant_subspace_and_restart_cap():
 def test_thick_restart_rejects_tiny_spaces():
     with pytest.raises(E.EdB200Error):
         E.eigh_logic_host(lambda v: v, 3, 2)
+
+
+def test_thick_restart_one_sided_spectrum():
+    """A sector whose whole spectrum lies on one side of zero (|alfa| >> beta in every Lanczos step): the case in which one
+    classical Gram-Schmidt pass per step lets the orthogonality error compound (an earlier version lost the basis after the
+    first restart here and returned -128 for a spectrum in [-10.1, -3.0]).  Found by the ed_diag test; kept as a regression."""
+    mdl = models.random_model(3, 1, 1, seed=5)
+    isec = models.get_sector(mdl.ns, 5, 5)  # Dim 36
+    orc = edo.Oracle(mdl)
+    ref = np.linalg.eigvalsh(orc.dense_hmat(isec))
+    assert ref[-1] < 0
+    orc.build_hv_sector(isec, edo.SPARSE_SERIAL)
+    for nblock in (20, 10, 35, 3):
+        w, z, info = E.eigh_logic_host(orc.hxv, orc.dim, 2, nblock=nblock, nitermax=2000, tol=1e-13)
+        assert info["nconv"] == 2, (nblock, info)
+        _check_pairs(orc.hxv, w, z, ref, 2, tol_e=1e-11)
+    orc.delete_hv_sector()
+    # the same with a shifted dense operator far from zero: H - 1000
+    rng = np.random.default_rng(11)
+    a = rng.normal(size=(120, 120))
+    a = (a + a.T) / 2 - 1000.0 * np.eye(120)
+    w, z, info = E.eigh_logic_host(lambda v: a @ v, 120, 3, nblock=16, nitermax=2000, tol=1e-14)
+    _check_pairs(lambda v: a @ v, w, z, np.linalg.eigvalsh(a), 3, tol_e=1e-12)
