@@ -97,7 +97,7 @@ struct TrlStats {
 // ncv = size of the Krylov basis between restarts (nev < ncv <= kTrlMaxNcv, ncv < dimension of the space),
 // maxrestart = ARPACK's mxiter, tol = ARPACK's tol: a pair counts as converged when its error bound
 // |beta_m y_{m,i}| <= max(tol, eps) * max(eps^(2/3), |theta_i|)  (dsconv / znaup2's test; bounds below eps cannot be
-// resolved from a dense solve of the projected problem, so the reference's default 1e-18 acts as eps).
+// resolved from a dense solve of the projected problem, so the reference's default 1e-18 acts as eps), or <= eps * |H|.
 template <class Backend>
 int trl_solve(Backend &be, int nev, int ncv, int maxrestart, double tol, std::vector<double> &theta, TrlStats &st) {
   typedef std::complex<double> cplx;
@@ -160,7 +160,9 @@ int trl_solve(Backend &be, int nev, int ncv, int maxrestart, double tol, std::ve
     jacobi_eigh(m, T, w, Y);
     int nconv = 0;
     for (int i = 0; i < nev; i++)
-      if (std::fabs(beta_last * Y[(size_t)(m - 1) * m + i]) <= tol_eff * std::max(eps23, std::fabs(w[i]))) nconv++;
+      // ARPACK's test, with the floor eps * |H| (anorm): a level that happens to sit at |theta| << |H| cannot be resolved
+      // below the rounding of the products however long the iteration runs
+      if (std::fabs(beta_last * Y[(size_t)(m - 1) * m + i]) <= std::max(tol_eff * std::max(eps23, std::fabs(w[i])), eps * anorm)) nconv++;
     st.nconv = nconv;
     st.nrestart = restart;
     const bool done = nconv >= nev || restart >= maxrestart;
