@@ -58,11 +58,19 @@ class FakeDevice:
     def lanc_local_energy(self, vec, mdl, peso=1.0):
         return self.o.lanc_local_energy(self.isec, vec, peso)
 
+    def build_Hmat(self):
+        isec = self.isec
+        self.o.delete_hv_sector()  # the oracle assembles the dense matrix without an active sector
+        h = self.o.dense_hmat(isec)
+        self.o.build_hv_sector(isec, edo.SPARSE_SERIAL)
+        return h
+
 
 def test_rehearse_u0_and_state_list_bodies(monkeypatch, oracle_lib):
     fake = FakeDevice()
     T.test_u0_gimp_equals_the_references_g0and_bath(fake, "models.hm2x2(1)")
     T.test_u0_observables_equal_the_slater_determinant(fake, "models.bhz2(1)")
+    T.test_hubbard_dimer_closed_form(fake, 2.0, 0.25)
     monkeypatch.setattr(gf_normal, "E", fake)
     monkeypatch.setattr(observables, "E", fake)
     T.test_gf_over_a_state_list_finite_temperature(fake, oracle_lib)
