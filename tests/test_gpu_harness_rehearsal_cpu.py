@@ -7,7 +7,7 @@ from math import comb
 import numpy as np
 
 from cdmft_lanc_ed_b200 import ed_hamiltonian as E
-from cdmft_lanc_ed_b200 import gf_normal, observables
+from cdmft_lanc_ed_b200 import ed_diag, gf_normal, observables
 from oracle import edo
 import tests.test_gpu_parity as T
 
@@ -74,3 +74,5 @@ def test_rehearse_u0_and_state_list_bodies(monkeypatch, oracle_lib):
     monkeypatch.setattr(gf_normal, "E", fake)
     monkeypatch.setattr(observables, "E", fake)
     T.test_gf_over_a_state_list_finite_temperature(fake, oracle_lib)
+    monkeypatch.setattr(ed_diag, "E", fake)
+    T.test_ed_diag_sector_loop_on_the_device(fake, oracle_lib)

@@ -673,6 +673,33 @@ def test_gf_over_a_state_list_finite_temperature(ed, oracle_lib):
     assert abs(np.trace(got["cluster_density_matrix"]).real - 1.0) < 1e-11
 
 
+def test_ed_diag_sector_loop_on_the_device(ed, oracle_lib):
+    """ed_diag_c through the product: the sector loop of cdmft_lanc_ed_b200/ed_diag.py with the device-resident sp_eigh for
+    large sectors and the dense Hmat + LAPACK branch for small ones, state-list rules included -- against the same loop
+    served by the oracle (tests/test_gf_normal_cpu.py pins that loop against the exact spectrum)."""
+    from cdmft_lanc_ed_b200 import ed_diag
+    from tests.test_gf_normal_cpu import OracleDiagBackend
+    mdl = models.hm2x2(1)
+    ed.ed_set_model(mdl)
+    sectors = [models.get_sector(mdl.ns, a, b) for a in (3, 4, 5) for b in (3, 4, 5)] + [models.get_sector(mdl.ns, 1, 1), models.get_sector(mdl.ns, 7, 7)]
+    for kw in (dict(finite_t=False, lanc_nstates_total=1), dict(finite_t=True, beta=5.0, lanc_nstates_total=6, cutoff=1e-6),
+               dict(finite_t=False, lanc_nstates_total=1, lanc_method="lanczos", lanc_tolerance=1e-14)):
+        kw.setdefault("lanc_tolerance", 1e-13)
+        got = ed_diag.ed_diag(mdl.ns, ed_diag.DiagParams(**kw), sectors=sectors)
+        ref = ed_diag.ed_diag(mdl.ns, ed_diag.DiagParams(**kw), sectors=sectors, backend=OracleDiagBackend(mdl))
+        if not kw["finite_t"]:  # (at finite T a multiplet spread over several sectors may be cut by the list size: which member stays is rounding)
+            assert [s[0] for s in got] == [s[0] for s in ref], kw
+        assert len(got) == len(ref)
+        assert np.abs(np.array([s[1] for s in got]) - np.array([s[1] for s in ref])).max() < 1e-9
+        for isec, e, v in got:  # eigenpairs, checked with the oracle's mat-vec
+            orc = oracle_lib.Oracle(mdl)
+            orc.build_hv_sector(isec, oracle_lib.SPARSE_SERIAL)
+            assert np.linalg.norm(orc.hxv(v) - e * v) < 1e-6
+            orc.delete_hv_sector()
+        st, zeta, numgs = ed_diag.ed_post_diag(mdl.ns, got, ed_diag.DiagParams(**kw))
+        assert numgs >= 1 and zeta >= 1.0
+
+
 def test_density_matrices_vs_oracle(oracle_lib):
     """density_matrix_impurity (ED_OBSERVABLES.f90:465-686): the cluster density matrix (Gram matrices of the amplitude
     blocks sharing a bath configuration) and <C^+_a C_b> against the oracle's restatement of the reference loops; one rank
