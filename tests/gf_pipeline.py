@@ -197,11 +197,12 @@ def slater_cluster_spectrum(rho):
 def hubbard_dimer(u, t, hfmode):
     """Two-site Hubbard model as an impurity model whose bath is switched off (V = 0, bath levels at +10): the textbook case
     with the closed-form singlet ground state E0 = U/2 - sqrt(U^2/4 + 4 t^2) (half filling, no chemical potential)."""
-    m = models.hubbard_cluster(2, 1, 1, ts=t, uloc=u)
+    m = models.hubbard_cluster(2, 1, 3, ts=t, uloc=u)  # Ns = 8: sector (1,1) has the 8 x 8 layout the other tiny-sector tests use
     m.vbath = np.zeros_like(m.vbath)
     m.hbath = np.asfortranarray(m.hbath * 0)
-    for a in range(2):
-        m.hbath[a, a, 0, 0, 0, 0, 0] = 10.0
+    for ib in range(3):
+        for a in range(2):
+            m.hbath[a, a, 0, 0, 0, 0, ib] = 10.0 + ib
     m.hfmode = hfmode
     m.xmu = 0.0
     m.name = f"dimer_U{u}_t{t}"
